@@ -1,0 +1,24 @@
+"""ctypes loader for libacp_infer.so (the C-ABI boundary, include/acp_infer.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``make -C agentcontrolplane_b200/csrc``).
+There is no fallback: if the shared object is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libacp_infer.so")
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the CUDA engine)")
+        _lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    return _lib

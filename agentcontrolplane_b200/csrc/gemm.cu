@@ -1,0 +1,132 @@
+// gemm.cu — host side of the tcgen05 GEMM: TMA descriptor construction and launch dispatch.
+#include "gemm.h"
+#include "gemm_tcgen05.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace acp {
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int tma_init() {
+  static std::once_flag once;
+  static int rc = 0;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      fprintf(stderr, "[acp_infer] cuTensorMapEncodeTiled unavailable: %s\n",
+              cudaGetErrorString(e));
+      rc = -5;
+      return;
+    }
+    g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  });
+  return rc;
+}
+
+int tma_encode_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                       uint32_t box_rows) {
+  if (tma_init() != 0) return -5;
+  // innermost dimension first
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};  // bytes, dims 1..rank-1
+  cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                        gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[acp_infer] cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%u\n",
+            (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return -5;
+  }
+  return 0;
+}
+
+int tma_make_weight(TmaMaps* m, const void* base, uint64_t rows, uint64_t cols) {
+  int rc = tma_encode_2d_bf16(&m->w, base, rows, cols, GEMM_BM);
+  m->has_w = (rc == 0);
+  return rc;
+}
+int tma_make_act(TmaMaps* m, const void* base, uint64_t rows, uint64_t cols) {
+  for (int i = 0; i < 5; ++i) {
+    uint32_t box = 16u << i;
+    // a box may not exceed the tensor: clamp (small buffers never use the large tiles)
+    if (box > rows) box = (uint32_t)rows;
+    int rc = tma_encode_2d_bf16(&m->x[i], base, rows, cols, box);
+    if (rc != 0) return rc;
+  }
+  m->has_x = true;
+  return 0;
+}
+
+int gemm_pick_bn(int N) {
+  if (N <= 16) return 16;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  return 256;
+}
+
+template <int BN, int EPI>
+static int launch_one(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t stream) {
+  GemmArgs a;
+  a.M = g.M; a.N = g.N; a.K = g.K; a.splits = g.splits; a.ld = g.ld; a.n_cap = g.n_cap;
+  a.out = g.out; a.amax_val = g.amax_val; a.amax_idx = g.amax_idx; a.n_dev = g.n_dev;
+  dim3 grid((g.M + GEMM_BM - 1) / GEMM_BM, (g.N + BN - 1) / BN, g.splits);
+  gemm_wx_kernel<BN, EPI><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(*g.w, tx, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[acp_infer] gemm launch failed BN=%d EPI=%d: %s\n", BN, EPI,
+            cudaGetErrorString(e));
+    return -5;
+  }
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t stream) {
+  switch (g.epi) {
+    case EPI_BF16: return launch_one<BN, EPI_BF16>(g, tx, stream);
+    case EPI_F32: return launch_one<BN, EPI_F32>(g, tx, stream);
+    case EPI_ARGMAX: return launch_one<BN, EPI_ARGMAX>(g, tx, stream);
+  }
+  return -1;
+}
+
+int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
+  if (g.N <= 0 || g.M <= 0) return 0;
+  if (g.epi != EPI_F32 && g.splits != 1) return -1;
+  const int bn = g.bn_override ? g.bn_override : gemm_pick_bn(g.N);
+  switch (bn) {
+    case 16: return launch_bn<16>(g, g.x->x[0], stream);
+    case 32: return launch_bn<32>(g, g.x->x[1], stream);
+    case 64: return launch_bn<64>(g, g.x->x[2], stream);
+    case 128: return launch_bn<128>(g, g.x->x[3], stream);
+    case 256: return launch_bn<256>(g, g.x->x[4], stream);
+  }
+  return -1;
+}
+
+template <int BN, int EPI>
+static int set_attr() {
+  cudaError_t e = cudaFuncSetAttribute(gemm_wx_kernel<BN, EPI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GemmCfg<BN>::kSmemBytes);
+  return e == cudaSuccess ? 0 : -5;
+}
+template <int BN>
+static int set_attr_bn() {
+  return set_attr<BN, EPI_BF16>() | set_attr<BN, EPI_F32>() | set_attr<BN, EPI_ARGMAX>();
+}
+int gemm_setup_attributes() {
+  int rc = set_attr_bn<16>() | set_attr_bn<32>() | set_attr_bn<64>() | set_attr_bn<128>() |
+           set_attr_bn<256>();
+  if (rc != 0) fprintf(stderr, "[acp_infer] cudaFuncSetAttribute(max dyn smem) failed\n");
+  return rc;
+}
+
+}  // namespace acp

@@ -1,0 +1,41 @@
+// gemm.h — host interface of the tcgen05 GEMM (see gemm_tcgen05.cuh for the kernel).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace acp {
+
+// TMA descriptors of one bf16 [rows][cols] row-major matrix, one per supported N-tile.
+// idx 0..4 <-> box rows 16, 32, 64, 128, 256; `w` is the 128-row box used for weights.
+struct TmaMaps {
+  CUtensorMap w;       // box {64, 128}
+  CUtensorMap x[5];    // box {64, 16 << i}
+  bool has_w = false, has_x = false;
+};
+
+int tma_init();  // resolves cuTensorMapEncodeTiled through cudart; 0 on success
+int tma_encode_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                       uint32_t box_rows);
+int tma_make_weight(TmaMaps* m, const void* base, uint64_t rows, uint64_t cols);
+int tma_make_act(TmaMaps* m, const void* base, uint64_t rows, uint64_t cols);
+
+struct GemmLaunch {
+  const CUtensorMap* w = nullptr;  // weight map (box 128 rows)
+  const TmaMaps* x = nullptr;      // activation maps
+  int M = 0, N = 0, K = 0;
+  int splits = 1;
+  int epi = 0;          // GemmEpi
+  int ld = 0;           // output leading dim
+  int n_cap = 0;        // partial-plane row capacity
+  void* out = nullptr;
+  float* amax_val = nullptr;
+  int* amax_idx = nullptr;
+  const int* n_dev = nullptr;
+  int bn_override = 0;  // 0 = pick from N
+};
+int gemm_pick_bn(int N);
+int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
+int gemm_setup_attributes();  // cudaFuncSetAttribute for every instantiation (once per device)
+
+}  // namespace acp

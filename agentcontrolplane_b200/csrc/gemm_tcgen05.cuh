@@ -1,0 +1,229 @@
+// gemm_tcgen05.cuh — the one dense-contraction kernel of the decode engine.
+//
+//   out[n][m] = sum_k W[m][k] * X[n][k]          (W: [M][K] bf16, X: [N][K] bf16, both K-major)
+//
+// "Swap-AB" orientation: the WEIGHT matrix is the UMMA A operand (M = 128 output features
+// per tile = 128 TMEM lanes) and the ACTIVATIONS are the B operand (N = sequences/tokens,
+// 16..256 per tile = TMEM columns).  Decode batches (N = 16..256 live sequences) therefore
+// fill a full-rate M=128 MMA while streaming every weight byte exactly once from HBM; prefill
+// uses the same kernel with N tiles of 256 tokens.
+//
+// Pipeline (warp-specialised, one CTA per (m-tile, n-tile, k-split)):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d W-tile {64 x 128} + X-tile {64 x BN},
+//               128-byte swizzle, into a STAGES-deep shared-memory ring (full/empty mbarriers)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per 64-wide k-block),
+//               tcgen05.commit releases ring slots and finally signals the epilogue
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (lane quarter = warp_id % 4) -> registers ->
+//               bf16 / fp32-partial / fused arg-max store
+//
+// Split-K: grid.z splits the k-block range; partials are written as fp32 [split][N][M] and are
+// summed IN FIXED ORDER by the consumer kernel (rope / add+rmsnorm / swiglu), which keeps the
+// result bit-reproducible run to run (no atomics).
+//
+// Reference boundary: this replaces the remote model behind
+// acp/internal/llmclient/langchaingo_client.go:102 (GenerateContent); see DESIGN.md.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+
+namespace acp {
+
+constexpr int GEMM_BM = 128;  // UMMA M (weight rows per tile)
+constexpr int GEMM_BK = 64;   // bf16 elements per k-block (= one 128-byte swizzle row)
+constexpr int GEMM_THREADS = 192;
+
+enum GemmEpi : int {
+  EPI_BF16 = 0,     // out_bf16[n*ld + m]
+  EPI_F32 = 1,      // out_f32[(split*n_cap + n)*ld + m]      (split-K partials, logits)
+  EPI_ARGMAX = 2,   // per (n, m-tile): max value + lowest index; optional fp32 logits
+};
+
+struct GemmArgs {
+  int M;         // rows of W (output features)
+  int N;         // valid activation rows
+  int K;
+  int splits;    // == gridDim.z
+  int ld;        // output leading dimension (elements)
+  int n_cap;     // row capacity of one split-K partial plane
+  void* out;     // bf16* or float* (may be null for EPI_ARGMAX)
+  float* amax_val;   // EPI_ARGMAX: [N][m_tiles]
+  int* amax_idx;     // EPI_ARGMAX: [N][m_tiles]
+  const int* n_dev;  // optional device scalar overriding N (CUDA-graph replay with varying batch)
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN <= 64) ? 4 : (BN == 128 ? 5 : 4);
+  static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;  // 16 KiB
+  static constexpr int kBBytes = BN * GEMM_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+               GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atom (8 rows x 128 B).
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GEMM_BM;
+  const int n0 = blockIdx.y * BN;
+  const int split = blockIdx.z;
+  const int nkb_total = (args.K + GEMM_BK - 1) / GEMM_BK;
+  const int kb_begin = (int)(((long long)nkb_total * split) / args.splits);
+  const int kb_end = (int)(((long long)nkb_total * (split + 1)) / args.splits);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * Cfg::kStageBytes;
+        uint8_t* b_dst = a_dst + Cfg::kABytes;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        const int kcoord = (kb_begin + kb) * GEMM_BK;
+        // weights are read once per step: evict-first; activations are re-read by every m-tile
+        tma_load_2d(a_dst, &tmap_w, &full_bar[s], kcoord, m0, kEvictFirst);
+        tma_load_2d(b_dst, &tmap_x, &full_bar[s], kcoord, n0, kEvictLast);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t b_addr = a_addr + Cfg::kABytes;
+        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+        const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          // advancing 16 bf16 (32 bytes) along K inside the swizzle atom = +2 in the
+          // (addr >> 4) start-address field
+          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read smem
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps 2..5 =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+    int n_valid = args.n_dev ? *args.n_dev : args.N;
+    if (nkb > 0) {
+      mbar_wait(accum_bar, 0);
+      tcgen05_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t r[16];
+      if (nkb > 0) {
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+      if constexpr (EPI == EPI_BF16) {
+        __nv_bfloat16* out = (__nv_bfloat16*)args.out;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c + j;
+          if (n < n_valid && m < args.M)
+            out[(size_t)n * args.ld + m] = __float2bfloat16_rn(__uint_as_float(r[j]));
+        }
+      } else if constexpr (EPI == EPI_F32) {
+        float* out = (float*)args.out;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c + j;
+          if (n < n_valid && m < args.M)
+            out[((size_t)split * args.n_cap + n) * args.ld + m] = __uint_as_float(r[j]);
+        }
+      } else {  // EPI_ARGMAX
+        float* out = (float*)args.out;
+        float* red_v = (float*)(smem);  // ring buffers are idle now: reuse [4][16] floats + ints
+        int* red_i = (int*)(smem + 4 * 16 * sizeof(float));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c + j;
+          float v = (m < args.M) ? __uint_as_float(r[j]) : -INFINITY;
+          int idx = m;
+          if (out != nullptr && n < n_valid && m < args.M) out[(size_t)n * args.ld + m] = v;
+          // warp arg-max with lowest-index tie-break (deterministic)
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+          }
+          if (lane == 0) { red_v[q * 16 + j] = v; red_i[q * 16 + j] = idx; }
+        }
+        // named barrier over the 4 epilogue warps (128 threads), id 1
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q == 2 && lane < 16) {  // warp 2 finishes: 4 candidates per column
+          float v = red_v[lane];
+          int idx = red_i[lane];
+#pragma unroll
+          for (int w = 1; w < 4; ++w) {
+            float ov = red_v[w * 16 + lane];
+            int oi = red_i[w * 16 + lane];
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+          }
+          const int n = n0 + c + lane;
+          if (n < n_valid) {
+            args.amax_val[(size_t)n * gridDim.x + blockIdx.x] = v;
+            args.amax_idx[(size_t)n * gridDim.x + blockIdx.x] = idx;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace acp

@@ -1,0 +1,107 @@
+// kernel_tests.cu — C-ABI per-kernel test hooks (include/acp_infer_kernels.h).
+// Host buffers in, host buffers out; used only by tests/ to compare each kernel with oracle/.
+#include "acp_infer_kernels.h"
+#include "common.cuh"
+#include "gemm.h"
+#include "gemm_tcgen05.cuh"
+#include <vector>
+
+using namespace acp;
+
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -5; }
+};
+__global__ void l2_flush_kernel(float* buf, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) buf[i] = buf[i] * 1.0001f + 1.0f;
+}
+}  // namespace
+
+extern "C" int acp_kernel_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int N, int K,
+                               int splits, int epi, int bn, void* out, float* amax_val,
+                               int* amax_idx, int iters, float* elapsed_ms) {
+  if (acp_kernel_device_count() <= 0) {
+    fprintf(stderr, "[acp_infer] no CUDA device: kernels cannot run (no CPU fallback)\n");
+    return -5;
+  }
+  if (gemm_setup_attributes() != 0) return -5;
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  DevBuf dw, dx, dout, dval, didx, dflush;
+  if (dw.alloc((size_t)M * K * 2) || dx.alloc((size_t)N * K * 2)) return -5;
+  ACP_CUDA_CHECK(cudaMemcpy(dw.p, w, (size_t)M * K * 2, cudaMemcpyHostToDevice));
+  ACP_CUDA_CHECK(cudaMemcpy(dx.p, x, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+  size_t out_bytes = 0;
+  if (epi == EPI_BF16) out_bytes = (size_t)N * M * 2;
+  else if (epi == EPI_F32) out_bytes = (size_t)splits * N * M * 4;
+  else if (out != nullptr) out_bytes = (size_t)N * M * 4;
+  if (dout.alloc(out_bytes)) return -5;
+  ACP_CUDA_CHECK(cudaMemset(dout.p, 0xff, out_bytes ? out_bytes : 1));
+  if (epi == EPI_ARGMAX) {
+    if (dval.alloc((size_t)N * m_tiles * 4) || didx.alloc((size_t)N * m_tiles * 4)) return -5;
+  }
+  TmaMaps mw, mx;
+  if (tma_make_weight(&mw, dw.p, M, K) != 0) return -5;
+  if (tma_make_act(&mx, dx.p, N, K) != 0) return -5;
+  GemmLaunch g;
+  g.w = &mw.w; g.x = &mx; g.M = M; g.N = N; g.K = K; g.splits = splits; g.epi = epi;
+  g.ld = M; g.n_cap = N;
+  g.out = (epi == EPI_ARGMAX && out == nullptr) ? nullptr : dout.p;
+  g.amax_val = (float*)dval.p; g.amax_idx = (int*)didx.p; g.bn_override = bn;
+  int rc = gemm_launch(g, 0);
+  if (rc != 0) return rc;
+  ACP_CUDA_CHECK(cudaDeviceSynchronize());
+  if (out != nullptr && out_bytes)
+    ACP_CUDA_CHECK(cudaMemcpy(out, dout.p, out_bytes, cudaMemcpyDeviceToHost));
+  if (epi == EPI_ARGMAX) {
+    // final reduction over m-tiles on the host for this hook (the engine does it on device)
+    std::vector<float> tv((size_t)N * m_tiles);
+    std::vector<int> ti((size_t)N * m_tiles);
+    ACP_CUDA_CHECK(cudaMemcpy(tv.data(), dval.p, tv.size() * 4, cudaMemcpyDeviceToHost));
+    ACP_CUDA_CHECK(cudaMemcpy(ti.data(), didx.p, ti.size() * 4, cudaMemcpyDeviceToHost));
+    for (int n = 0; n < N; ++n) {
+      float bv = tv[(size_t)n * m_tiles];
+      int bi = ti[(size_t)n * m_tiles];
+      for (int t = 1; t < m_tiles; ++t) {
+        float v = tv[(size_t)n * m_tiles + t];
+        int i = ti[(size_t)n * m_tiles + t];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+      amax_val[n] = bv;
+      amax_idx[n] = bi;
+    }
+  }
+  if (iters > 0 && elapsed_ms != nullptr) {
+    const size_t flush_n = (size_t)64 << 20;  // 256 MiB of fp32 > 126 MB L2
+    if (dflush.alloc(flush_n * 4)) return -5;
+    ACP_CUDA_CHECK(cudaMemset(dflush.p, 0, flush_n * 4));
+    cudaEvent_t e0, e1;
+    ACP_CUDA_CHECK(cudaEventCreate(&e0));
+    ACP_CUDA_CHECK(cudaEventCreate(&e1));
+    float total = 0.f;
+    for (int it = 0; it < iters + 2; ++it) {
+      l2_flush_kernel<<<1184, 256>>>((float*)dflush.p, flush_n);
+      ACP_CUDA_CHECK(cudaEventRecord(e0, 0));
+      rc = gemm_launch(g, 0);
+      if (rc != 0) return rc;
+      ACP_CUDA_CHECK(cudaEventRecord(e1, 0));
+      ACP_CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      ACP_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      if (it >= 2) total += ms;  // two warm-up launches
+    }
+    *elapsed_ms = total / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  return 0;
+}

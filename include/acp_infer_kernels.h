@@ -1,0 +1,34 @@
+/* acp_infer_kernels.h — per-kernel test entry points of libacp_infer.so.
+ *
+ * These are NOT part of the drop-in boundary (that is include/acp_infer.h).  They exist so the
+ * parity tests in tests/ can drive each sm_100a kernel in isolation with HOST buffers (plain
+ * pointers and sizes; the library does the cudaMalloc / cudaMemcpy) and compare against the
+ * oracle in oracle/.  Every function returns 0 on success or a negative ACP_ERR_* code, never
+ * throws, and fails loudly (ACP_ERR_CUDA) when no CUDA device is usable — there is no CPU
+ * fallback anywhere in the library.
+ */
+#ifndef ACP_INFER_KERNELS_H
+#define ACP_INFER_KERNELS_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* out[n][m] = sum_k w[m][k] * x[n][k]; w,x are bf16 bit patterns.
+ * epi 0: out = bf16 [N][M]; epi 1: out = fp32 [splits][N][M] (split-K partial planes);
+ * epi 2: amax_val/amax_idx = per-row arg-max over M (lowest index wins ties), out = optional
+ * fp32 logits [N][M] (may be NULL).  bn = 0 picks the N tile from N; otherwise 16..256.
+ * iters > 0 additionally times `iters` launches with CUDA events (L2 flushed between
+ * launches) and stores the mean milliseconds in *elapsed_ms. */
+int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int N, int K, int splits,
+                    int epi, int bn, void* out, float* amax_val, int* amax_idx, int iters,
+                    float* elapsed_ms);
+
+/* Number of visible CUDA devices (0 when none / no driver). */
+int acp_kernel_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
