@@ -1,0 +1,490 @@
+// attention.cu — paged-KV GQA attention for the decode engine (decode + causal prefill).
+//
+// KV cache layout per layer:  K, V : [num_pages][kv_heads][KV_PAGE=32][128] bf16.  Seen by TMA as
+// a 2-D tensor [num_pages*kv_heads*32 rows][128 cols]; one (page, kv-head) block is 32 contiguous
+// rows, loaded as two boxes {64 cols x 32 rows} with the 128-byte swizzle, so each staged block
+// in shared memory is [32 rows][128 B] with 16-byte chunks XOR-ed by (row & 7): ldmatrix reads
+// are bank-conflict free with no padding.
+//
+// A CTA stages 64-token tiles (2 pages: K 16 KiB + V 16 KiB per stage) through a 4-deep ring
+// filled by a dedicated producer warp (cp.async.bulk.tensor + mbarrier complete_tx); consumer
+// warps run mma.sync m16n8k16 (bf16 in, fp32 accumulate) with an online softmax:
+//   rows of the 16-row MMA tile = (query token, head-in-group); GQA packs the G query heads that
+//   share one KV head into one tile, so K/V bytes are read once per KV head.
+//   P is split into bf16 hi + lo parts (two PV MMAs) so that P keeps ~16 mantissa bits: the
+//   result matches an fp32-softmax oracle to ~1e-6 and no bf16 rounding of P needs mirroring.
+//
+// decode  : CTA = (sequence, kv head, kv split); the 4 consumer warps take alternate tiles and
+//           merge their (m, l, O) through shared memory; splits merge in attn_merge_kernel.
+// prefill : CTA = (16/G*4 query tokens of one sequence, kv head); every warp owns 16 rows
+//           (16/G tokens x G heads) and all warps walk the causal range of tiles together.
+//
+// This is HBM/L2-bound byte movement (4..8 useful rows per MMA): tensor-core use here is only to
+// keep the issue slots free, the roofline is bytes of K/V per second.
+#include "attention.h"
+#include "common.cuh"
+#include "gemm.h"
+
+namespace acp {
+
+namespace {
+
+constexpr int TILE_TOK = 64;                 // tokens per staged tile (2 pages)
+constexpr int BLOCK_BYTES = KV_PAGE * 128;   // one {64 cols x 32 rows} box = 4 KiB
+constexpr int K_TILE_BYTES = 4 * BLOCK_BYTES;  // 2 pages x 2 halves
+constexpr int STAGE_BYTES = 2 * K_TILE_BYTES;  // K + V = 32 KiB
+constexpr int STAGES = 3;
+constexpr int CONSUMER_WARPS = 4;
+constexpr int ATTN_THREADS = (CONSUMER_WARPS + 1) * 32;
+
+ACP_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+ACP_DEVINL void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+ACP_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+// byte offset of (token-in-tile, dim) inside a staged K or V tile
+ACP_DEVINL uint32_t tile_off(int tok, int dim) {
+  const int page = tok >> 5, r = tok & 31, hf = dim >> 6, c = (dim & 63) >> 3;
+  return (uint32_t)((page * 2 + hf) * BLOCK_BYTES + r * 128 + ((c ^ (r & 7)) << 4));
+}
+
+struct WarpState {
+  float o[16][4];   // 16 dim-tiles of 8: c0,c1 -> row lane/4 ; c2,c3 -> row lane/4+8
+  float m[2];       // running max (raw score units) for the two rows of this thread
+  float l[2];       // per-thread partial row sums
+};
+
+// One 64-token tile for one warp.  key_limit[r] = number of visible keys for row r (keys with
+// absolute index < key_limit are visible), tile_tok0 = absolute index of the tile's first key.
+ACP_DEVINL void process_tile(WarpState& st, const uint32_t (&qf)[8][4], uint32_t k_base,
+                             uint32_t v_base, int tile_tok0, int key_limit_lo, int key_limit_hi,
+                             float sl2e, int lane) {
+  float s[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+  const int mi = lane >> 3, rr = lane & 7;
+  // ---- S = Q K^T ----
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {          // 8 key n-tiles of 8 tokens
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {     // 4 pairs of k-steps (32 dims each)
+      uint32_t b[4];
+      ldmatrix_x4(b, k_base + tile_off(j * 8 + rr, kp * 32 + mi * 8));
+      mma_bf16_16816(s[j], qf[kp * 2], b[0], b[1]);
+      mma_bf16_16816(s[j], qf[kp * 2 + 1], b[2], b[3]);
+    }
+  }
+  // ---- mask + online softmax ----
+  float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int t0 = tile_tok0 + j * 8 + 2 * (lane & 3);
+    if (t0 >= key_limit_lo) s[j][0] = -INFINITY;
+    if (t0 + 1 >= key_limit_lo) s[j][1] = -INFINITY;
+    if (t0 >= key_limit_hi) s[j][2] = -INFINITY;
+    if (t0 + 1 >= key_limit_hi) s[j][3] = -INFINITY;
+    mx_lo = fmaxf(mx_lo, fmaxf(s[j][0], s[j][1]));
+    mx_hi = fmaxf(mx_hi, fmaxf(s[j][2], s[j][3]));
+  }
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+  const float mn_lo = fmaxf(st.m[0], mx_lo), mn_hi = fmaxf(st.m[1], mx_hi);
+  // rows with nothing visible yet keep m = -inf; use 0 as the exponent base there (all p = 0)
+  const float base_lo = (mn_lo == -INFINITY) ? 0.f : mn_lo * sl2e;
+  const float base_hi = (mn_hi == -INFINITY) ? 0.f : mn_hi * sl2e;
+  const float corr_lo = (st.m[0] == -INFINITY) ? 0.f : exp2f(st.m[0] * sl2e - base_lo);
+  const float corr_hi = (st.m[1] == -INFINITY) ? 0.f : exp2f(st.m[1] * sl2e - base_hi);
+  st.m[0] = mn_lo; st.m[1] = mn_hi;
+  st.l[0] *= corr_lo; st.l[1] *= corr_hi;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    st.o[d][0] *= corr_lo; st.o[d][1] *= corr_lo;
+    st.o[d][2] *= corr_hi; st.o[d][3] *= corr_hi;
+  }
+  uint32_t p_hi[4][4], p_lo[4][4];  // A fragments for the 4 PV k-steps (16 tokens each)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float p[4];
+    p[0] = exp2f(s[j][0] * sl2e - base_lo);
+    p[1] = exp2f(s[j][1] * sl2e - base_lo);
+    p[2] = exp2f(s[j][2] * sl2e - base_hi);
+    p[3] = exp2f(s[j][3] * sl2e - base_hi);
+    st.l[0] += p[0] + p[1];
+    st.l[1] += p[2] + p[3];
+    float h[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { h[e] = bf16_round(p[e]); lo[e] = p[e] - h[e]; }
+    const int kt = j >> 1, half = j & 1;
+    p_hi[kt][half * 2 + 0] = pack_bf16x2(h[0], h[1]);
+    p_hi[kt][half * 2 + 1] = pack_bf16x2(h[2], h[3]);
+    p_lo[kt][half * 2 + 0] = pack_bf16x2(lo[0], lo[1]);
+    p_lo[kt][half * 2 + 1] = pack_bf16x2(lo[2], lo[3]);
+  }
+  // ---- O += P V ----
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {       // 16 tokens per k-step
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {     // 16 dims per ldmatrix.x4.trans
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, v_base + tile_off(kt * 16 + (mi & 1) * 8 + rr, nd * 16 + (mi >> 1) * 8));
+      mma_bf16_16816(st.o[nd * 2], p_hi[kt], b[0], b[1]);
+      mma_bf16_16816(st.o[nd * 2], p_lo[kt], b[0], b[1]);
+      mma_bf16_16816(st.o[nd * 2 + 1], p_hi[kt], b[2], b[3]);
+      mma_bf16_16816(st.o[nd * 2 + 1], p_lo[kt], b[2], b[3]);
+    }
+  }
+}
+
+// V rows of tokens that do not exist yet may hold stale bytes (NaN patterns): zero them so that
+// 0 * garbage cannot poison the accumulators.  Called by the consuming warp on a landed tile.
+ACP_DEVINL void zero_v_tail(uint8_t* v_tile, int first_invalid_tok, int lane) {
+  for (int t = first_invalid_tok; t < TILE_TOK; ++t) {
+    const int page = t >> 5, r = t & 31;
+    // 2 halves x 128 B per row = 16 uint4; lanes 0..15 write one each
+    if (lane < 16) {
+      const int hf = lane >> 3, c = lane & 7;
+      *reinterpret_cast<uint4*>(v_tile + (page * 2 + hf) * BLOCK_BYTES + r * 128 + c * 16) =
+          make_uint4(0, 0, 0, 0);
+    }
+  }
+  __syncwarp();
+}
+
+ACP_DEVINL void load_q_frags(uint32_t (&qf)[8][4], const __nv_bfloat16* q_lo,
+                             const __nv_bfloat16* q_hi, int lane) {
+  const int c = 2 * (lane & 3);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    qf[ks][0] = q_lo ? *reinterpret_cast<const uint32_t*>(q_lo + ks * 16 + c) : 0u;
+    qf[ks][1] = q_hi ? *reinterpret_cast<const uint32_t*>(q_hi + ks * 16 + c) : 0u;
+    qf[ks][2] = q_lo ? *reinterpret_cast<const uint32_t*>(q_lo + ks * 16 + 8 + c) : 0u;
+    qf[ks][3] = q_hi ? *reinterpret_cast<const uint32_t*>(q_hi + ks * 16 + 8 + c) : 0u;
+  }
+}
+
+// Producer: stage tiles [tile_begin, tile_end) of sequence `seq`, kv head `kh`.
+ACP_DEVINL void produce_tiles(const CUtensorMap* tm_k, const CUtensorMap* tm_v, uint8_t* stages,
+                              uint64_t* full_bar, uint64_t* empty_bar, const int* pt_row, int kh,
+                              int kv_heads, int tile_begin, int tile_end, int last_tok /*exclusive*/) {
+  int it = 0;
+  for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+    const int s = it % STAGES;
+    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+    mbar_wait(&empty_bar[s], ph ^ 1u);
+    const int tok0 = tile * TILE_TOK;
+    const int n_pages = (last_tok - tok0 > KV_PAGE) ? 2 : 1;
+    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(n_pages * 4 * BLOCK_BYTES));
+    uint8_t* kdst = stages + s * STAGE_BYTES;
+    uint8_t* vdst = kdst + K_TILE_BYTES;
+    for (int p = 0; p < n_pages; ++p) {
+      const int page = pt_row[tok0 / KV_PAGE + p];
+      const int row = (page * kv_heads + kh) * KV_PAGE;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        tma_load_2d(kdst + (p * 2 + hf) * BLOCK_BYTES, tm_k, &full_bar[s], hf * 64, row, kEvictFirst);
+        tma_load_2d(vdst + (p * 2 + hf) * BLOCK_BYTES, tm_v, &full_bar[s], hf * 64, row, kEvictFirst);
+      }
+    }
+  }
+}
+
+struct SmemLayout {
+  uint8_t* stages;
+  uint64_t* full_bar;
+  uint64_t* empty_bar;
+};
+ACP_DEVINL SmemLayout carve(uint8_t* raw) {
+  SmemLayout L;
+  uint8_t* base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  L.stages = base;
+  L.full_bar = (uint64_t*)(base + STAGES * STAGE_BYTES);
+  L.empty_bar = L.full_bar + STAGES;
+  return L;
+}
+// decode cross-warp merge scratch [4 warps][16 rows][130] aliases the (drained) stage ring
+constexpr int SCRATCH_FLOATS = CONSUMER_WARPS * 16 * 130;
+static_assert(SCRATCH_FLOATS * 4 <= STAGES * STAGE_BYTES, "scratch must fit in the ring");
+constexpr int ATTN_SMEM = STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + 16;
+
+// =================================================================================
+// decode
+// =================================================================================
+__global__ void __launch_bounds__(ATTN_THREADS, 2)
+attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                   AttnDecodeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout L = carve(smem_raw);
+  const int b = blockIdx.x, kh = blockIdx.y, sp = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = a.heads / a.kv_heads;
+  const int ctx = a.ctx_len[b];
+  const int tok_begin = sp * a.split_tokens;
+  if (tok_begin >= ctx) return;  // uniform per CTA
+  const int tok_end = min(ctx, tok_begin + a.split_tokens);
+  const int tile_begin = tok_begin / TILE_TOK;
+  const int tile_end = (tok_end + TILE_TOK - 1) / TILE_TOK;
+  const int n_tiles = tile_end - tile_begin;
+  const int n_splits = (ctx + a.split_tokens - 1) / a.split_tokens;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&L.full_bar[s], 1); mbar_init(&L.empty_bar[s], 1); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == CONSUMER_WARPS) {
+    if (lane == 0)
+      produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
+                    a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, tile_begin, tile_end, tok_end);
+    return;
+  }
+  // ---- consumers ----
+  const int q_row = a.q_rows ? a.q_rows[b] : b;
+  const int r_lo = lane >> 2;  // rows r_lo (and r_lo+8) of the 16-row tile; row r = head-in-group
+  const __nv_bfloat16* qbase = a.q + (size_t)q_row * a.heads * HEAD_DIM + (size_t)kh * G * HEAD_DIM;
+  uint32_t qf[8][4];
+  load_q_frags(qf, r_lo < G ? qbase + r_lo * HEAD_DIM : nullptr,
+               r_lo + 8 < G ? qbase + (r_lo + 8) * HEAD_DIM : nullptr, lane);
+  WarpState st;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) st.o[d][0] = st.o[d][1] = st.o[d][2] = st.o[d][3] = 0.f;
+  st.m[0] = st.m[1] = -INFINITY;
+  st.l[0] = st.l[1] = 0.f;
+  const float sl2e = a.scale * 1.4426950408889634f;
+  for (int it = warp; it < n_tiles; it += CONSUMER_WARPS) {
+    const int s = it % STAGES;
+    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+    mbar_wait(&L.full_bar[s], ph);
+    uint8_t* kt = L.stages + s * STAGE_BYTES;
+    uint8_t* vt = kt + K_TILE_BYTES;
+    const int tile_tok0 = (tile_begin + it) * TILE_TOK;
+    if (tok_end - tile_tok0 < TILE_TOK) zero_v_tail(vt, tok_end - tile_tok0, lane);
+    process_tile(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_end, tok_end, sl2e, lane);
+    __syncwarp();
+    if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }
+  }
+  // ---- merge the 4 warps (rows < G only; G <= 16) ----
+  st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 1);
+  st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 2);
+  st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 1);
+  st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 2);
+  // every consumer is done with the ring before it is reused as merge scratch
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  float* scratch = reinterpret_cast<float*>(L.stages);
+  float* my = scratch + warp * 16 * 130;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int r = r_lo + hh * 8;
+    if (r < G) {
+      if ((lane & 3) == 0) { my[r * 130 + 128] = st.m[hh]; my[r * 130 + 129] = st.l[hh]; }
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        my[r * 130 + d * 8 + 2 * (lane & 3)] = st.o[d][hh * 2];
+        my[r * 130 + d * 8 + 2 * (lane & 3) + 1] = st.o[d][hh * 2 + 1];
+      }
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int d = threadIdx.x;  // 128 consumer threads <-> 128 dims
+  for (int r = 0; r < G; ++r) {
+    float M = -INFINITY;
+    for (int w = 0; w < CONSUMER_WARPS; ++w) M = fmaxf(M, scratch[(w * 16 + r) * 130 + 128]);
+    float num = 0.f, den = 0.f;
+    for (int w = 0; w < CONSUMER_WARPS; ++w) {  // fixed order
+      const float mw = scratch[(w * 16 + r) * 130 + 128];
+      const float wgt = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * sl2e);
+      num += wgt * scratch[(w * 16 + r) * 130 + d];
+      den += wgt * scratch[(w * 16 + r) * 130 + 129];
+    }
+    const int head = kh * G + r;
+    const float val = num / den;
+    if (n_splits == 1) {
+      a.out[(size_t)q_row * a.heads * HEAD_DIM + head * HEAD_DIM + d] = __float2bfloat16_rn(val);
+    } else {
+      const size_t slot = ((size_t)b * a.heads + head) * a.max_splits + sp;
+      a.ws_o[slot * HEAD_DIM + d] = val;
+      if (d == 0) { a.ws_m[slot] = M; a.ws_l[slot] = den; }
+    }
+  }
+}
+
+// merge split partials: one CTA (128 threads = dims) per (sequence, head)
+__global__ void __launch_bounds__(128)
+attn_merge_kernel(AttnDecodeArgs a) {
+  const int b = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
+  const int ctx = a.ctx_len[b];
+  const int n_splits = (ctx + a.split_tokens - 1) / a.split_tokens;
+  if (n_splits <= 1) return;
+  const float sl2e = a.scale * 1.4426950408889634f;
+  const size_t slot0 = ((size_t)b * a.heads + head) * a.max_splits;
+  float M = -INFINITY;
+  for (int s = 0; s < n_splits; ++s) M = fmaxf(M, a.ws_m[slot0 + s]);
+  float num = 0.f, den = 0.f;
+  for (int s = 0; s < n_splits; ++s) {
+    const float w = a.ws_l[slot0 + s] * exp2f((a.ws_m[slot0 + s] - M) * sl2e);
+    num += w * a.ws_o[(slot0 + s) * HEAD_DIM + d];
+    den += w;
+  }
+  const int q_row = a.q_rows ? a.q_rows[b] : b;
+  a.out[(size_t)q_row * a.heads * HEAD_DIM + head * HEAD_DIM + d] = __float2bfloat16_rn(num / den);
+}
+
+// =================================================================================
+// prefill (causal, chunk-capable: queries may start at any position of the sequence)
+// =================================================================================
+__global__ void __launch_bounds__(ATTN_THREADS, 2)
+attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                    AttnPrefillArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout L = carve(smem_raw);
+  const int blk = blockIdx.x, kh = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = a.heads / a.kv_heads;
+  const int tpw = 16 / G;                    // query tokens per warp
+  const int b = a.blk_seq[blk];
+  const int tq0 = a.blk_tok0[blk];           // first query token (index within the new tokens)
+  const int q_len = a.q_len[b], ctx = a.ctx_len[b];
+  const int pos0 = ctx - q_len;              // absolute position of new token 0
+  const int blk_tokens = min(tpw * CONSUMER_WARPS, q_len - tq0);
+  const int last_pos = pos0 + tq0 + blk_tokens - 1;
+  const int n_tiles = last_pos / TILE_TOK + 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&L.full_bar[s], 1);
+      mbar_init(&L.empty_bar[s], CONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == CONSUMER_WARPS) {
+    if (lane == 0)
+      produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
+                    a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, last_pos + 1);
+    return;
+  }
+  // rows of this warp: r -> token tq0 + warp*tpw + r / G, head kh*G + r % G
+  const int r_lo = lane >> 2, r_hi = r_lo + 8;
+  const int tq_lo = tq0 + warp * tpw + r_lo / G, tq_hi = tq0 + warp * tpw + r_hi / G;
+  const bool v_lo = tq_lo < q_len, v_hi = tq_hi < q_len;
+  const size_t row_lo = (size_t)(a.q_start[b] + tq_lo), row_hi = (size_t)(a.q_start[b] + tq_hi);
+  const int h_lo = kh * G + r_lo % G, h_hi = kh * G + r_hi % G;
+  uint32_t qf[8][4];
+  load_q_frags(qf, v_lo ? a.q + (row_lo * a.heads + h_lo) * HEAD_DIM : nullptr,
+               v_hi ? a.q + (row_hi * a.heads + h_hi) * HEAD_DIM : nullptr, lane);
+  const int lim_lo = v_lo ? pos0 + tq_lo + 1 : 0, lim_hi = v_hi ? pos0 + tq_hi + 1 : 0;
+  // this warp needs tiles only up to its own last query position
+  const int warp_last = pos0 + min(q_len - 1, tq0 + warp * tpw + tpw - 1);
+  const bool warp_active = (tq0 + warp * tpw) < q_len;
+  WarpState st;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) st.o[d][0] = st.o[d][1] = st.o[d][2] = st.o[d][3] = 0.f;
+  st.m[0] = st.m[1] = -INFINITY;
+  st.l[0] = st.l[1] = 0.f;
+  const float sl2e = a.scale * 1.4426950408889634f;
+  for (int it = 0; it < n_tiles; ++it) {
+    const int s = it % STAGES;
+    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+    mbar_wait(&L.full_bar[s], ph);
+    uint8_t* kt = L.stages + s * STAGE_BYTES;
+    uint8_t* vt = kt + K_TILE_BYTES;
+    const int tile_tok0 = it * TILE_TOK;
+    if (warp_active && tile_tok0 <= warp_last) {
+      // tokens past last_pos were not loaded (or belong to the future): zero V there.  Every
+      // active warp writes the same zeros, which is benign.
+      if (last_pos + 1 - tile_tok0 < TILE_TOK) zero_v_tail(vt, last_pos + 1 - tile_tok0, lane);
+      process_tile(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, lim_lo, lim_hi, sl2e, lane);
+    }
+    __syncwarp();
+    if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }
+  }
+  st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 1);
+  st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 2);
+  st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 1);
+  st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 2);
+  const int c = 2 * (lane & 3);
+  if (v_lo) {
+    const float inv = 1.0f / st.l[0];
+    __nv_bfloat16* o = a.out + (row_lo * a.heads + h_lo) * HEAD_DIM;
+#pragma unroll
+    for (int d = 0; d < 16; ++d)
+      *reinterpret_cast<uint32_t*>(o + d * 8 + c) = pack_bf16x2(st.o[d][0] * inv, st.o[d][1] * inv);
+  }
+  if (v_hi) {
+    const float inv = 1.0f / st.l[1];
+    __nv_bfloat16* o = a.out + (row_hi * a.heads + h_hi) * HEAD_DIM;
+#pragma unroll
+    for (int d = 0; d < 16; ++d)
+      *reinterpret_cast<uint32_t*>(o + d * 8 + c) = pack_bf16x2(st.o[d][2] * inv, st.o[d][3] * inv);
+  }
+}
+
+}  // namespace
+
+int attn_setup_attributes() {
+  cudaError_t e1 = cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  cudaError_t e2 = cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    fprintf(stderr, "[acp_infer] attention cudaFuncSetAttribute failed\n");
+    return -5;
+  }
+  return 0;
+}
+
+int attn_make_kv_map(CUtensorMap* out, const void* base, uint64_t num_pages, int kv_heads) {
+  // 2-D view [num_pages*kv_heads*KV_PAGE rows][128 cols]; box {64 cols, 32 rows}
+  return tma_encode_2d_bf16(out, base, num_pages * (uint64_t)kv_heads * KV_PAGE, HEAD_DIM, KV_PAGE);
+}
+
+int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnDecodeArgs& a,
+                       int num_seqs, int max_ctx, cudaStream_t s) {
+  if (num_seqs <= 0) return 0;
+  if (a.heads % a.kv_heads != 0 || a.heads / a.kv_heads > 16 || a.split_tokens % TILE_TOK != 0) return -1;
+  const int n_splits = (max_ctx + a.split_tokens - 1) / a.split_tokens;
+  if (n_splits > a.max_splits) return -1;
+  dim3 grid(num_seqs, a.kv_heads, n_splits);
+  attn_decode_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, s>>>(tm_k, tm_v, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode launch: %s\n", cudaGetErrorString(e)); return -5; }
+  if (n_splits > 1) {
+    attn_merge_kernel<<<dim3(num_seqs, a.heads), 128, 0, s>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_merge launch: %s\n", cudaGetErrorString(e)); return -5; }
+  }
+  return 0;
+}
+
+int attn_prefill_block_tokens(int heads, int kv_heads) { return (16 / (heads / kv_heads)) * CONSUMER_WARPS; }
+
+int launch_attn_prefill(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnPrefillArgs& a,
+                        int num_blocks, cudaStream_t s) {
+  if (num_blocks <= 0) return 0;
+  const int G = a.heads / a.kv_heads;
+  if (a.heads % a.kv_heads != 0 || G > 16 || (16 % G) != 0) return -1;
+  dim3 grid(num_blocks, a.kv_heads);
+  attn_prefill_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, s>>>(tm_k, tm_v, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_prefill launch: %s\n", cudaGetErrorString(e)); return -5; }
+  return 0;
+}
+
+}  // namespace acp

@@ -1,0 +1,476 @@
+// engine.cc — see engine.h.
+#include "engine.h"
+#include <algorithm>
+#include <stdio.h>
+
+namespace acp {
+
+using clk = std::chrono::steady_clock;
+static double ms_between(clk::time_point a, clk::time_point b) {
+  return std::chrono::duration<double, std::milli>(b - a).count();
+}
+
+Engine::~Engine() { shutdown(); }
+
+int Engine::init(const char* config_json) {
+  Json cfg;
+  std::string err;
+  const std::string text = config_json && *config_json ? config_json : "{}";
+  if (!Json::parse(text, &cfg, &err) || !cfg.is_object()) {
+    fprintf(stderr, "[acp_infer] bad config JSON: %s\n", err.c_str());
+    return -1;
+  }
+  ModelConfig mc;
+  std::string name = cfg.get("model").as_string();
+  if (name.empty()) name = "tiny";
+  if (!model_preset(name, &mc)) {
+    fprintf(stderr, "[acp_infer] unknown model preset '%s'\n", name.c_str());
+    return -1;
+  }
+  const std::string weights = cfg.get("weights").as_string();
+  if (!weights.empty() && weights != "synthetic") {
+    fprintf(stderr, "[acp_infer] weights='%s' not supported: only 'synthetic' (no checkpoints in this image)\n",
+            weights.c_str());
+    return -1;
+  }
+  if (cfg.find("seed")) mc.seed = (uint64_t)cfg.get("seed").as_int((long long)mc.seed);
+  if (cfg.find("layers")) mc.layers = (int)cfg.get("layers").as_int(mc.layers);  // truncated-depth runs
+  ModelLimits lim;
+  lim.max_batch = (int)cfg.get("max_batch").as_int(lim.max_batch);
+  lim.max_tokens = (int)cfg.get("max_tokens_per_step").as_int(lim.max_tokens);
+  lim.num_pages = (int)cfg.get("kv_pages").as_int(lim.num_pages);
+  lim.max_pages_per_seq = (int)cfg.get("max_pages_per_seq").as_int(lim.max_pages_per_seq);
+  lim.split_tokens = (int)cfg.get("attn_split_tokens").as_int(lim.split_tokens);
+  if (cfg.find("splitk_target_ctas")) lim.splitk_target_ctas = (int)cfg.get("splitk_target_ctas").as_int(lim.splitk_target_ctas);
+  if (lim.max_batch < 1 || lim.max_tokens < 16 || lim.num_pages < 2 || lim.split_tokens % 64 != 0 ||
+      lim.max_pages_per_seq < 1) {
+    fprintf(stderr, "[acp_infer] invalid engine limits\n");
+    return -1;
+  }
+  const int device = (int)cfg.get("device").as_int(0);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    fprintf(stderr, "[acp_infer] no CUDA device available: provider local cannot start (no CPU fallback)\n");
+    return -5;
+  }
+  if (device < 0 || device >= ndev) {
+    fprintf(stderr, "[acp_infer] device %d out of range (%d visible)\n", device, ndev);
+    return -1;
+  }
+  model_name_ = name;
+  int rc = model_.init(mc, lim, device);
+  if (rc != 0) return rc;
+  if (cudaEventCreate(&ev0_) != cudaSuccess || cudaEventCreate(&ev1_) != cudaSuccess) return -5;
+  max_ctx_tokens_ = std::min(lim.max_pages_per_seq * KV_PAGE, mc.max_pos);
+  for (int p = lim.num_pages - 1; p >= 1; --p) free_pages_.push_back(p);  // page 0 reserved
+  thread_ = std::thread([this] { run(); });
+  return 0;
+}
+
+void Engine::shutdown() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (stop_.exchange(true)) {
+      // already stopping
+    }
+  }
+  cv_work_.notify_all();
+  if (thread_.joinable()) thread_.join();
+  std::lock_guard<std::mutex> lk(mu_);
+  for (auto& kv : all_) {
+    if (!kv.second->done) {
+      kv.second->done = true;
+      kv.second->status = 503;
+      kv.second->error_type = "engine_shutdown";
+      kv.second->error_msg = "engine is shutting down";
+    }
+  }
+  cv_done_.notify_all();
+  if (ev0_) { cudaEventDestroy(ev0_); ev0_ = nullptr; }
+  if (ev1_) { cudaEventDestroy(ev1_); ev1_ = nullptr; }
+}
+
+int Engine::submit(const char* json, size_t len, uint64_t* ticket) {
+  if (!json || !ticket) return -1;
+  auto s = std::make_shared<Sequence>();
+  s->t_submit = clk::now();
+  ChatRequest req;
+  std::string err;
+  int status = parse_chat_request(json, len, &req, &err);
+  std::string etype = "invalid_request_error";
+  if (status == 0) {
+    if (!req.model.empty() && req.model != model_name_) {
+      status = 404; etype = "model_not_found";
+      err = "model '" + req.model + "' is not served by this engine (serving '" + model_name_ + "')";
+    }
+  }
+  if (status == 0) {
+    if (req.has_prompt_ids) s->tokens = req.prompt_token_ids;
+    else render_prompt(req, &s->tokens);
+    const int vocab = model_.config().vocab;
+    for (int t : s->tokens)
+      if (t < 0 || t >= vocab) { status = 400; err = "prompt token id out of range"; break; }
+    for (int t : req.force_tokens)
+      if (t < 0 || t >= vocab) { status = 400; err = "force token id out of range"; break; }
+    if (status == 0 && s->tokens.empty()) { status = 400; err = "empty prompt"; }
+  }
+  if (status == 0) {
+    s->prompt_len = (int)s->tokens.size();
+    s->sampling = req.sampling;
+    s->tools = std::move(req.tools);
+    s->force_tokens = std::move(req.force_tokens);
+    s->return_logits = std::max(0, std::min(req.return_logits, 64));
+    const long long need = (long long)s->prompt_len + s->sampling.max_tokens;
+    if (need > max_ctx_tokens_) {
+      status = 400; etype = "context_length_exceeded";
+      err = "prompt (" + std::to_string(s->prompt_len) + " tokens) + max_tokens (" +
+            std::to_string(s->sampling.max_tokens) + ") exceeds the engine context limit of " +
+            std::to_string(max_ctx_tokens_) + " tokens";
+    }
+    const long long pages_needed = (need + KV_PAGE - 1) / KV_PAGE;
+    if (status == 0 && pages_needed > model_.limits().num_pages - 1) {
+      status = 400; etype = "context_length_exceeded";
+      err = "request needs more KV pages than the pool holds";
+    }
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  if (stop_) return -6;
+  s->ticket = next_ticket_++;
+  *ticket = s->ticket;
+  all_[s->ticket] = s;
+  if (status != 0) {
+    s->done = true; s->status = status; s->error_type = etype; s->error_msg = err;
+    s->t_done = clk::now();
+    finished_unreported_.push_back(s->ticket);
+    ++stats_.requests_failed;
+    cv_done_.notify_all();
+    return 0;
+  }
+  if (broken_) {
+    s->done = true; s->status = 500; s->error_type = "engine_error";
+    s->error_msg = "engine stopped after a CUDA failure";
+    finished_unreported_.push_back(s->ticket);
+    cv_done_.notify_all();
+    return 0;
+  }
+  waiting_.push_back(s);
+  cv_work_.notify_one();
+  return 0;
+}
+
+int Engine::wait(uint64_t ticket, int timeout_ms) {
+  std::unique_lock<std::mutex> lk(mu_);
+  auto it = all_.find(ticket);
+  if (it == all_.end()) return -2;
+  auto s = it->second;
+  auto pred = [&] { return s->done; };
+  if (timeout_ms < 0) cv_done_.wait(lk, pred);
+  else if (!cv_done_.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred)) return -3;
+  return 0;
+}
+
+int Engine::poll(uint64_t* tickets, int max, int timeout_ms) {
+  if (!tickets || max <= 0) return -1;
+  std::unique_lock<std::mutex> lk(mu_);
+  auto pred = [&] { return !finished_unreported_.empty() || stop_.load(); };
+  if (timeout_ms < 0) cv_done_.wait(lk, pred);
+  else if (timeout_ms > 0) cv_done_.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred);
+  int n = 0;
+  while (n < max && !finished_unreported_.empty()) {
+    tickets[n++] = finished_unreported_.front();
+    finished_unreported_.pop_front();
+  }
+  return n;
+}
+
+int Engine::result_logits(uint64_t ticket, float* out, int max_positions) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = all_.find(ticket);
+  if (it == all_.end()) return -2;
+  if (!it->second->done) return -7;
+  const int vocab = model_.config().vocab;
+  const int n = std::min(max_positions, it->second->logits_kept);
+  if (n > 0 && out) memcpy(out, it->second->logits.data(), (size_t)n * vocab * sizeof(float));
+  return n;
+}
+
+int Engine::result(uint64_t ticket, std::string* body, int* status) {
+  std::shared_ptr<Sequence> s;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = all_.find(ticket);
+    if (it == all_.end()) return -2;
+    if (!it->second->done) return -7;
+    s = it->second;
+    all_.erase(it);
+    for (auto f = finished_unreported_.begin(); f != finished_unreported_.end(); ++f)
+      if (*f == ticket) { finished_unreported_.erase(f); break; }
+  }
+  *status = s->status;
+  if (s->status != 200) {
+    *body = build_error_response(s->status, s->error_type, s->error_msg);
+    return 0;
+  }
+  // detokenise + tool-call extraction happen here, on the caller's thread, not on the scheduler
+  std::vector<int> gen(s->tokens.begin() + s->prompt_len, s->tokens.end());
+  std::vector<int> text_ids = gen;
+  if (s->finish_reason == "stop" && !text_ids.empty()) text_ids.pop_back();  // drop the stop token
+  const std::string text = decode_tokens(text_ids);
+  ParsedCompletion pc = parse_completion(text, s->tools, "call_" + std::to_string(ticket) + "_");
+  if (pc.tool_calls.empty() && pc.content.empty()) {
+    // The Task controller loops forever on an empty assistant message
+    // (state_machine.go:608/641 + checkToolCalls with zero ToolCalls): surface a terminal 4xx.
+    *status = 422;
+    *body = build_error_response(422, "empty_completion", "model produced an empty completion");
+    return 0;
+  }
+  *body = build_chat_response(ticket, model_name_, pc, s->finish_reason, s->prompt_len, gen,
+                              ms_between(s->t_submit, s->t_admit), ms_between(s->t_admit, s->t_first),
+                              ms_between(s->t_first, s->t_done));
+  return 0;
+}
+
+void Engine::cancel(uint64_t ticket) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = all_.find(ticket);
+  if (it == all_.end() || it->second->done) return;
+  it->second->cancelled = true;
+  cv_work_.notify_one();
+}
+
+void Engine::release_pages(Sequence& s) {
+  for (int p : s.pages) free_pages_.push_back(p);
+  s.pages.clear();
+}
+
+// caller holds mu_
+void Engine::finish(const std::shared_ptr<Sequence>& s, int status, const std::string& type,
+                    const std::string& msg, const std::string& finish_reason) {
+  release_pages(*s);
+  s->done = true;
+  s->status = status;
+  s->error_type = type;
+  s->error_msg = msg;
+  s->finish_reason = finish_reason;
+  s->t_done = clk::now();
+  if (status == 200) ++stats_.requests_done; else ++stats_.requests_failed;
+  finished_unreported_.push_back(s->ticket);
+}
+
+void Engine::fail_all_running(const std::string& msg) {
+  std::lock_guard<std::mutex> lk(mu_);
+  broken_ = true;
+  for (auto& s : running_) finish(s, 500, "engine_error", msg, "");
+  running_.clear();
+  while (!waiting_.empty()) { finish(waiting_.front(), 500, "engine_error", msg, ""); waiting_.pop_front(); }
+  cv_done_.notify_all();
+}
+
+// caller holds mu_
+void Engine::admit_locked() {
+  const int max_batch = model_.limits().max_batch;
+  // drop cancelled requests that never started
+  for (auto it = waiting_.begin(); it != waiting_.end();) {
+    if ((*it)->cancelled) { finish(*it, 499, "cancelled", "request cancelled", ""); it = waiting_.erase(it); }
+    else ++it;
+  }
+  while (!waiting_.empty() && (int)running_.size() < max_batch) {
+    auto& s = waiting_.front();
+    const int need = (s->prompt_len + s->sampling.max_tokens + KV_PAGE - 1) / KV_PAGE;
+    if (need > (int)free_pages_.size()) break;  // FIFO: wait for pages to come back
+    for (int i = 0; i < need; ++i) { s->pages.push_back(free_pages_.back()); free_pages_.pop_back(); }
+    s->t_admit = clk::now();
+    running_.push_back(s);
+    waiting_.pop_front();
+  }
+}
+
+void Engine::run() {
+  cudaSetDevice(model_.device());
+  while (true) {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      if (stop_) break;
+      admit_locked();
+      // cancelled while running
+      bool any_cancel = false;
+      for (auto it = running_.begin(); it != running_.end();) {
+        if ((*it)->cancelled) { finish(*it, 499, "cancelled", "request cancelled", ""); it = running_.erase(it); any_cancel = true; }
+        else ++it;
+      }
+      if (any_cancel) { cv_done_.notify_all(); admit_locked(); }
+      if (running_.empty()) {
+        cv_done_.notify_all();
+        cv_work_.wait(lk, [&] { return stop_.load() || !waiting_.empty(); });
+        continue;
+      }
+    }
+    if (!step()) std::this_thread::yield();
+  }
+}
+
+bool Engine::step() {
+  const ModelLimits& lim = model_.limits();
+  const int vocab = model_.config().vocab;
+  // running_ is only mutated by this thread
+  std::vector<Sequence*> part;   // sequences in this step
+  std::vector<int> take;
+  bool prefill = false;
+  for (auto& s : running_)
+    if ((int)s->tokens.size() - s->n_cached > 1) { prefill = true; break; }
+  int T = 0, n_blocks = 0;
+  const int blk_tokens = attn_prefill_block_tokens(model_.config().heads, model_.config().kv_heads);
+  if (prefill) {
+    int budget = lim.max_tokens;
+    for (auto& s : running_) {
+      const int pending = (int)s->tokens.size() - s->n_cached;
+      if (pending <= 1) continue;
+      if (budget == 0 || (int)part.size() == lim.max_batch) break;
+      const int t = std::min(pending, budget);
+      part.push_back(s.get());
+      take.push_back(t);
+      budget -= t;
+      T += t;
+      n_blocks += (t + blk_tokens - 1) / blk_tokens;
+    }
+  } else {
+    for (auto& s : running_) { part.push_back(s.get()); take.push_back(1); }
+    T = (int)part.size();
+  }
+  if (part.empty()) return false;
+  const int B = (int)part.size();
+  StepInput& in = model_.stage_begin(T, B, n_blocks);
+  in.decode = !prefill;
+  int row = 0, nb = 0, ns = 0, max_ctx = 0;
+  bool all_greedy = true, want_logits = false;
+  std::vector<int> sample_seq;  // index into part for each sampled row
+  for (int b = 0; b < B; ++b) {
+    Sequence& s = *part[b];
+    const int q = take[b];
+    in.q_start[b] = row;
+    in.q_len[b] = q;
+    in.ctx_len[b] = s.n_cached + q;
+    max_ctx = std::max(max_ctx, s.n_cached + q);
+    for (int i = 0; i < q; ++i) {
+      in.tok[row + i] = s.tokens[s.n_cached + i];
+      in.pos[row + i] = s.n_cached + i;
+      in.seq_of_row[row + i] = b;
+    }
+    if (prefill)
+      for (int t0 = 0; t0 < q; t0 += blk_tokens) { in.blk_seq[nb] = b; in.blk_tok0[nb] = t0; ++nb; }
+    int* pt = in.page_table + (size_t)b * lim.max_pages_per_seq;
+    const int np = std::min((int)s.pages.size(), lim.max_pages_per_seq);
+    for (int i = 0; i < np; ++i) pt[i] = s.pages[i];
+    for (int i = np; i < lim.max_pages_per_seq; ++i) pt[i] = 0;
+    if (s.n_cached + q == (int)s.tokens.size()) {  // reaches the end of known tokens: sample
+      in.sample_rows[ns] = row + q - 1;
+      const int gen_idx = (int)s.tokens.size() - s.prompt_len;
+      SampleParams& sp = in.sample_params[ns];
+      sp.temperature = s.sampling.temperature;
+      sp.top_k = s.sampling.top_k;
+      sp.top_p = s.sampling.top_p;
+      sp.seed = s.sampling.seed ^ (s.ticket * 0x9E3779B97F4A7C15ull);
+      sp.step = (uint32_t)gen_idx;
+      if (s.sampling.temperature > 0.f) all_greedy = false;
+      if (gen_idx < s.return_logits) want_logits = true;
+      sample_seq.push_back(b);
+      ++ns;
+    }
+    row += q;
+  }
+  in.n_sample = ns;
+  in.all_greedy = all_greedy;
+  in.want_logits = want_logits;
+  in.max_ctx = max_ctx;
+
+  cudaEventRecord(ev0_, model_.stream());
+  int rc = model_.forward(in);
+  cudaEventRecord(ev1_, model_.stream());
+  if (rc == 0) rc = model_.sync();
+  if (rc != 0) { fail_all_running("CUDA step failed (see stderr)"); return true; }
+  float step_ms = 0.f;
+  cudaEventElapsedTime(&step_ms, ev0_, ev1_);
+
+  const int* toks = model_.host_tokens();
+  const auto now = clk::now();
+  std::lock_guard<std::mutex> lk(mu_);
+  if (prefill) { ++stats_.prefill_steps; stats_.prefill_tokens += T; stats_.prefill_ms += step_ms; }
+  else {
+    ++stats_.decode_steps; stats_.decode_tokens += B; stats_.decode_ms += step_ms;
+    for (int b = 0; b < B; ++b) stats_.decode_ctx_tokens += part[b]->n_cached;  // keys read (excl. own)
+    if (stats_.decode_step_ms.size() < 65536) stats_.decode_step_ms.push_back(step_ms);
+  }
+  for (int b = 0; b < B; ++b) part[b]->n_cached += take[b];
+  bool any_done = false;
+  for (int i = 0; i < ns; ++i) {
+    Sequence& s = *part[sample_seq[i]];
+    int tok = toks[i];
+    const int gen_idx = (int)s.tokens.size() - s.prompt_len;
+    if (gen_idx < s.return_logits) {
+      if (s.logits.empty()) s.logits.resize((size_t)s.return_logits * vocab);
+      memcpy(s.logits.data() + (size_t)gen_idx * vocab, model_.host_logits() + (size_t)i * vocab,
+             (size_t)vocab * sizeof(float));
+      s.logits_kept = gen_idx + 1;
+    }
+    if (gen_idx < (int)s.force_tokens.size()) tok = s.force_tokens[gen_idx];
+    if (gen_idx == 0) s.t_first = now;
+    s.tokens.push_back(tok);
+    const bool stop_tok = (tok == TOK_EOT || tok == TOK_END_OF_TEXT || tok == TOK_EOM);
+    const bool at_cap = (gen_idx + 1 >= s.sampling.max_tokens);
+    if (stop_tok || at_cap) {
+      for (auto it = running_.begin(); it != running_.end(); ++it)
+        if (it->get() == &s) {
+          auto sp = *it;
+          running_.erase(it);
+          finish(sp, 200, "", "", stop_tok ? "stop" : "length");
+          break;
+        }
+      any_done = true;
+    }
+  }
+  if (any_done) cv_done_.notify_all();
+  return true;
+}
+
+std::string Engine::stats_json() {
+  std::lock_guard<std::mutex> lk(mu_);
+  const ModelConfig& c = model_.config();
+  Json j = Json::object();
+  j.set("model", Json(model_name_));
+  j.set("layers", Json(c.layers));
+  j.set("decode_steps", Json(stats_.decode_steps));
+  j.set("decode_tokens", Json(stats_.decode_tokens));
+  j.set("decode_ctx_tokens", Json(stats_.decode_ctx_tokens));
+  j.set("decode_ms", Json(stats_.decode_ms));
+  j.set("prefill_steps", Json(stats_.prefill_steps));
+  j.set("prefill_tokens", Json(stats_.prefill_tokens));
+  j.set("prefill_ms", Json(stats_.prefill_ms));
+  j.set("requests_done", Json(stats_.requests_done));
+  j.set("requests_failed", Json(stats_.requests_failed));
+  j.set("kernel_launches", Json(model_.launches()));
+  j.set("weight_bytes_per_step", Json(c.weight_bytes()));
+  j.set("kv_bytes_per_token", Json(c.kv_bytes_per_token()));
+  // bytes_step = W + sum_seq ctx*K + B*K, summed over the decode steps so far
+  const double bytes = (double)stats_.decode_steps * c.weight_bytes() +
+                       c.kv_bytes_per_token() * ((double)stats_.decode_ctx_tokens + (double)stats_.decode_tokens);
+  j.set("decode_bytes_algorithmic", Json(bytes));
+  std::vector<float> v = stats_.decode_step_ms;
+  if (!v.empty()) {
+    std::sort(v.begin(), v.end());
+    j.set("decode_step_ms_p50", Json((double)v[v.size() / 2]));
+    j.set("decode_step_ms_min", Json((double)v.front()));
+    j.set("decode_step_ms_max", Json((double)v.back()));
+  }
+  j.set("kv_pages_free", Json((int)free_pages_.size()));
+  j.set("kv_pages_total", Json(model_.limits().num_pages - 1));
+  j.set("running", Json((int)running_.size()));
+  j.set("waiting", Json((int)waiting_.size()));
+  return j.dump();
+}
+
+void Engine::stats_reset() {
+  std::lock_guard<std::mutex> lk(mu_);
+  stats_ = EngineStats();
+}
+
+}  // namespace acp

@@ -1,0 +1,91 @@
+// engine.h — continuous-batching scheduler of the local provider (one per GPU).
+//
+// Many concurrent LLMClient.SendRequest callers (Task.Reconcile goroutines in the reference,
+// acp/internal/controller/task/state_machine.go:238) submit chat requests; ONE scheduler thread
+// coalesces them into prefill / decode steps over the paged KV pool and runs Model::forward.
+// Multi-producer (submit/cancel/wait from any thread), single consumer (the scheduler).
+#pragma once
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+#include "chat.h"
+#include "model.h"
+
+namespace acp {
+
+struct Sequence {
+  uint64_t ticket = 0;
+  std::vector<ToolDef> tools;
+  SamplingParams sampling;
+  std::vector<int> force_tokens;
+  int return_logits = 0;
+  std::vector<int> tokens;   // prompt + generated
+  int prompt_len = 0;
+  int n_cached = 0;          // tokens whose K/V are in the cache
+  std::vector<int> pages;
+  std::atomic<bool> cancelled{false};
+  bool done = false, reported = false;
+  int status = 0;            // HTTP-like, valid when done
+  std::string error_type, error_msg, finish_reason;
+  std::vector<float> logits; // return_logits x vocab
+  int logits_kept = 0;
+  std::chrono::steady_clock::time_point t_submit, t_admit, t_first, t_done;
+};
+
+struct EngineStats {
+  long long decode_steps = 0, decode_tokens = 0, decode_ctx_tokens = 0;
+  long long prefill_steps = 0, prefill_tokens = 0;
+  double decode_ms = 0, prefill_ms = 0;
+  long long requests_done = 0, requests_failed = 0;
+  std::vector<float> decode_step_ms;
+};
+
+class Engine {
+ public:
+  Engine() = default;
+  ~Engine();
+  int init(const char* config_json);
+  int submit(const char* json, size_t len, uint64_t* ticket);
+  int wait(uint64_t ticket, int timeout_ms);
+  int poll(uint64_t* tickets, int max, int timeout_ms);
+  int result(uint64_t ticket, std::string* body, int* status);
+  int result_logits(uint64_t ticket, float* out, int max_positions);
+  void cancel(uint64_t ticket);
+  std::string stats_json();
+  void stats_reset();
+  void shutdown();
+
+ private:
+  void run();
+  void admit_locked();
+  bool step();  // returns false when there was nothing to do
+  void finish(const std::shared_ptr<Sequence>& s, int status, const std::string& type,
+              const std::string& msg, const std::string& finish_reason);
+  void fail_all_running(const std::string& msg);
+  void release_pages(Sequence& s);
+
+  Model model_;
+  std::string model_name_;
+  std::thread thread_;
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::deque<std::shared_ptr<Sequence>> waiting_;
+  std::vector<std::shared_ptr<Sequence>> running_;
+  std::unordered_map<uint64_t, std::shared_ptr<Sequence>> all_;
+  std::deque<uint64_t> finished_unreported_;
+  std::vector<int> free_pages_;
+  std::atomic<bool> stop_{false};
+  bool broken_ = false;
+  uint64_t next_ticket_ = 1;
+  EngineStats stats_;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  int max_ctx_tokens_ = 0;
+};
+
+}  // namespace acp

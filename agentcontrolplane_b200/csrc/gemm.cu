@@ -53,9 +53,9 @@ int tma_make_weight(TmaMaps* m, const void* base, uint64_t rows, uint64_t cols) 
 }
 int tma_make_act(TmaMaps* m, const void* base, uint64_t rows, uint64_t cols) {
   for (int i = 0; i < 5; ++i) {
-    uint32_t box = 16u << i;
-    // a box may not exceed the tensor: clamp (small buffers never use the large tiles)
-    if (box > rows) box = (uint32_t)rows;
+    // NOTE: the box is never clamped to the tensor: the producer always expects the full
+    // BN x 128 bytes per stage and TMA zero-fills rows past the end of the tensor.
+    const uint32_t box = 16u << i;
     int rc = tma_encode_2d_bf16(&m->x[i], base, rows, cols, box);
     if (rc != 0) return rc;
   }

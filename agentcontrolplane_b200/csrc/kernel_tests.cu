@@ -37,7 +37,10 @@ extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int 
   if (gemm_setup_attributes() != 0) return -5;
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   DevBuf dw, dx, dout, dval, didx, dflush;
-  if (dw.alloc((size_t)M * K * 2) || dx.alloc((size_t)N * K * 2)) return -5;
+  // activation rows are padded to the largest N tile like the engine's buffers (zero rows)
+  const int n_pad = ((N + 255) / 256) * 256;
+  if (dw.alloc((size_t)M * K * 2) || dx.alloc((size_t)n_pad * K * 2)) return -5;
+  ACP_CUDA_CHECK(cudaMemset(dx.p, 0, (size_t)n_pad * K * 2));
   ACP_CUDA_CHECK(cudaMemcpy(dw.p, w, (size_t)M * K * 2, cudaMemcpyHostToDevice));
   ACP_CUDA_CHECK(cudaMemcpy(dx.p, x, (size_t)N * K * 2, cudaMemcpyHostToDevice));
   size_t out_bytes = 0;
@@ -51,7 +54,7 @@ extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int 
   }
   TmaMaps mw, mx;
   if (tma_make_weight(&mw, dw.p, M, K) != 0) return -5;
-  if (tma_make_act(&mx, dx.p, N, K) != 0) return -5;
+  if (tma_make_act(&mx, dx.p, n_pad, K) != 0) return -5;
   GemmLaunch g;
   g.w = &mw.w; g.x = &mx; g.M = M; g.N = N; g.K = K; g.splits = splits; g.epi = epi;
   g.ld = M; g.n_cap = N;

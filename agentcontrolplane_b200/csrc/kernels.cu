@@ -1,0 +1,415 @@
+// kernels.cu — HBM-bound kernels: embedding gather, (residual add +) RMSNorm, RoPE + paged-KV
+// scatter, SwiGLU, arg-max finish, sampling, synthetic weight generation.
+// All vectorised (8/16-byte accesses), warp-shuffle reductions, bf16 round-to-nearest-even at
+// exactly the points listed in oracle/llama_oracle.py.
+#include "kernels.cuh"
+#include "common.cuh"
+
+namespace acp {
+
+#define ACP_LAUNCH_CHECK(name)                                                         \
+  do {                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess) {                                                           \
+      fprintf(stderr, "[acp_infer] launch %s failed: %s\n", name, cudaGetErrorString(_e)); \
+      return -5;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// Reading 4 consecutive GEMM outputs (columns m..m+3 of row t) as bf16-rounded fp32.
+// ---------------------------------------------------------------------------------
+struct GemmOutDev {
+  const void* ptr;
+  int splits, n_cap, ld;
+};
+static inline GemmOutDev to_dev(const GemmOut& g) { return GemmOutDev{g.ptr, g.splits, g.n_cap, g.ld}; }
+
+ACP_DEVINL void gemm_out_load4(const GemmOutDev& g, int t, int m, float (&v)[4]) {
+  if (g.splits == 0) {
+    const uint2 raw = *reinterpret_cast<const uint2*>((const __nv_bfloat16*)g.ptr + (size_t)t * g.ld + m);
+    v[0] = bf16_lo(raw.x); v[1] = bf16_hi(raw.x); v[2] = bf16_lo(raw.y); v[3] = bf16_hi(raw.y);
+  } else {
+    const float* p = (const float*)g.ptr + (size_t)t * g.ld + m;
+    float4 acc = *reinterpret_cast<const float4*>(p);
+    for (int s = 1; s < g.splits; ++s) {  // fixed order => deterministic
+      const float4 q = *reinterpret_cast<const float4*>(p + (size_t)s * g.n_cap * g.ld);
+      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    }
+    v[0] = bf16_round(acc.x); v[1] = bf16_round(acc.y); v[2] = bf16_round(acc.z); v[3] = bf16_round(acc.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// embedding gather
+// ---------------------------------------------------------------------------------
+__global__ void embed_kernel(const int* __restrict__ tok, const __nv_bfloat16* __restrict__ E,
+                             __nv_bfloat16* __restrict__ x, int hidden) {
+  const int t = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(E + (size_t)tok[t] * hidden);
+  uint4* dst = reinterpret_cast<uint4*>(x + (size_t)t * hidden);
+  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
+}
+int launch_embed(const int* tok, const __nv_bfloat16* E, __nv_bfloat16* x, int T, int hidden,
+                 cudaStream_t s) {
+  if (T <= 0) return 0;
+  embed_kernel<<<T, 128, 0, s>>>(tok, E, x, hidden);
+  ACP_LAUNCH_CHECK("embed");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// (residual add +) RMSNorm.  One CTA per output row, row staged in shared memory as fp32.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+add_rmsnorm_kernel(__nv_bfloat16* __restrict__ x, GemmOutDev add, const __nv_bfloat16* __restrict__ gain,
+                   __nv_bfloat16* __restrict__ xn, const int* __restrict__ row_map, int hidden,
+                   float eps) {
+  extern __shared__ float row[];
+  __shared__ float red[8];
+  const int out_row = blockIdx.x;
+  const int src_row = row_map ? row_map[out_row] : out_row;
+  __nv_bfloat16* xr = x + (size_t)src_row * hidden;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 4; i < hidden; i += blockDim.x * 4) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(xr + i);
+    float v[4] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y)};
+    if (add.ptr != nullptr) {
+      float a[4];
+      gemm_out_load4(add, src_row, i, a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = bf16_round(v[j] + a[j]);
+      if (row_map == nullptr) {
+        uint2 packed;
+        packed.x = pack_bf16x2(v[0], v[1]);
+        packed.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(xr + i) = packed;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { row[i + j] = v[j]; ss += v[j] * v[j]; }
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+  const float rstd = 1.0f / sqrtf(tot / (float)hidden + eps);
+  __nv_bfloat16* o = xn + (size_t)out_row * hidden;
+  for (int i = threadIdx.x * 4; i < hidden; i += blockDim.x * 4) {
+    const uint2 graw = *reinterpret_cast<const uint2*>(gain + i);
+    const float g[4] = {bf16_lo(graw.x), bf16_hi(graw.x), bf16_lo(graw.y), bf16_hi(graw.y)};
+    float y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = g[j] * bf16_round(row[i + j] * rstd);
+    uint2 packed;
+    packed.x = pack_bf16x2(y[0], y[1]);
+    packed.y = pack_bf16x2(y[2], y[3]);
+    *reinterpret_cast<uint2*>(o + i) = packed;
+  }
+}
+int launch_add_rmsnorm(__nv_bfloat16* x, const GemmOut& add, const __nv_bfloat16* gain,
+                       __nv_bfloat16* xn, const int* row_map, int T, int hidden, float eps,
+                       cudaStream_t s) {
+  if (T <= 0) return 0;
+  add_rmsnorm_kernel<<<T, 256, hidden * sizeof(float), s>>>(x, to_dev(add), gain, xn, row_map,
+                                                              hidden, eps);
+  ACP_LAUNCH_CHECK("add_rmsnorm");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// RoPE + paged-KV scatter.  One CTA per token row; each thread handles 4 consecutive "i"
+// (frequency indices) of one head: elements (i, i+64) of the 128-wide head vector.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rope_kv_kernel(GemmOutDev qkv, const int* __restrict__ pos, const int* __restrict__ seq_of_row,
+               const int* __restrict__ page_table, int max_pages, const float* __restrict__ cos_tab,
+               const float* __restrict__ sin_tab, __nv_bfloat16* __restrict__ qbuf,
+               __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache, int heads,
+               int kv_heads) {
+  const int t = blockIdx.x;
+  const int p = pos[t];
+  const int seq = seq_of_row[t];
+  const int page = page_table[(size_t)seq * max_pages + p / KV_PAGE];
+  const int q_dim = heads * HEAD_DIM, kv_dim = kv_heads * HEAD_DIM;
+  const float* ct = cos_tab + (size_t)p * (HEAD_DIM / 2);
+  const float* st = sin_tab + (size_t)p * (HEAD_DIM / 2);
+  // rotated heads: q heads then k heads; 16 threads per head (4 i's each)
+  const int n_rot = heads + kv_heads;
+  for (int w = threadIdx.x; w < n_rot * 16; w += blockDim.x) {
+    const int head = w >> 4, i0 = (w & 15) * 4;
+    const int col = head * HEAD_DIM;  // q heads and k heads are contiguous in the qkv row
+    float a[4], b[4];
+    gemm_out_load4(qkv, t, col + i0, a);
+    gemm_out_load4(qkv, t, col + 64 + i0, b);
+    const float4 c = *reinterpret_cast<const float4*>(ct + i0);
+    const float4 s = *reinterpret_cast<const float4*>(st + i0);
+    const float cc[4] = {c.x, c.y, c.z, c.w}, sn[4] = {s.x, s.y, s.z, s.w};
+    float lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // explicit rn ops: no FMA contraction, so the oracle's numpy expression matches bit for bit
+      lo[j] = __fsub_rn(__fmul_rn(a[j], cc[j]), __fmul_rn(b[j], sn[j]));
+      hi[j] = __fadd_rn(__fmul_rn(b[j], cc[j]), __fmul_rn(a[j], sn[j]));
+    }
+    uint2 plo, phi;
+    plo.x = pack_bf16x2(lo[0], lo[1]); plo.y = pack_bf16x2(lo[2], lo[3]);
+    phi.x = pack_bf16x2(hi[0], hi[1]); phi.y = pack_bf16x2(hi[2], hi[3]);
+    __nv_bfloat16* dst;
+    if (head < heads) {
+      dst = qbuf + (size_t)t * q_dim + head * HEAD_DIM;
+    } else {
+      const int kh = head - heads;
+      dst = k_cache + (((size_t)page * kv_heads + kh) * KV_PAGE + (p % KV_PAGE)) * HEAD_DIM;
+    }
+    *reinterpret_cast<uint2*>(dst + i0) = plo;
+    *reinterpret_cast<uint2*>(dst + 64 + i0) = phi;
+  }
+  // v: plain copy, 4 elements per thread
+  for (int w = threadIdx.x; w < kv_dim / 4; w += blockDim.x) {
+    const int e = w * 4;
+    float v[4];
+    gemm_out_load4(qkv, t, q_dim + kv_dim + e, v);
+    const int kh = e / HEAD_DIM, d = e % HEAD_DIM;
+    uint2 pv;
+    pv.x = pack_bf16x2(v[0], v[1]); pv.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(v_cache + (((size_t)page * kv_heads + kh) * KV_PAGE + (p % KV_PAGE)) * HEAD_DIM + d) = pv;
+  }
+}
+int launch_rope_kv(const RopeKvArgs& a, cudaStream_t s) {
+  if (a.T <= 0) return 0;
+  rope_kv_kernel<<<a.T, 256, 0, s>>>(to_dev(a.qkv), a.pos, a.seq_of_row, a.page_table, a.max_pages,
+                                     a.cos_tab, a.sin_tab, a.qbuf, a.k_cache, a.v_cache, a.heads,
+                                     a.kv_heads);
+  ACP_LAUNCH_CHECK("rope_kv");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// SwiGLU
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+swiglu_kernel(GemmOutDev gu, __nv_bfloat16* __restrict__ h, int ffn) {
+  const int t = blockIdx.y;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j >= ffn) return;
+  float g[4], u[4], o[4];
+  gemm_out_load4(gu, t, j, g);
+  gemm_out_load4(gu, t, ffn + j, u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float act = bf16_round(g[k] / (1.0f + expf(-g[k])));
+    o[k] = act * u[k];
+  }
+  uint2 packed;
+  packed.x = pack_bf16x2(o[0], o[1]);
+  packed.y = pack_bf16x2(o[2], o[3]);
+  *reinterpret_cast<uint2*>(h + (size_t)t * ffn + j) = packed;
+}
+int launch_swiglu(const GemmOut& gu, __nv_bfloat16* h, int T, int ffn, cudaStream_t s) {
+  if (T <= 0) return 0;
+  dim3 grid((ffn / 4 + 255) / 256, T);
+  swiglu_kernel<<<grid, 256, 0, s>>>(to_dev(gu), h, ffn);
+  ACP_LAUNCH_CHECK("swiglu");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// arg-max finish: reduce the per-m-tile candidates of the fused LM-head epilogue
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+argmax_finish_kernel(const float* __restrict__ tile_val, const int* __restrict__ tile_idx,
+                     int m_tiles, int* __restrict__ token_out, float* __restrict__ val_out) {
+  __shared__ float sv[4];
+  __shared__ int si[4];
+  const int n = blockIdx.x;
+  float v = -INFINITY;
+  int idx = 0x7fffffff;
+  for (int t = threadIdx.x; t < m_tiles; t += blockDim.x) {
+    const float ov = tile_val[(size_t)n * m_tiles + t];
+    const int oi = tile_idx[(size_t)n * m_tiles + t];
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 4; ++w)
+      if (sv[w] > v || (sv[w] == v && si[w] < idx)) { v = sv[w]; idx = si[w]; }
+    token_out[n] = idx;
+    if (val_out) val_out[n] = v;
+  }
+}
+int launch_argmax_finish(const float* tile_val, const int* tile_idx, int m_tiles, int N,
+                         int* token_out, float* val_out, cudaStream_t s) {
+  if (N <= 0) return 0;
+  argmax_finish_kernel<<<N, 128, 0, s>>>(tile_val, tile_idx, m_tiles, token_out, val_out);
+  ACP_LAUNCH_CHECK("argmax_finish");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Sampling: temperature / top-k / top-p on fp32 logits, one CTA per row.
+//   1. m = max logit; weights w_i = exp((l_i - m)/T)
+//   2. top-k: threshold = k-th largest logit, found by bisection on the value range
+//   3. top-p: smallest threshold tau such that sum_{w_i >= tau} w_i >= top_p * Z (bisection)
+//   4. inverse-CDF walk in index order over the kept set with a counter-based uniform.
+// Everything is a deterministic function of (logits, params): reductions are fixed-shape.
+// ---------------------------------------------------------------------------------
+ACP_DEVINL float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+ACP_DEVINL float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, red[w]);
+  return t;
+}
+ACP_DEVINL uint64_t splitmix64(uint64_t z) {
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+
+__global__ void __launch_bounds__(1024)
+sample_kernel(const float* __restrict__ logits, int V, const SampleParams* __restrict__ params,
+              int* __restrict__ token_out) {
+  __shared__ float red[32];
+  __shared__ float s_prefix[1024];
+  const int n = blockIdx.x;
+  const SampleParams sp = params[n];
+  const float* l = logits + (size_t)n * V;
+  float lmax = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) lmax = fmaxf(lmax, l[i]);
+  lmax = block_max(lmax, red);
+  if (sp.temperature <= 0.f) {  // greedy: lowest index among maxima
+    int best = 0x7fffffff;
+    for (int i = threadIdx.x; i < V; i += blockDim.x)
+      if (l[i] == lmax) best = min(best, i);
+    best = -(int)block_max((float)(-best), red);  // V < 2^24 so exact in fp32
+    if (threadIdx.x == 0) token_out[n] = best;
+    return;
+  }
+  const float invT = 1.0f / sp.temperature;
+  float lo_thr = -INFINITY;  // keep logits >= lo_thr
+  if (sp.top_k > 0 && sp.top_k < V) {
+    float lo = lmax - 80.f * sp.temperature - 1.f, hi = lmax;
+    // smallest interval [lo, hi] with count(l >= hi) <= k: 40 bisection steps
+    for (int it = 0; it < 40; ++it) {
+      const float mid = 0.5f * (lo + hi);
+      float c = 0.f;
+      for (int i = threadIdx.x; i < V; i += blockDim.x) c += (l[i] >= mid) ? 1.f : 0.f;
+      c = block_sum(c, red);
+      if (c > (float)sp.top_k) lo = mid; else hi = mid;
+    }
+    lo_thr = hi;
+  }
+  float z = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x)
+    if (l[i] >= lo_thr) z += expf((l[i] - lmax) * invT);
+  z = block_sum(z, red);
+  if (sp.top_p < 1.0f) {
+    float lo = fmaxf(lo_thr, lmax - 80.f * sp.temperature - 1.f), hi = lmax;
+    for (int it = 0; it < 40; ++it) {
+      const float mid = 0.5f * (lo + hi);
+      float m = 0.f;
+      for (int i = threadIdx.x; i < V; i += blockDim.x)
+        if (l[i] >= mid && l[i] >= lo_thr) m += expf((l[i] - lmax) * invT);
+      m = block_sum(m, red);
+      if (m >= sp.top_p * z) lo = mid; else hi = mid;
+    }
+    lo_thr = fmaxf(lo_thr, lo);
+    z = 0.f;
+    for (int i = threadIdx.x; i < V; i += blockDim.x)
+      if (l[i] >= lo_thr) z += expf((l[i] - lmax) * invT);
+    z = block_sum(z, red);
+  }
+  // uniform in [0,1) from (seed, step)
+  const uint64_t r = splitmix64(sp.seed * 0x9E3779B97F4A7C15ull + (uint64_t)sp.step + 1ull);
+  const float u = (float)(r >> 40) * (1.0f / 16777216.0f);
+  const float target = u * z;
+  // contiguous chunk per thread so the CDF walk is in index order
+  const int chunk = (V + blockDim.x - 1) / blockDim.x;
+  const int b = threadIdx.x * chunk, e = min(V, b + chunk);
+  float mine = 0.f;
+  for (int i = b; i < e; ++i)
+    if (l[i] >= lo_thr) mine += expf((l[i] - lmax) * invT);
+  s_prefix[threadIdx.x] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    int chosen_thread = -1;
+    float base = 0.f;
+    for (int t = 0; t < (int)blockDim.x; ++t) {
+      if (acc + s_prefix[t] > target && s_prefix[t] > 0.f) { chosen_thread = t; base = acc; break; }
+      acc += s_prefix[t];
+    }
+    int tok = -1;
+    if (chosen_thread >= 0) {
+      const int bb = chosen_thread * chunk, ee = min(V, bb + chunk);
+      float a2 = base;
+      for (int i = bb; i < ee; ++i) {
+        if (l[i] >= lo_thr) {
+          a2 += expf((l[i] - lmax) * invT);
+          tok = i;  // last kept index seen; stop once the CDF passes the target
+          if (a2 > target) break;
+        }
+      }
+    }
+    if (tok < 0) {  // numerical corner (target == z): fall back to the arg-max
+      for (int i = 0; i < V; ++i) if (l[i] == lmax) { tok = i; break; }
+    }
+    token_out[n] = tok;
+  }
+}
+int launch_sample(const float* logits, int V, int N, const SampleParams* params_dev,
+                  int* token_out, cudaStream_t s) {
+  if (N <= 0) return 0;
+  sample_kernel<<<N, 1024, 0, s>>>(logits, V, params_dev, token_out);
+  ACP_LAUNCH_CHECK("sample");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// synthetic weights (bit-identical to oracle/synth.py)
+// ---------------------------------------------------------------------------------
+__global__ void synth_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n, uint64_t base,
+                                    float scale, int plus_one) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint64_t z = splitmix64(base + (uint64_t)i * 0xD1B54A32D192ED03ull);
+    const int s = (int)(z & 0xffff) + (int)((z >> 16) & 0xffff) + (int)((z >> 32) & 0xffff) +
+                  (int)(z >> 48) - 131070;
+    float w = __fmul_rn((float)s, scale);
+    if (plus_one) w = __fadd_rn(w, 1.0f);
+    out[i] = __float2bfloat16_rn(w);
+  }
+}
+int launch_synth(__nv_bfloat16* out, size_t n, uint64_t seed, uint32_t tid, double std,
+                 int plus_one, cudaStream_t s) {
+  if (n == 0) return 0;
+  const uint64_t base = seed + (uint64_t)tid * 0x9E3779B97F4A7C15ull;
+  const float scale = (float)(std / 37837.22671196048);
+  synth_weight_kernel<<<148 * 8, 256, 0, s>>>(out, n, base, scale, plus_one);
+  ACP_LAUNCH_CHECK("synth");
+  return 0;
+}
+
+}  // namespace acp

@@ -1,0 +1,74 @@
+// kernels.cuh — host launchers of the HBM-bound (non-GEMM) kernels of the decode engine.
+// Every kernel that consumes a GEMM result accepts it either as bf16 [T][M] (prefill, split-K off)
+// or as `splits` fp32 partial planes [splits][n_cap][M] which it sums in index order before the
+// bf16 rounding — the deterministic split-K reduction (see gemm_tcgen05.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace acp {
+
+// A GEMM result as seen by its consumer.
+struct GemmOut {
+  const void* ptr = nullptr;  // bf16* when splits == 0, else float* partial planes
+  int splits = 0;             // 0 => bf16 [T][ld]; >=1 => fp32 [splits][n_cap][ld]
+  int n_cap = 0;
+  int ld = 0;
+};
+
+// x[t][:] = E[tok[t]][:]
+int launch_embed(const int* tok, const __nv_bfloat16* E, __nv_bfloat16* x, int T, int hidden,
+                 cudaStream_t s);
+
+// (optional) x = bf16(x + bf16(gemm_out)); xn[i] = bf16(g * bf16(x[row] * rstd)).
+// row_map == nullptr: row i <- i for i < T, residual x is updated in place.
+// row_map != nullptr: output row i is computed from source row row_map[i] (i < T outputs); the
+//                     residual is NOT written back (used for the final norm on sampled rows).
+int launch_add_rmsnorm(__nv_bfloat16* x, const GemmOut& add, const __nv_bfloat16* gain,
+                       __nv_bfloat16* xn, const int* row_map, int T, int hidden, float eps,
+                       cudaStream_t s);
+
+// RoPE (rotate-half, table driven) on q and k, then scatter k,v into the paged KV cache and q
+// into qbuf.  qkv row layout: [q_dim | kv_dim (k) | kv_dim (v)].
+struct RopeKvArgs {
+  GemmOut qkv;
+  const int* pos;        // [T] absolute position of each row
+  const int* seq_of_row; // [T] index into page_table rows
+  const int* page_table; // [num_seqs][max_pages]
+  int max_pages;
+  const float* cos_tab;  // [max_pos][64]
+  const float* sin_tab;
+  __nv_bfloat16* qbuf;   // [T][q_dim]
+  __nv_bfloat16* k_cache;  // layer base: [num_pages][kv_heads][PAGE][128]
+  __nv_bfloat16* v_cache;
+  int T, heads, kv_heads;
+};
+int launch_rope_kv(const RopeKvArgs& a, cudaStream_t s);
+
+// h[t][j] = bf16( bf16(silu(g)) * u ), g = gu[t][j], u = gu[t][ffn + j]
+int launch_swiglu(const GemmOut& gu, __nv_bfloat16* h, int T, int ffn, cudaStream_t s);
+
+// token[n] = argmax over m-tiles of the fused GEMM arg-max epilogue (lowest index on ties)
+int launch_argmax_finish(const float* tile_val, const int* tile_idx, int m_tiles, int N,
+                         int* token_out, float* val_out, cudaStream_t s);
+
+// Non-greedy sampling on fp32 logits [N][V]: temperature, top-k, top-p, deterministic counter RNG.
+struct SampleParams {  // per row
+  float temperature;   // <= 0 => greedy
+  int top_k;           // <= 0 => off
+  float top_p;         // >= 1 => off
+  uint64_t seed;       // request seed
+  uint32_t step;       // decode step index (RNG counter)
+};
+int launch_sample(const float* logits, int V, int N, const SampleParams* params_dev,
+                  int* token_out, cudaStream_t s);
+
+// Seeded synthetic tensor (bit-identical to oracle/synth.py)
+int launch_synth(__nv_bfloat16* out, size_t n, uint64_t seed, uint32_t tid, double std,
+                 int plus_one, cudaStream_t s);
+
+constexpr int KV_PAGE = 32;   // tokens per KV page
+constexpr int HEAD_DIM = 128;
+
+}  // namespace acp

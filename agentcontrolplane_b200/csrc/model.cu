@@ -1,0 +1,358 @@
+// model.cu — weights in HBM, activation buffers, and the forward pass of one engine step.
+//
+// Per step (T token rows, B sequences):
+//   embed -> [ rmsnorm -> QKV GEMM -> RoPE + KV scatter -> paged attention -> O GEMM ->
+//              add+rmsnorm -> gate/up GEMM -> SwiGLU -> down GEMM -> add+rmsnorm ] x L
+//   -> final norm on the sampled rows only -> LM-head GEMM with fused arg-max -> token ids.
+// Decode steps (T <= 256) run the GEMMs split-K with fp32 partial planes reduced in fixed order by
+// the consumer kernels; prefill steps write bf16 directly.  bf16 rounding points are exactly the
+// ones listed in oracle/llama_oracle.py.
+#include "model.h"
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace acp {
+
+bool model_preset(const std::string& name, ModelConfig* c) {
+  ModelConfig m;
+  m.name = name;
+  if (name == "tiny") { m.hidden = 512; m.layers = 2; m.heads = 4; m.kv_heads = 1; m.ffn = 1024; }
+  else if (name == "tiny-g2") { m.hidden = 512; m.layers = 3; m.heads = 4; m.kv_heads = 2; m.ffn = 1536; }
+  else if (name == "llama-3-8b-l2") { m.hidden = 4096; m.layers = 2; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; }
+  else if (name == "llama-3-8b") { m.hidden = 4096; m.layers = 32; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; }
+  else if (name == "llama-3-70b") { m.hidden = 8192; m.layers = 80; m.heads = 64; m.kv_heads = 8; m.ffn = 28672; }
+  else return false;
+  *c = m;
+  return true;
+}
+
+#define ACP_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+Model::~Model() {
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (void* p : allocs_) cudaFree(p);
+  if (h_ints_) cudaFreeHost(h_ints_);
+  if (h_sparams_) cudaFreeHost(h_sparams_);
+  if (h_tokens_) cudaFreeHost(h_tokens_);
+  if (h_logits_) cudaFreeHost(h_logits_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+static int dmalloc(std::vector<void*>& allocs, void** p, size_t bytes, bool zero = false) {
+  cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[acp_infer] cudaMalloc(%zu MiB) failed: %s\n", bytes >> 20, cudaGetErrorString(e));
+    return -4;
+  }
+  allocs.push_back(*p);
+  if (zero) {
+    e = cudaMemset(*p, 0, bytes ? bytes : 16);
+    if (e != cudaSuccess) return -5;
+  }
+  return 0;
+}
+template <class T>
+static int dmalloc_t(std::vector<void*>& allocs, T** p, size_t count, bool zero = false) {
+  return dmalloc(allocs, (void**)p, count * sizeof(T), zero);
+}
+
+int Model::choose_splits(int M, int K, int N) const {
+  if (N > 256) return 1;
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int nkb = (K + GEMM_BK - 1) / GEMM_BK;
+  int s = (lim_.splitk_target_ctas + m_tiles / 2) / m_tiles;
+  if (s < 1) s = 1;
+  const int max_s = nkb / 4 > 0 ? nkb / 4 : 1;  // at least 4 k-blocks per split
+  if (s > max_s) s = max_s;
+  if (s > 16) s = 16;
+  return s;
+}
+
+int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device) {
+  cfg_ = cfg;
+  lim_ = lim;
+  device_ = device;
+  if (cfg.hidden % 64 || cfg.ffn % 64 || cfg.vocab % 8 || cfg.heads % cfg.kv_heads) {
+    fprintf(stderr, "[acp_infer] unsupported model dims\n");
+    return -1;
+  }
+  const char* env = getenv("ACP_SPLITK_TARGET");
+  if (env) lim_.splitk_target_ctas = atoi(env);
+  ACP_CUDA_CHECK(cudaSetDevice(device));
+  ACP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  ACP_TRY(tma_init());
+  ACP_TRY(gemm_setup_attributes());
+  ACP_TRY(attn_setup_attributes());
+  ACP_TRY(alloc_all());
+  ACP_TRY(gen_weights());
+  ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  return 0;
+}
+
+int Model::alloc_all() {
+  const ModelConfig& c = cfg_;
+  const size_t H = c.hidden;
+  const int T = ((lim_.max_tokens + 255) / 256) * 256;
+  const int Bp = ((lim_.max_batch + 255) / 256) * 256;
+  layers_.resize(c.layers);
+  const size_t kv_elems = (size_t)lim_.num_pages * c.kv_heads * KV_PAGE * HEAD_DIM;
+  for (int l = 0; l < c.layers; ++l) {
+    Layer& L = layers_[l];
+    ACP_TRY(dmalloc_t(allocs_, &L.wqkv, (size_t)c.qkv_dim() * H));
+    ACP_TRY(dmalloc_t(allocs_, &L.wo, H * c.q_dim()));
+    ACP_TRY(dmalloc_t(allocs_, &L.wgu, (size_t)2 * c.ffn * H));
+    ACP_TRY(dmalloc_t(allocs_, &L.wdown, H * c.ffn));
+    ACP_TRY(dmalloc_t(allocs_, &L.attn_norm, H));
+    ACP_TRY(dmalloc_t(allocs_, &L.ffn_norm, H));
+    ACP_TRY(dmalloc_t(allocs_, &L.k_cache, kv_elems, true));
+    ACP_TRY(dmalloc_t(allocs_, &L.v_cache, kv_elems, true));
+    ACP_TRY(tma_make_weight(&L.m_qkv, L.wqkv, c.qkv_dim(), H));
+    ACP_TRY(tma_make_weight(&L.m_o, L.wo, H, c.q_dim()));
+    ACP_TRY(tma_make_weight(&L.m_gu, L.wgu, 2 * c.ffn, H));
+    ACP_TRY(tma_make_weight(&L.m_down, L.wdown, H, c.ffn));
+    ACP_TRY(attn_make_kv_map(&L.tm_k, L.k_cache, lim_.num_pages, c.kv_heads));
+    ACP_TRY(attn_make_kv_map(&L.tm_v, L.v_cache, lim_.num_pages, c.kv_heads));
+  }
+  ACP_TRY(dmalloc_t(allocs_, &embed_, (size_t)c.vocab * H));
+  ACP_TRY(dmalloc_t(allocs_, &lm_head_, (size_t)c.vocab * H));
+  ACP_TRY(dmalloc_t(allocs_, &final_norm_, H));
+  ACP_TRY(tma_make_weight(&m_lm_, lm_head_, c.vocab, H));
+  ACP_TRY(dmalloc_t(allocs_, &cos_, (size_t)c.max_pos * 64));
+  ACP_TRY(dmalloc_t(allocs_, &sin_, (size_t)c.max_pos * 64));
+  // activations (rows padded to the largest N tile, zero initialised)
+  ACP_TRY(dmalloc_t(allocs_, &x_, (size_t)T * H, true));
+  ACP_TRY(dmalloc_t(allocs_, &xn_, (size_t)T * H, true));
+  ACP_TRY(dmalloc_t(allocs_, &qbuf_, (size_t)T * c.q_dim(), true));
+  ACP_TRY(dmalloc_t(allocs_, &attn_, (size_t)T * c.q_dim(), true));
+  ACP_TRY(dmalloc_t(allocs_, &h_, (size_t)T * c.ffn, true));
+  ACP_TRY(dmalloc_t(allocs_, &xs_, (size_t)Bp * H, true));
+  int max_m = c.qkv_dim();
+  if (2 * c.ffn > max_m) max_m = 2 * c.ffn;
+  if (c.hidden > max_m) max_m = c.hidden;
+  ACP_TRY(dmalloc_t(allocs_, &gemm_bf16_, (size_t)T * max_m, true));
+  ACP_TRY(tma_make_act(&m_xn_, xn_, T, H));
+  ACP_TRY(tma_make_act(&m_attn_, attn_, T, c.q_dim()));
+  ACP_TRY(tma_make_act(&m_h_, h_, T, c.ffn));
+  ACP_TRY(tma_make_act(&m_xs_, xs_, Bp, H));
+  // split-K workspace: worst case over the four GEMMs at N = 256 rows
+  size_t ws = 0;
+  const int shapes[4][2] = {{c.qkv_dim(), c.hidden}, {c.hidden, c.q_dim()}, {2 * c.ffn, c.hidden}, {c.hidden, c.ffn}};
+  for (auto& s : shapes) {
+    size_t b = (size_t)choose_splits(s[0], s[1], 256) * 256 * s[0] * sizeof(float);
+    for (int n = 16; n <= 256; n *= 2) {
+      size_t bb = (size_t)choose_splits(s[0], s[1], n) * n * s[0] * sizeof(float);
+      if (bb > b) b = bb;
+    }
+    if (b > ws) ws = b;
+  }
+  ws_bytes_ = ws;
+  ACP_TRY(dmalloc(allocs_, (void**)&ws_, ws_bytes_));
+  const int m_tiles_lm = (c.vocab + GEMM_BM - 1) / GEMM_BM;
+  ACP_TRY(dmalloc_t(allocs_, &amax_val_, (size_t)Bp * m_tiles_lm));
+  ACP_TRY(dmalloc_t(allocs_, &amax_idx_, (size_t)Bp * m_tiles_lm));
+  ACP_TRY(dmalloc_t(allocs_, &logits_, (size_t)lim_.max_batch * c.vocab));
+  max_splits_ = (lim_.max_pages_per_seq * KV_PAGE + lim_.split_tokens - 1) / lim_.split_tokens;
+  ACP_TRY(dmalloc_t(allocs_, &attn_ws_o_, (size_t)lim_.max_batch * c.heads * max_splits_ * HEAD_DIM));
+  ACP_TRY(dmalloc_t(allocs_, &attn_ws_m_, (size_t)lim_.max_batch * c.heads * max_splits_));
+  ACP_TRY(dmalloc_t(allocs_, &attn_ws_l_, (size_t)lim_.max_batch * c.heads * max_splits_));
+  // step staging
+  ints_cap_ = (size_t)5 * lim_.max_tokens + (size_t)4 * lim_.max_batch +
+              (size_t)lim_.max_batch * lim_.max_pages_per_seq + 64;
+  ACP_TRY(dmalloc_t(allocs_, &d_ints_, ints_cap_));
+  ACP_CUDA_CHECK(cudaMallocHost((void**)&h_ints_, ints_cap_ * sizeof(int)));
+  ACP_TRY(dmalloc_t(allocs_, &d_sparams_, (size_t)lim_.max_batch));
+  ACP_CUDA_CHECK(cudaMallocHost((void**)&h_sparams_, lim_.max_batch * sizeof(SampleParams)));
+  ACP_TRY(dmalloc_t(allocs_, &d_tokens_, (size_t)lim_.max_batch));
+  ACP_CUDA_CHECK(cudaMallocHost((void**)&h_tokens_, lim_.max_batch * sizeof(int)));
+  ACP_CUDA_CHECK(cudaMallocHost((void**)&h_logits_, (size_t)lim_.max_batch * c.vocab * sizeof(float)));
+  return 0;
+}
+
+int Model::gen_weights() {
+  const ModelConfig& c = cfg_;
+  const size_t H = c.hidden;
+  // tensor ids shared with oracle/synth.py
+  ACP_TRY(launch_synth(embed_, (size_t)c.vocab * H, c.seed, 1, c.w_std, 0, stream_));
+  ACP_TRY(launch_synth(lm_head_, (size_t)c.vocab * H, c.seed, 2, c.w_std, 0, stream_));
+  ACP_TRY(launch_synth(final_norm_, H, c.seed, 3, 0.1, 1, stream_));
+  for (int l = 0; l < c.layers; ++l) {
+    Layer& L = layers_[l];
+    const uint32_t base = 16 + (uint32_t)l * 16;
+    ACP_TRY(launch_synth(L.wqkv, (size_t)c.qkv_dim() * H, c.seed, base + 0, c.w_std, 0, stream_));
+    ACP_TRY(launch_synth(L.wo, H * c.q_dim(), c.seed, base + 1, c.w_std, 0, stream_));
+    ACP_TRY(launch_synth(L.wgu, (size_t)2 * c.ffn * H, c.seed, base + 2, c.w_std, 0, stream_));
+    ACP_TRY(launch_synth(L.wdown, H * c.ffn, c.seed, base + 3, c.w_std, 0, stream_));
+    ACP_TRY(launch_synth(L.attn_norm, H, c.seed, base + 4, 0.1, 1, stream_));
+    ACP_TRY(launch_synth(L.ffn_norm, H, c.seed, base + 5, 0.1, 1, stream_));
+  }
+  // RoPE tables: same recipe as oracle/llama_oracle.py rope_tables()
+  std::vector<float> hc((size_t)c.max_pos * 64), hs((size_t)c.max_pos * 64);
+  float inv[64];
+  for (int i = 0; i < 64; ++i) inv[i] = (float)pow(c.rope_theta, -(2.0 * i) / (double)HEAD_DIM);
+  for (int p = 0; p < c.max_pos; ++p)
+    for (int i = 0; i < 64; ++i) {
+      const float ang = (float)p * inv[i];
+      hc[(size_t)p * 64 + i] = (float)cos((double)ang);
+      hs[(size_t)p * 64 + i] = (float)sin((double)ang);
+    }
+  ACP_CUDA_CHECK(cudaMemcpyAsync(cos_, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice, stream_));
+  ACP_CUDA_CHECK(cudaMemcpyAsync(sin_, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, stream_));
+  ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  return 0;
+}
+
+int Model::debug_read_weight(int layer, int which, uint16_t* out, size_t n, size_t offset) {
+  const __nv_bfloat16* src = nullptr;
+  if (layer < 0) src = which == 1 ? embed_ : which == 2 ? lm_head_ : final_norm_;
+  else {
+    Layer& L = layers_[layer];
+    const __nv_bfloat16* t[6] = {L.wqkv, L.wo, L.wgu, L.wdown, L.attn_norm, L.ffn_norm};
+    if (which < 0 || which > 5) return -1;
+    src = t[which];
+  }
+  ACP_CUDA_CHECK(cudaMemcpy(out, src + offset, n * 2, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+static inline size_t align4(size_t v) { return (v + 3) & ~(size_t)3; }
+
+StepInput& Model::stage_begin(int T, int B, int n_blocks) {
+  StepInput& s = stage_;
+  s = StepInput();
+  s.T = T; s.B = B; s.n_blocks = n_blocks;
+  size_t off = 0;
+  auto carve = [&](size_t n) { int* p = h_ints_ + off; off += align4(n); return p; };
+  s.tok = carve(T); s.pos = carve(T); s.seq_of_row = carve(T);
+  s.q_start = carve(B); s.q_len = carve(B); s.ctx_len = carve(B); s.sample_rows = carve(B);
+  s.blk_seq = carve(n_blocks); s.blk_tok0 = carve(n_blocks);
+  s.page_table = carve((size_t)B * lim_.max_pages_per_seq);
+  ints_used_ = off;
+  s.sample_params = h_sparams_;
+  return s;
+}
+
+int Model::gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, GemmOut* out) {
+  GemmLaunch g;
+  g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
+  const int splits = choose_splits(M, K, N);
+  if (N <= 256) {
+    g.epi = EPI_F32; g.splits = splits; g.out = ws_; g.ld = M; g.n_cap = N;
+    if ((size_t)splits * N * M * sizeof(float) > ws_bytes_) return -4;
+    out->ptr = ws_; out->splits = splits; out->n_cap = N; out->ld = M;
+  } else {
+    g.epi = EPI_BF16; g.splits = 1; g.out = gemm_bf16_; g.ld = M; g.n_cap = N;
+    out->ptr = gemm_bf16_; out->splits = 0; out->n_cap = N; out->ld = M;
+  }
+  ++launches_;
+  return gemm_launch(g, stream_);
+}
+
+int Model::forward(const StepInput& in) {
+  const ModelConfig& c = cfg_;
+  if (in.T <= 0 || in.T > lim_.max_tokens || in.B > lim_.max_batch || in.n_sample > lim_.max_batch)
+    return -1;
+  ACP_CUDA_CHECK(cudaSetDevice(device_));
+  ACP_CUDA_CHECK(cudaMemcpyAsync(d_ints_, h_ints_, ints_used_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  auto dev = [&](const int* hp) { return d_ints_ + (hp - h_ints_); };
+  const int* d_tok = dev(in.tok);
+  const int* d_pos = dev(in.pos);
+  const int* d_seq = dev(in.seq_of_row);
+  const int* d_qstart = dev(in.q_start);
+  const int* d_qlen = dev(in.q_len);
+  const int* d_ctx = dev(in.ctx_len);
+  const int* d_srows = dev(in.sample_rows);
+  const int* d_bseq = dev(in.blk_seq);
+  const int* d_btok0 = dev(in.blk_tok0);
+  const int* d_pt = dev(in.page_table);
+  const int T = in.T;
+  const float scale = 1.0f / sqrtf((float)HEAD_DIM);
+
+  ACP_TRY(launch_embed(d_tok, embed_, x_, T, c.hidden, stream_));
+  ++launches_;
+  GemmOut none;
+  ACP_TRY(launch_add_rmsnorm(x_, none, layers_[0].attn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
+  ++launches_;
+  for (int l = 0; l < c.layers; ++l) {
+    Layer& L = layers_[l];
+    GemmOut qkv, o, gu, dn;
+    ACP_TRY(gemm(L.m_qkv, m_xn_, c.qkv_dim(), c.hidden, T, &qkv));
+    RopeKvArgs ra;
+    ra.qkv = qkv; ra.pos = d_pos; ra.seq_of_row = d_seq; ra.page_table = d_pt;
+    ra.max_pages = lim_.max_pages_per_seq; ra.cos_tab = cos_; ra.sin_tab = sin_; ra.qbuf = qbuf_;
+    ra.k_cache = L.k_cache; ra.v_cache = L.v_cache; ra.T = T; ra.heads = c.heads; ra.kv_heads = c.kv_heads;
+    ACP_TRY(launch_rope_kv(ra, stream_));
+    ++launches_;
+    if (in.decode) {
+      AttnDecodeArgs aa;
+      aa.q = qbuf_; aa.out = attn_; aa.ctx_len = d_ctx; aa.q_rows = nullptr; aa.page_table = d_pt;
+      aa.max_pages = lim_.max_pages_per_seq; aa.heads = c.heads; aa.kv_heads = c.kv_heads;
+      aa.scale = scale; aa.split_tokens = lim_.split_tokens; aa.max_splits = max_splits_;
+      aa.ws_o = attn_ws_o_; aa.ws_m = attn_ws_m_; aa.ws_l = attn_ws_l_;
+      ACP_TRY(launch_attn_decode(L.tm_k, L.tm_v, aa, in.B, in.max_ctx, stream_));
+      launches_ += (in.max_ctx > lim_.split_tokens) ? 2 : 1;
+    } else {
+      AttnPrefillArgs pa;
+      pa.q = qbuf_; pa.out = attn_; pa.blk_seq = d_bseq; pa.blk_tok0 = d_btok0; pa.q_start = d_qstart;
+      pa.q_len = d_qlen; pa.ctx_len = d_ctx; pa.page_table = d_pt; pa.max_pages = lim_.max_pages_per_seq;
+      pa.heads = c.heads; pa.kv_heads = c.kv_heads; pa.scale = scale;
+      ACP_TRY(launch_attn_prefill(L.tm_k, L.tm_v, pa, in.n_blocks, stream_));
+      ++launches_;
+    }
+    ACP_TRY(gemm(L.m_o, m_attn_, c.hidden, c.q_dim(), T, &o));
+    ACP_TRY(launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
+    ++launches_;
+    ACP_TRY(gemm(L.m_gu, m_xn_, 2 * c.ffn, c.hidden, T, &gu));
+    ACP_TRY(launch_swiglu(gu, h_, T, c.ffn, stream_));
+    ++launches_;
+    ACP_TRY(gemm(L.m_down, m_h_, c.hidden, c.ffn, T, &dn));
+    if (l + 1 < c.layers) {
+      ACP_TRY(launch_add_rmsnorm(x_, dn, layers_[l + 1].attn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
+    } else {
+      // final norm only on the rows that are sampled (residual add folded in, not written back)
+      ACP_TRY(launch_add_rmsnorm(x_, dn, final_norm_, xs_, d_srows, in.n_sample, c.hidden, c.eps, stream_));
+    }
+    ++launches_;
+  }
+  if (in.n_sample > 0) {
+    const int m_tiles = (c.vocab + GEMM_BM - 1) / GEMM_BM;
+    GemmLaunch g;
+    g.w = &m_lm_.w; g.x = &m_xs_; g.M = c.vocab; g.N = in.n_sample; g.K = c.hidden; g.splits = 1;
+    g.epi = EPI_ARGMAX; g.ld = c.vocab; g.n_cap = in.n_sample;
+    const bool logits = in.want_logits || !in.all_greedy;
+    g.out = logits ? logits_ : nullptr;
+    g.amax_val = amax_val_; g.amax_idx = amax_idx_;
+    ACP_TRY(gemm_launch(g, stream_));
+    ++launches_;
+    if (in.all_greedy) {
+      ACP_TRY(launch_argmax_finish(amax_val_, amax_idx_, m_tiles, in.n_sample, d_tokens_, nullptr, stream_));
+    } else {
+      ACP_CUDA_CHECK(cudaMemcpyAsync(d_sparams_, h_sparams_, in.n_sample * sizeof(SampleParams),
+                                     cudaMemcpyHostToDevice, stream_));
+      ACP_TRY(launch_sample(logits_, c.vocab, in.n_sample, d_sparams_, d_tokens_, stream_));
+    }
+    ++launches_;
+    ACP_CUDA_CHECK(cudaMemcpyAsync(h_tokens_, d_tokens_, in.n_sample * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    if (in.want_logits)
+      ACP_CUDA_CHECK(cudaMemcpyAsync(h_logits_, logits_, (size_t)in.n_sample * c.vocab * sizeof(float),
+                                     cudaMemcpyDeviceToHost, stream_));
+  }
+  return 0;
+}
+
+int Model::sync() {
+  cudaError_t e = cudaStreamSynchronize(stream_);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[acp_infer] step failed: %s\n", cudaGetErrorString(e));
+    return -5;
+  }
+  return 0;
+}
+
+}  // namespace acp

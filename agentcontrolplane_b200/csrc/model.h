@@ -1,0 +1,134 @@
+// model.h — Llama-architecture weights, HBM layout and the per-step forward pass of the local
+// provider's decode engine.  One Model per GPU (request-level data parallelism = one engine
+// replica per GPU, no collective).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "attention.h"
+#include "gemm.h"
+#include "kernels.cuh"
+
+namespace acp {
+
+struct ModelConfig {
+  std::string name = "tiny";
+  int hidden = 512, layers = 2, heads = 4, kv_heads = 1, ffn = 1024, vocab = 128256;
+  double rope_theta = 500000.0;
+  float eps = 1e-5f;
+  double w_std = 0.02;
+  int max_pos = 8192;
+  uint64_t seed = 0xACB200ull;
+  int q_dim() const { return heads * HEAD_DIM; }
+  int kv_dim() const { return kv_heads * HEAD_DIM; }
+  int qkv_dim() const { return q_dim() + 2 * kv_dim(); }
+  // bytes of weights streamed by one decode step (SURVEY.md §8d "W")
+  double weight_bytes() const {
+    double per_layer = (double)qkv_dim() * hidden + (double)hidden * q_dim() +
+                       2.0 * ffn * hidden + (double)hidden * ffn + 2.0 * hidden;
+    return 2.0 * (per_layer * layers + (double)vocab * hidden + hidden);
+  }
+  double kv_bytes_per_token() const { return 2.0 * kv_dim() * 2.0 * layers; }
+};
+bool model_preset(const std::string& name, ModelConfig* out);
+
+struct ModelLimits {
+  int max_batch = 256;       // sequences per decode step / sampled rows per step
+  int max_tokens = 8192;     // token rows per step (prefill chunk budget)
+  int num_pages = 2048;      // KV pages (32 tokens each) in the pool, page 0 is reserved
+  int max_pages_per_seq = 256;
+  int split_tokens = 512;    // decode attention KV split
+  int splitk_target_ctas = 222;
+};
+
+// Host-side description of one engine step (all arrays in pinned host memory, sized by limits).
+struct StepInput {
+  int T = 0;            // token rows
+  int B = 0;            // sequences taking part in this step
+  int n_sample = 0;     // rows whose next token is sampled
+  int n_blocks = 0;     // prefill query blocks (0 for a pure decode step)
+  bool decode = false;  // every sequence has exactly one new token
+  bool want_logits = false;
+  bool all_greedy = true;
+  int max_ctx = 0;
+  // packed int32 region, uploaded with one copy:
+  int* tok;         // [T]
+  int* pos;         // [T]
+  int* seq_of_row;  // [T]
+  int* q_start;     // [B]
+  int* q_len;       // [B]
+  int* ctx_len;     // [B]
+  int* sample_rows; // [n_sample]
+  int* blk_seq;     // [n_blocks]
+  int* blk_tok0;    // [n_blocks]
+  int* page_table;  // [B][max_pages_per_seq]
+  SampleParams* sample_params;  // [n_sample] (pinned, separate upload when !all_greedy)
+};
+
+class Model {
+ public:
+  Model() = default;
+  ~Model();
+  int init(const ModelConfig& cfg, const ModelLimits& lim, int device);
+  // Runs one step on `stream()`: tokens for the n_sample rows land in host_tokens() after sync().
+  int forward(const StepInput& in);
+  int sync();
+  // Carves the pinned staging buffer for a step of T rows, B sequences, n_blocks prefill query
+  // blocks; the engine fills the returned arrays, then calls forward(staging()).
+  StepInput& stage_begin(int T, int B, int n_blocks);
+  StepInput& staging() { return stage_; }
+  const int* host_tokens() const { return h_tokens_; }
+  const float* host_logits() const { return h_logits_; }  // [n_sample][vocab] when want_logits
+  cudaStream_t stream() const { return stream_; }
+  const ModelConfig& config() const { return cfg_; }
+  const ModelLimits& limits() const { return lim_; }
+  int device() const { return device_; }
+  long long launches() const { return launches_; }
+  // test hooks: copy tensors back to the host
+  int debug_read_weight(int layer, int which, uint16_t* out, size_t n, size_t offset);
+
+ private:
+  int alloc_all();
+  int gen_weights();
+  int gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, GemmOut* out);
+  int choose_splits(int M, int K, int N) const;
+
+  ModelConfig cfg_;
+  ModelLimits lim_;
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  long long launches_ = 0;
+
+  struct Layer {
+    __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;
+    __nv_bfloat16 *k_cache, *v_cache;
+    TmaMaps m_qkv, m_o, m_gu, m_down;
+    CUtensorMap tm_k, tm_v;
+  };
+  std::vector<Layer> layers_;
+  __nv_bfloat16 *embed_ = nullptr, *lm_head_ = nullptr, *final_norm_ = nullptr;
+  TmaMaps m_lm_;
+  float *cos_ = nullptr, *sin_ = nullptr;
+  // activations
+  __nv_bfloat16 *x_ = nullptr, *xn_ = nullptr, *qbuf_ = nullptr, *attn_ = nullptr, *h_ = nullptr,
+                *xs_ = nullptr, *gemm_bf16_ = nullptr;
+  TmaMaps m_xn_, m_attn_, m_h_, m_xs_;
+  float* ws_ = nullptr;  // split-K partial planes
+  size_t ws_bytes_ = 0;
+  float *amax_val_ = nullptr, *logits_ = nullptr;
+  int* amax_idx_ = nullptr;
+  float *attn_ws_o_ = nullptr, *attn_ws_m_ = nullptr, *attn_ws_l_ = nullptr;
+  int max_splits_ = 1;
+  int* d_ints_ = nullptr;     // packed step ints
+  size_t ints_cap_ = 0, ints_used_ = 0;
+  int* h_ints_ = nullptr;     // pinned mirror
+  SampleParams *d_sparams_ = nullptr, *h_sparams_ = nullptr;
+  int *d_tokens_ = nullptr, *h_tokens_ = nullptr;
+  float* h_logits_ = nullptr;
+  StepInput stage_;
+  std::vector<void*> allocs_;
+};
+
+}  // namespace acp
