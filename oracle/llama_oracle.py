@@ -131,6 +131,17 @@ class Weights:
         return self._gain(synth.layer_tid(l, synth.TID_FFN_NORM), self.cfg.hidden)
 
 
+_WEIGHTS_CACHE: dict = {}
+
+
+def shared_weights(cfg: LlamaConfig, seed: int) -> Weights:
+    """One Weights object per (config, seed): the 128256-row LM head takes seconds to generate."""
+    key = (cfg, seed)
+    if key not in _WEIGHTS_CACHE:
+        _WEIGHTS_CACHE[key] = Weights(cfg, seed)
+    return _WEIGHTS_CACHE[key]
+
+
 class LlamaOracle:
     """One sequence, KV cached.  mode='bf16' mirrors the engine's rounding points, 'fp32' has none
     (that mode is what is pinned against HuggingFace)."""
@@ -138,7 +149,7 @@ class LlamaOracle:
     def __init__(self, cfg: LlamaConfig, seed: int, mode: str = "bf16", weights: Weights | None = None):
         assert mode in ("bf16", "fp32")
         self.cfg, self.mode = cfg, mode
-        self.w = weights or Weights(cfg, seed)
+        self.w = weights or shared_weights(cfg, seed)
         self.cos, self.sin = rope_tables(cfg, cfg.max_pos)
         self.k = [np.zeros((0, cfg.kv_heads, cfg.head_dim), np.float32) for _ in range(cfg.layers)]
         self.v = [np.zeros((0, cfg.kv_heads, cfg.head_dim), np.float32) for _ in range(cfg.layers)]

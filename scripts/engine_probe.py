@@ -1,0 +1,51 @@
+"""Dev probe: N concurrent requests of fixed prompt length through the C ABI; prints engine stats.
+usage: python scripts/engine_probe.py [model] [n_requests] [prompt_len] [max_tokens] [layers]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from agentcontrolplane_b200.engine import Engine  # noqa: E402
+
+model = sys.argv[1] if len(sys.argv) > 1 else "llama-3-8b"
+n_req = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+plen = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+max_new = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+cfg = {"model": model, "max_batch": max(64, n_req), "kv_pages": n_req * ((plen + max_new) // 32 + 2) + 8,
+       "max_tokens_per_step": 8192, "max_pages_per_seq": max(32, (plen + max_new) // 32 + 2)}
+if len(sys.argv) > 5:
+    cfg["layers"] = int(sys.argv[5])
+t0 = time.time()
+eng = Engine(cfg)
+print("init s:", round(time.time() - t0, 2), flush=True)
+for rep in range(3):
+    eng.stats_reset()
+    rng = np.random.default_rng(rep)
+    t0 = time.time()
+    tickets = []
+    for i in range(n_req):
+        prompt = [128000] + [int(t) for t in rng.integers(0, 256, size=plen - 1)]
+        tickets.append(eng.submit({"model": model, "max_tokens": max_new, "acp": {"prompt_token_ids": prompt}}))
+    for t in tickets:
+        eng.wait(t, -1)
+    wall = time.time() - t0
+    ntok = 0
+    for t in tickets:
+        st, body = eng.result(t)
+        assert st == 200, body
+        ntok += len(body["acp"]["token_ids"])
+    s = eng.stats()
+    dec_tps = s["decode_tokens"] / (s["decode_ms"] / 1e3) if s["decode_ms"] else 0
+    gbs = s["decode_bytes_algorithmic"] / (s["decode_ms"] / 1e3) / 1e9 if s["decode_ms"] else 0
+    print(json.dumps({"rep": rep, "wall_s": round(wall, 3), "gen_tokens": ntok,
+                      "reconciles_per_s": round(n_req / wall, 2),
+                      "decode_tok_per_s": round(dec_tps, 1), "decode_GBps": round(gbs, 1),
+                      "frac_of_6590": round(gbs / 6590, 3),
+                      "decode_step_ms_p50": s.get("decode_step_ms_p50"),
+                      "prefill_ms": round(s["prefill_ms"], 2), "prefill_tokens": s["prefill_tokens"],
+                      "prefill_tok_per_s": round(s["prefill_tokens"] / (s["prefill_ms"] / 1e3), 1) if s["prefill_ms"] else 0,
+                      "decode_ms": round(s["decode_ms"], 2), "decode_steps": s["decode_steps"]}), flush=True)
+eng.close()

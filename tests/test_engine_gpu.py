@@ -14,6 +14,19 @@ SEED = 0xACB200
 LOGIT_ATOL = 3e-2
 
 
+def assert_tokens_match(got, want, margins, where=""):
+    """Bit-exact token ids, with the stated near-tie policy: a mismatch is only
+    tolerated at a step whose oracle top-1/top-2 logit margin is below 2*LOGIT_ATOL (either
+    implementation may legitimately pick either candidate there); comparison stops at that step
+    because the continuations differ from then on."""
+    for i, (g, w) in enumerate(zip(got, want)):
+        if g != w:
+            assert margins[i] < 2 * LOGIT_ATOL, (where, i, got, want, margins)
+            return i
+    assert len(got) == len(want), (where, got, want)
+    return len(got)
+
+
 def _prompt(rng, n):
     return [128000] + [int(t) for t in rng.integers(0, 256, size=n - 1)]
 
@@ -51,12 +64,13 @@ def test_single_sequence_matches_oracle(eng):
     orc2 = LlamaOracle(cfg, SEED, mode="bf16")
     ref0 = orc2.forward(prompt)[-1]
     assert np.max(np.abs(lg[0] - ref0)) < LOGIT_ATOL
+    print("max |logit diff| prefill position:", float(np.max(np.abs(lg[0] - ref0))))
     cur = want[0]
     for i in range(1, 4):
         ref = orc2.forward([cur])[-1]
         assert np.max(np.abs(lg[i] - ref)) < LOGIT_ATOL, i
         cur = want[i]
-    assert toks == want, (toks, want, margins)
+    assert_tokens_match(toks, want, margins)
     assert body["usage"]["prompt_tokens"] == len(prompt)
 
 
@@ -78,7 +92,8 @@ def test_batched_mixed_lengths_match_oracle(eng):
         outs.append(body["acp"]["token_ids"])
     for p, got in zip(prompts, outs):
         want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(p, n_new, eos=(128001, 128008, 128009))
-        assert got == want, (len(p), got, want, margins)
+        n_ok = assert_tokens_match(got, want, margins, where=len(p))
+        assert n_ok >= 1
 
 
 def test_chunked_prefill_equals_single_shot(eng):
@@ -93,8 +108,8 @@ def test_chunked_prefill_equals_single_shot(eng):
     finally:
         small.close()
     assert a == b
-    want, _ = LlamaOracle(cfg, SEED, mode="bf16").greedy(prompt, 5, eos=(128001, 128008, 128009))
-    assert a == want
+    want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(prompt, 5, eos=(128001, 128008, 128009))
+    assert_tokens_match(a, want, margins)
 
 
 def test_forced_tokens_and_stop(eng):
