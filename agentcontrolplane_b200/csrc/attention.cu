@@ -6,7 +6,7 @@
 // in shared memory is [32 rows][128 B] with 16-byte chunks XOR-ed by (row & 7): ldmatrix reads
 // are bank-conflict free with no padding.
 //
-// A CTA stages 64-token tiles (2 pages: K 16 KiB + V 16 KiB per stage) through a 4-deep ring
+// A CTA stages 64-token tiles (2 pages: K 16 KiB + V 16 KiB per stage) through a 3-deep ring
 // filled by a dedicated producer warp (cp.async.bulk.tensor + mbarrier complete_tx); consumer
 // warps run mma.sync m16n8k16 (bf16 in, fp32 accumulate) with an online softmax:
 //   rows of the 16-row MMA tile = (query token, head-in-group); GQA packs the G query heads that
@@ -14,8 +14,9 @@
 //   P is split into bf16 hi + lo parts (two PV MMAs) so that P keeps ~16 mantissa bits: the
 //   result matches an fp32-softmax oracle to ~1e-6 and no bf16 rounding of P needs mirroring.
 //
-// decode  : CTA = (sequence, kv head, kv split); the 4 consumer warps take alternate tiles and
-//           merge their (m, l, O) through shared memory; splits merge in attn_merge_kernel.
+// decode  : CTA = (sequence, kv head, kv split); the 4 consumer warps each take a 16-token slice
+//           of every tile and merge their (m, l, O) through shared memory; kv splits merge in
+//           attn_merge_kernel.
 // prefill : CTA = (16/G*4 query tokens of one sequence, kv head); every warp owns 16 rows
 //           (16/G tokens x G heads) and all warps walk the causal range of tiles together.
 //
@@ -69,20 +70,23 @@ struct WarpState {
 
 // One 64-token tile for one warp.  key_limit[r] = number of visible keys for row r (keys with
 // absolute index < key_limit are visible), tile_tok0 = absolute index of the tile's first key.
+// NT = number of 8-token n-tiles this warp handles, starting at token `tok_off` of the tile
+// (prefill: NT = 8, the whole tile; decode: NT = 2, the warp's 16-token slice).
+template <int NT>
 ACP_DEVINL void process_tile(WarpState& st, const uint32_t (&qf)[8][4], uint32_t k_base,
-                             uint32_t v_base, int tile_tok0, int key_limit_lo, int key_limit_hi,
-                             float sl2e, int lane) {
-  float s[8][4];
+                             uint32_t v_base, int tile_tok0, int tok_off, int key_limit_lo,
+                             int key_limit_hi, float sl2e, int lane) {
+  float s[NT][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+  for (int j = 0; j < NT; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
   const int mi = lane >> 3, rr = lane & 7;
   // ---- S = Q K^T ----
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {          // 8 key n-tiles of 8 tokens
+  for (int j = 0; j < NT; ++j) {         // key n-tiles of 8 tokens
 #pragma unroll
     for (int kp = 0; kp < 4; ++kp) {     // 4 pairs of k-steps (32 dims each)
       uint32_t b[4];
-      ldmatrix_x4(b, k_base + tile_off(j * 8 + rr, kp * 32 + mi * 8));
+      ldmatrix_x4(b, k_base + tile_off(tok_off + j * 8 + rr, kp * 32 + mi * 8));
       mma_bf16_16816(s[j], qf[kp * 2], b[0], b[1]);
       mma_bf16_16816(s[j], qf[kp * 2 + 1], b[2], b[3]);
     }
@@ -90,8 +94,8 @@ ACP_DEVINL void process_tile(WarpState& st, const uint32_t (&qf)[8][4], uint32_t
   // ---- mask + online softmax ----
   float mx_lo = -INFINITY, mx_hi = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int t0 = tile_tok0 + j * 8 + 2 * (lane & 3);
+  for (int j = 0; j < NT; ++j) {
+    const int t0 = tile_tok0 + tok_off + j * 8 + 2 * (lane & 3);
     if (t0 >= key_limit_lo) s[j][0] = -INFINITY;
     if (t0 + 1 >= key_limit_lo) s[j][1] = -INFINITY;
     if (t0 >= key_limit_hi) s[j][2] = -INFINITY;
@@ -116,9 +120,9 @@ ACP_DEVINL void process_tile(WarpState& st, const uint32_t (&qf)[8][4], uint32_t
     st.o[d][0] *= corr_lo; st.o[d][1] *= corr_lo;
     st.o[d][2] *= corr_hi; st.o[d][3] *= corr_hi;
   }
-  uint32_t p_hi[4][4], p_lo[4][4];  // A fragments for the 4 PV k-steps (16 tokens each)
+  uint32_t p_hi[NT / 2][4], p_lo[NT / 2][4];  // A fragments for the PV k-steps (16 tokens each)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NT; ++j) {
     float p[4];
     p[0] = exp2f(s[j][0] * sl2e - base_lo);
     p[1] = exp2f(s[j][1] * sl2e - base_lo);
@@ -137,11 +141,11 @@ ACP_DEVINL void process_tile(WarpState& st, const uint32_t (&qf)[8][4], uint32_t
   }
   // ---- O += P V ----
 #pragma unroll
-  for (int kt = 0; kt < 4; ++kt) {       // 16 tokens per k-step
+  for (int kt = 0; kt < NT / 2; ++kt) {  // 16 tokens per k-step
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd) {     // 16 dims per ldmatrix.x4.trans
       uint32_t b[4];
-      ldmatrix_x4_trans(b, v_base + tile_off(kt * 16 + (mi & 1) * 8 + rr, nd * 16 + (mi >> 1) * 8));
+      ldmatrix_x4_trans(b, v_base + tile_off(tok_off + kt * 16 + (mi & 1) * 8 + rr, nd * 16 + (mi >> 1) * 8));
       mma_bf16_16816(st.o[nd * 2], p_hi[kt], b[0], b[1]);
       mma_bf16_16816(st.o[nd * 2], p_lo[kt], b[0], b[1]);
       mma_bf16_16816(st.o[nd * 2 + 1], p_hi[kt], b[2], b[3]);
@@ -152,8 +156,8 @@ ACP_DEVINL void process_tile(WarpState& st, const uint32_t (&qf)[8][4], uint32_t
 
 // V rows of tokens that do not exist yet may hold stale bytes (NaN patterns): zero them so that
 // 0 * garbage cannot poison the accumulators.  Called by the consuming warp on a landed tile.
-ACP_DEVINL void zero_v_tail(uint8_t* v_tile, int first_invalid_tok, int lane) {
-  for (int t = first_invalid_tok; t < TILE_TOK; ++t) {
+ACP_DEVINL void zero_v_tail(uint8_t* v_tile, int first_invalid_tok, int end_tok, int lane) {
+  for (int t = first_invalid_tok; t < end_tok; ++t) {
     const int page = t >> 5, r = t & 31;
     // 2 halves x 128 B per row = 16 uint4; lanes 0..15 write one each
     if (lane < 16) {
@@ -244,7 +248,10 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&L.full_bar[s], 1); mbar_init(&L.empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&L.full_bar[s], 1);
+      mbar_init(&L.empty_bar[s], CONSUMER_WARPS);
+    }
     fence_mbar_init();
   }
   __syncthreads();
@@ -268,15 +275,21 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   st.m[0] = st.m[1] = -INFINITY;
   st.l[0] = st.l[1] = 0.f;
   const float sl2e = a.scale * 1.4426950408889634f;
-  for (int it = warp; it < n_tiles; it += CONSUMER_WARPS) {
+  // Every consumer warp waits on EVERY tile in order (consecutive mbarrier phases: a parity wait
+  // is only sound one phase at a time) and works on its own 16-token slice of the tile.
+  const int tok_off = warp * 16;
+  for (int it = 0; it < n_tiles; ++it) {
     const int s = it % STAGES;
     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
     mbar_wait(&L.full_bar[s], ph);
     uint8_t* kt = L.stages + s * STAGE_BYTES;
     uint8_t* vt = kt + K_TILE_BYTES;
     const int tile_tok0 = (tile_begin + it) * TILE_TOK;
-    if (tok_end - tile_tok0 < TILE_TOK) zero_v_tail(vt, tok_end - tile_tok0, lane);
-    process_tile(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_end, tok_end, sl2e, lane);
+    const int valid = tok_end - tile_tok0;   // tokens of this tile that exist
+    if (valid > tok_off) {
+      if (valid < tok_off + 16) zero_v_tail(vt, valid, tok_off + 16, lane);
+      process_tile<2>(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_off, tok_end, tok_end, sl2e, lane);
+    }
     __syncwarp();
     if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }
   }
@@ -411,8 +424,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
     if (warp_active && tile_tok0 <= warp_last) {
       // tokens past last_pos were not loaded (or belong to the future): zero V there.  Every
       // active warp writes the same zeros, which is benign.
-      if (last_pos + 1 - tile_tok0 < TILE_TOK) zero_v_tail(vt, last_pos + 1 - tile_tok0, lane);
-      process_tile(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, lim_lo, lim_hi, sl2e, lane);
+      if (last_pos + 1 - tile_tok0 < TILE_TOK) zero_v_tail(vt, last_pos + 1 - tile_tok0, TILE_TOK, lane);
+      process_tile<8>(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, 0, lim_lo, lim_hi, sl2e, lane);
     }
     __syncwarp();
     if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }

@@ -29,10 +29,24 @@ bool model_preset(const std::string& name, ModelConfig* c) {
   return true;
 }
 
-#define ACP_TRY(expr)            \
-  do {                           \
-    int _rc = (expr);            \
-    if (_rc != 0) return _rc;    \
+static bool debug_sync_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACP_DEBUG_SYNC"); v = (e && *e && *e != '0') ? 1 : 0; }
+  return v == 1;
+}
+// ACP_DEBUG_SYNC=1: synchronise after every launch and name the kernel that failed.
+#define ACP_TRY(expr)                                                                      \
+  do {                                                                                     \
+    int _rc = (expr);                                                                      \
+    if (_rc != 0) return _rc;                                                              \
+    if (debug_sync_enabled() && stream_) {                                                 \
+      cudaError_t _e = cudaStreamSynchronize(stream_);                                     \
+      if (_e != cudaSuccess) {                                                             \
+        fprintf(stderr, "[acp_infer] ACP_DEBUG_SYNC: failure after `%s` (%s:%d): %s\n",    \
+                #expr, __FILE__, __LINE__, cudaGetErrorString(_e));                        \
+        return -5;                                                                         \
+      }                                                                                    \
+    }                                                                                      \
   } while (0)
 
 Model::~Model() {
