@@ -448,6 +448,8 @@ std::string Engine::stats_json() {
   j.set("requests_done", Json(stats_.requests_done));
   j.set("requests_failed", Json(stats_.requests_failed));
   j.set("kernel_launches", Json(model_.launches()));
+  j.set("h2d_bytes", Json(model_.h2d_bytes()));
+  j.set("d2h_bytes", Json(model_.d2h_bytes()));
   j.set("weight_bytes_per_step", Json(c.weight_bytes()));
   j.set("kv_bytes_per_token", Json(c.kv_bytes_per_token()));
   // bytes_step = W + sum_seq ctx*K + B*K, summed over the decode steps so far

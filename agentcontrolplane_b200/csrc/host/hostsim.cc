@@ -1,0 +1,532 @@
+// host/hostsim.cc — C entry points of include/acp_host.h: test hooks over the host mirror, the
+// loopback stub completion server and the reconcile-loop simulator used by bench.py.
+#include "acp_host.h"
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <string.h>
+#include <sys/socket.h>
+#include <unistd.h>
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include "../chat.h"
+#include "task.h"
+
+using namespace acp;
+using acp::llmclient::Message;
+using acp::llmclient::Tool;
+
+static char* dup_out(const std::string& s, size_t* len = nullptr) {
+  char* p = (char*)malloc(s.size() + 1);
+  if (!p) return nullptr;
+  memcpy(p, s.data(), s.size());
+  p[s.size()] = 0;
+  if (len) *len = s.size();
+  return p;
+}
+static int ret_json(const Json& j, char** out) {
+  *out = dup_out(j.dump());
+  return *out ? ACP_OK : ACP_ERR_NOMEM;
+}
+
+static bool tools_from_json(const Json& arr, std::vector<Tool>* tools) {
+  for (const Json& t : arr.items()) {
+    Tool tool;
+    tool.Type = t.get("type").as_string();
+    if (tool.Type.empty()) tool.Type = "function";
+    const Json& fn = t.get("function");
+    tool.Function.Name = fn.get("name").as_string();
+    tool.Function.Description = fn.get("description").as_string();
+    tool.Function.Parameters = fn.get("parameters");
+    tool.ACPToolType = t.get("acpToolType").as_string();
+    tools->push_back(std::move(tool));
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------
+// mock client: llmmocks.NewMockLLMClient in the reference's tests
+// ---------------------------------------------------------------------------------
+namespace {
+class MockClient : public llmclient::LLMClient {
+ public:
+  explicit MockClient(const Json& spec, std::string* request_sink) : spec_(spec), sink_(request_sink) {}
+  bool SendRequest(const llmclient::Context&, const std::vector<Message>& messages,
+                   const std::vector<Tool>& tools, Message* out, llmclient::Error* err) override {
+    if (sink_) *sink_ = llmclient::build_chat_request_json("mock", messages, tools, 0, nullptr);
+    if (spec_.find("error")) { err->Message = spec_.get("error").as_string(); return false; }
+    if (spec_.find("request_error")) {
+      err->is_request_error = true;
+      err->StatusCode = (int)spec_.get("request_error").get("status").as_int(400);
+      err->Message = spec_.get("request_error").get("message").as_string();
+      return false;
+    }
+    llmclient::message_from_crd_json(spec_.get("message"), out);
+    return true;
+  }
+
+ private:
+  Json spec_;
+  std::string* sink_;
+};
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+// stub completion server
+// ---------------------------------------------------------------------------------
+namespace {
+struct StubServer {
+  int listen_fd = -1;
+  int port = 0;
+  std::string body;
+  std::atomic<bool> stop{false};
+  std::thread thread;
+  std::atomic<long long> served{0};
+};
+StubServer* g_stubs[16] = {nullptr};
+std::mutex g_stub_mu;
+
+void serve_conn(StubServer* s, int fd) {
+  // HTTP/1.1 keep-alive: serve requests on this connection until the peer closes it
+  std::string buf_acc;
+  char buf[16384];
+  while (true) {
+    size_t he;
+    while ((he = buf_acc.find("\r\n\r\n")) == std::string::npos) {
+      ssize_t n = recv(fd, buf, sizeof buf, 0);
+      if (n <= 0) { close(fd); return; }
+      buf_acc.append(buf, (size_t)n);
+    }
+    size_t cl = buf_acc.find("Content-Length:");
+    const size_t len = (cl == std::string::npos || cl > he) ? 0 : (size_t)atoll(buf_acc.c_str() + cl + 15);
+    const size_t need = he + 4 + len;
+    while (buf_acc.size() < need) {
+      ssize_t n = recv(fd, buf, sizeof buf, 0);
+      if (n <= 0) { close(fd); return; }
+      buf_acc.append(buf, (size_t)n);
+    }
+    buf_acc.erase(0, need);
+    const std::string resp = "HTTP/1.1 200 OK\r\nContent-Type: application/json\r\nContent-Length: " +
+                             std::to_string(s->body.size()) + "\r\n\r\n" + s->body;
+    size_t off = 0;
+    while (off < resp.size()) {
+      ssize_t n = send(fd, resp.data() + off, resp.size() - off, MSG_NOSIGNAL);
+      if (n <= 0) { close(fd); return; }
+      off += (size_t)n;
+    }
+    ++s->served;
+  }
+}
+
+void stub_loop(StubServer* s) {
+  while (!s->stop) {
+    sockaddr_in peer;
+    socklen_t pl = sizeof peer;
+    int fd = accept(s->listen_fd, (sockaddr*)&peer, &pl);
+    if (fd < 0) { if (s->stop) break; continue; }
+    int one = 1;
+    setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+    std::thread(serve_conn, s, fd).detach();  // one goroutine per connection, like net/http
+  }
+}
+}  // namespace
+
+extern "C" int acp_host_stub_server_start(const char* body, int* port) {
+  if (!port) return ACP_ERR_INVALID;
+  StubServer* s = new StubServer();
+  s->body = body ? body : "{\"id\":\"test-id\",\"choices\":[{\"message\":{\"content\":\"test\"}}]}";
+  s->listen_fd = socket(AF_INET, SOCK_STREAM, 0);
+  int one = 1;
+  setsockopt(s->listen_fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+  sockaddr_in addr;
+  memset(&addr, 0, sizeof addr);
+  addr.sin_family = AF_INET;
+  addr.sin_addr.s_addr = htonl(INADDR_LOOPBACK);
+  addr.sin_port = 0;
+  if (bind(s->listen_fd, (sockaddr*)&addr, sizeof addr) != 0 || listen(s->listen_fd, 1024) != 0) {
+    close(s->listen_fd);
+    delete s;
+    return ACP_ERR_INVALID;
+  }
+  socklen_t al = sizeof addr;
+  getsockname(s->listen_fd, (sockaddr*)&addr, &al);
+  s->port = ntohs(addr.sin_port);
+  *port = s->port;
+  s->thread = std::thread(stub_loop, s);
+  std::lock_guard<std::mutex> lk(g_stub_mu);
+  for (int i = 0; i < 16; ++i)
+    if (!g_stubs[i]) { g_stubs[i] = s; return i; }
+  return ACP_ERR_NOMEM;
+}
+
+extern "C" void acp_host_stub_server_stop(int handle) {
+  StubServer* s = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_stub_mu);
+    if (handle < 0 || handle >= 16 || !g_stubs[handle]) return;
+    s = g_stubs[handle];
+    g_stubs[handle] = nullptr;
+  }
+  s->stop = true;
+  shutdown(s->listen_fd, SHUT_RDWR);
+  close(s->listen_fd);
+  if (s->thread.joinable()) s->thread.join();
+  std::this_thread::sleep_for(std::chrono::milliseconds(20));  // let detached handlers drain
+  delete s;
+}
+
+// ---------------------------------------------------------------------------------
+// chat-side hooks
+// ---------------------------------------------------------------------------------
+extern "C" int acp_host_render_prompt(const char* chat_request_json, size_t len, char** out_json) {
+  if (!chat_request_json || !out_json) return ACP_ERR_INVALID;
+  ChatRequest req;
+  std::string err;
+  Json out = Json::object();
+  int status = parse_chat_request(chat_request_json, len, &req, &err);
+  if (status != 0) {
+    out.set("status", Json(status));
+    out.set("error", Json(err));
+    return ret_json(out, out_json);
+  }
+  std::vector<int> ids;
+  if (req.has_prompt_ids) ids = req.prompt_token_ids; else render_prompt(req, &ids);
+  Json arr = Json::array();
+  for (int t : ids) arr.push(Json(t));
+  out.set("text", Json(render_prompt_text(req)));
+  out.set("token_ids", arr);
+  return ret_json(out, out_json);
+}
+
+extern "C" int acp_host_parse_completion(const char* text, size_t len, const char* tools_json,
+                                         const char* call_id_prefix, char** out_json) {
+  if (!text || !out_json) return ACP_ERR_INVALID;
+  std::vector<ToolDef> tools;
+  if (tools_json && *tools_json) {
+    Json arr;
+    std::string err;
+    if (!Json::parse(std::string(tools_json), &arr, &err)) return ACP_ERR_INVALID;
+    for (const Json& t : arr.items()) {
+      ToolDef td;
+      td.type = "function";
+      td.name = t.get("function").get("name").as_string();
+      tools.push_back(td);
+    }
+  }
+  ParsedCompletion pc = parse_completion(std::string(text, len), tools, call_id_prefix ? call_id_prefix : "call_");
+  Json out = Json::object();
+  if (!pc.tool_calls.empty()) {
+    Json tcs = Json::array();
+    for (auto& t : pc.tool_calls) {
+      Json fn = Json::object();
+      fn.set("name", Json(t.name));
+      fn.set("arguments", Json(t.arguments));
+      Json o = Json::object();
+      o.set("id", Json(t.id));
+      o.set("type", Json(t.type));
+      o.set("function", fn);
+      tcs.push(o);
+    }
+    out.set("tool_calls", tcs);
+  } else {
+    out.set("content", Json(pc.content));
+  }
+  return ret_json(out, out_json);
+}
+
+extern "C" int acp_host_decode_tokens(const int* ids, int n, char** out_text, size_t* out_len) {
+  if ((!ids && n > 0) || !out_text) return ACP_ERR_INVALID;
+  std::vector<int> v(ids, ids + n);
+  *out_text = dup_out(decode_tokens(v), out_len);
+  return *out_text ? ACP_OK : ACP_ERR_NOMEM;
+}
+
+extern "C" int acp_host_build_chat_request(const char* model, const char* messages_crd_json,
+                                           const char* tools_json, char** out_json) {
+  if (!messages_crd_json || !out_json) return ACP_ERR_INVALID;
+  Json msgs, tools;
+  std::string err;
+  if (!Json::parse(std::string(messages_crd_json), &msgs, &err)) return ACP_ERR_INVALID;
+  if (tools_json && *tools_json && !Json::parse(std::string(tools_json), &tools, &err)) return ACP_ERR_INVALID;
+  std::vector<Message> mv;
+  for (const Json& m : msgs.items()) { Message mm; llmclient::message_from_crd_json(m, &mm); mv.push_back(mm); }
+  std::vector<Tool> tv;
+  tools_from_json(tools, &tv);
+  *out_json = dup_out(llmclient::build_chat_request_json(model ? model : "", mv, tv, 0, nullptr));
+  return *out_json ? ACP_OK : ACP_ERR_NOMEM;
+}
+
+extern "C" int acp_host_convert_response(const char* response_json, char** out_message_crd_json) {
+  if (!response_json || !out_message_crd_json) return ACP_ERR_INVALID;
+  Message m;
+  std::string err;
+  if (!llmclient::convert_from_response_json(response_json, &m, &err)) return ACP_ERR_INVALID;
+  return ret_json(llmclient::message_to_crd_json(m), out_message_crd_json);
+}
+
+// ---------------------------------------------------------------------------------
+// one state-machine operation
+// ---------------------------------------------------------------------------------
+static Json result_json(const task::Result& r) {
+  Json j = Json::object();
+  j.set("requeue", Json(r.Requeue));
+  j.set("requeueAfter", Json(r.RequeueAfter));
+  return j;
+}
+
+extern "C" int acp_host_task_step(acp_engine* engine, const char* input_json, char** out_json) {
+  if (!input_json || !out_json) return ACP_ERR_INVALID;
+  Json in;
+  std::string perr;
+  if (!Json::parse(std::string(input_json), &in, &perr)) return ACP_ERR_INVALID;
+  task::ObjectStore store;
+  task::Recorder rec;
+  task::StateMachine sm(&store, &rec);
+  task::Task t;
+  if (!task::task_from_json(in.get("task"), &t)) return ACP_ERR_INVALID;
+  std::vector<Tool> tools;
+  tools_from_json(in.get("tools"), &tools);
+  for (const Json& tcj : in.get("toolcalls").items())
+    store.Put("ToolCall", tcj.get("metadata").get("name").as_string(), tcj);
+  const long long writes0 = store.writes();
+  const std::string op = in.get("op").as_string();
+  std::string err, request_json;
+  task::Result res;
+  if (op == "checkToolCalls") {
+    res = sm.checkToolCalls(&t, &err);
+  } else {
+    const Json& llm = in.get("llm");
+    const std::string provider = llm.get("provider").as_string();
+    llmclient::BaseConfig bc;
+    bc.Model = llm.get("model").as_string();
+    bc.BaseURL = llm.get("baseURL").as_string();
+    bc.MaxTokens = (int)llm.get("maxTokens").as_int(0);
+    task::ClientFactory factory = [&](std::string* cerr) -> std::unique_ptr<llmclient::LLMClient> {
+      if (provider == "mock")
+        return std::unique_ptr<llmclient::LLMClient>(new MockClient(llm.get("mock"), &request_json));
+      auto c = llmclient::NewLLMClient(provider, "test-key", bc, engine, cerr);
+      if (c && provider == "local" && llm.get("acp").is_object())
+        static_cast<llmclient::LocalClient*>(c.get())->set_extension(llm.get("acp"));
+      return c;
+    };
+    llmclient::Context ctx;
+    res = sm.sendLLMRequest(ctx, &t, tools, factory, &err);
+  }
+  Json out = Json::object();
+  out.set("task", task::task_to_json(t));
+  out.set("result", result_json(res));
+  out.set("error", Json(err));
+  Json evs = Json::array();
+  for (auto& e : rec.events) {
+    Json ej = Json::object();
+    ej.set("type", Json(e.Type));
+    ej.set("reason", Json(e.Reason));
+    ej.set("message", Json(e.Message));
+    evs.push(ej);
+  }
+  out.set("events", evs);
+  Json tcs = Json::array();
+  if (!t.Status.ToolCallRequestID.empty())
+    for (Json& j : store.ListToolCalls(t.Name, t.Status.ToolCallRequestID)) tcs.push(j);
+  out.set("toolcalls", tcs);
+  out.set("store_writes", Json(store.writes() - writes0));
+  if (!request_json.empty()) out.set("request_json", Json(request_json));
+  return ret_json(out, out_json);
+}
+
+// ---------------------------------------------------------------------------------
+// reconcile-loop simulator
+// ---------------------------------------------------------------------------------
+static uint64_t mix64(uint64_t z) {
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+
+// user content of `n` ASCII letters/spaces, deterministic in (seed, task)
+static std::string synth_text(uint64_t seed, int task, int n) {
+  std::string s;
+  s.reserve(n);
+  static const char alphabet[] = "abcdefghijklmnopqrstuvwxyz    ";
+  for (int i = 0; i < n; ++i)
+    s.push_back(alphabet[mix64(seed * 1000003ull + (uint64_t)task * 7919ull + (uint64_t)i) % 30]);
+  return s;
+}
+
+extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char** result_json_out) {
+  if (!config_json || !result_json_out) return ACP_ERR_INVALID;
+  Json cfg;
+  std::string perr;
+  if (!Json::parse(std::string(config_json), &cfg, &perr) || !cfg.is_object()) return ACP_ERR_INVALID;
+  const int n_tasks = (int)cfg.get("tasks").as_int(1);
+  const int workers = std::max(1, (int)cfg.get("workers").as_int(1));
+  const std::string provider = cfg.get("provider").as_string().empty() ? "local" : cfg.get("provider").as_string();
+  llmclient::BaseConfig bc;
+  bc.Model = cfg.get("model").as_string();
+  bc.BaseURL = cfg.get("baseURL").as_string();
+  bc.MaxTokens = (int)cfg.get("max_tokens").as_int(64);
+  const int prompt_tokens = (int)cfg.get("prompt_tokens").as_int(0);
+  const int n_tools = (int)cfg.get("tools").as_int(0);
+  const bool tool_loop = cfg.get("tool_loop").as_bool(false);
+  const uint64_t seed = (uint64_t)cfg.get("seed").as_int(1);
+  const bool lease = cfg.find("emulate_lease") ? cfg.get("emulate_lease").as_bool(true) : true;
+  if (provider == "local" && !engine) return ACP_ERR_INVALID;
+
+  // agent-level tool list (collectTools): synthetic MCP tools server__tool_i
+  std::vector<Json> mcp;
+  for (int i = 0; i < n_tools; ++i) {
+    Json t = Json::object();
+    t.set("name", Json("tool_" + std::to_string(i)));
+    t.set("description", Json("synthetic tool " + std::to_string(i)));
+    Json url = Json::object(); url.set("type", Json("string"));
+    Json props = Json::object(); props.set("url", url);
+    Json schema = Json::object();
+    schema.set("type", Json("object"));
+    schema.set("properties", props);
+    t.set("inputSchema", schema);
+    mcp.push_back(t);
+  }
+  const std::vector<Tool> tools = task::ConvertMCPTools(mcp, "fetch");
+
+  task::ObjectStore store;
+  task::Recorder rec;
+  const std::string system_prompt = "You are a helpful test assistant.";  // test_getting_started.go:279
+  // size the user message so that the rendered window is exactly prompt_tokens tokens
+  auto render_len = [&](const std::string& user) {
+    ChatRequest cr;
+    ChatMessage s; s.role = "system"; s.content = system_prompt;
+    ChatMessage u; u.role = "user"; u.content = user;
+    cr.messages = {s, u};
+    for (const Tool& t : tools) {
+      ToolDef td; td.type = t.Type; td.name = t.Function.Name; td.description = t.Function.Description;
+      td.parameters = t.Function.Parameters;
+      cr.tools.push_back(td);
+    }
+    std::vector<int> ids;
+    render_prompt(cr, &ids);
+    return (int)ids.size();
+  };
+  const int overhead = render_len("");
+  int user_len = 30;  // "What is the capital of France?" scale when no target is given
+  if (prompt_tokens > 0) {
+    if (prompt_tokens < overhead) return ACP_ERR_INVALID;
+    user_len = prompt_tokens - overhead;
+  }
+  for (int i = 0; i < n_tasks; ++i) {
+    task::Task t;
+    t.Name = "task-" + std::to_string(i);
+    t.UID = "uid-" + std::to_string(i);
+    t.AgentName = "test-agent";
+    t.Status.Phase = "ReadyForLLM";
+    t.Status.Status = "Ready";
+    t.Status.ContextWindow = task::buildInitialContextWindow(
+        {}, system_prompt, prompt_tokens > 0 ? synth_text(seed, i, user_len) : std::string("What is the capital of France?"));
+    store.Put("Task", t.Name, task::task_to_json(t));
+  }
+
+  std::atomic<int> next{0};
+  std::atomic<long long> reconciles{0};
+  std::mutex lat_mu;
+  std::vector<double> lat_ms;
+  std::map<std::string, int> phases;
+  uint64_t digest = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto worker = [&]() {
+    task::StateMachine sm(&store, &rec);
+    sm.emulate_lease = lease;
+    while (true) {
+      const int i = next.fetch_add(1);
+      if (i >= n_tasks) break;
+      const std::string name = "task-" + std::to_string(i);
+      int steps = 0;
+      while (steps < 8) {
+        Json tj;
+        if (!store.Get("Task", name, &tj)) break;  // r.getTask (task_controller.go:216)
+        task::Task t;
+        task::task_from_json(tj, &t);
+        if (t.Status.Phase == "ReadyForLLM") {
+          const auto s0 = std::chrono::steady_clock::now();
+          task::ClientFactory factory = [&](std::string* cerr) -> std::unique_ptr<llmclient::LLMClient> {
+            auto c = llmclient::NewLLMClient(provider, "test-key", bc, engine, cerr);
+            if (c && provider == "local" && tool_loop && steps == 0 && !tools.empty()) {
+              // scripted step 1: force the model's output to be a tool call (BASELINE config 3)
+              const std::string call = "{\"name\": \"" + tools[0].Function.Name +
+                                       "\", \"parameters\": {\"url\": \"https://api.example.com/data\"}}";
+              Json ext = Json::object();
+              Json forced = Json::array();
+              for (unsigned char ch : call) forced.push(Json((int)ch));
+              forced.push(Json(TOK_EOT));
+              ext.set("force_tokens", forced);
+              static_cast<llmclient::LocalClient*>(c.get())->set_extension(ext);
+            }
+            return c;
+          };
+          llmclient::Context ctx;
+          std::string err;
+          sm.sendLLMRequest(ctx, &t, tools, factory, &err);
+          const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count();
+          ++reconciles;
+          {
+            std::lock_guard<std::mutex> lk(lat_mu);
+            lat_ms.push_back(ms);
+          }
+          ++steps;
+          if (!err.empty()) break;  // would requeue after 5 s; out of the timed loop
+        } else if (t.Status.Phase == "ToolCallsPending") {
+          // the (out of scope) ToolCall controller "executes" instantly with a fixed result
+          for (Json& tcj : store.ListToolCalls(name, t.Status.ToolCallRequestID)) {
+            task::ToolCall tc;
+            task::toolcall_from_json(tcj, &tc);
+            tc.StatusStatus = "Succeeded";
+            tc.StatusResult = "{\"data\": \"" + synth_text(seed ^ 0x5151, i, 96) + "\"}";
+            store.Put("ToolCall", tc.Name, task::toolcall_to_json(tc));
+          }
+          std::string err;
+          sm.checkToolCalls(&t, &err);
+        } else {
+          break;  // FinalAnswer / Failed
+        }
+      }
+      Json tj;
+      if (store.Get("Task", name, &tj)) {
+        task::Task t;
+        task::task_from_json(tj, &t);
+        std::lock_guard<std::mutex> lk(lat_mu);
+        ++phases[t.Status.Phase];
+        uint64_t h = 1469598103934665603ull;
+        const std::string d = t.Status.Output + "|" + t.Status.Phase;
+        for (unsigned char ch : d) { h ^= ch; h *= 1099511628211ull; }
+        digest ^= mix64(h + (uint64_t)i);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int w = 0; w < workers; ++w) pool.emplace_back(worker);
+  for (auto& th : pool) th.join();
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  std::sort(lat_ms.begin(), lat_ms.end());
+  Json out = Json::object();
+  out.set("reconciles", Json((long long)reconciles.load()));
+  out.set("tasks", Json(n_tasks));
+  out.set("workers", Json(workers));
+  out.set("wall_s", Json(wall));
+  out.set("reconciles_per_s", Json(wall > 0 ? reconciles.load() / wall : 0.0));
+  if (!lat_ms.empty()) {
+    out.set("step_ms_p50", Json(lat_ms[lat_ms.size() / 2]));
+    out.set("step_ms_p99", Json(lat_ms[std::min(lat_ms.size() - 1, (size_t)(lat_ms.size() * 0.99))]));
+  }
+  out.set("store_writes", Json(store.writes()));
+  out.set("store_reads", Json(store.reads()));
+  out.set("prompt_tokens", Json(prompt_tokens > 0 ? prompt_tokens : overhead + user_len));
+  Json ph = Json::object();
+  for (auto& kv : phases) ph.set(kv.first, Json(kv.second));
+  out.set("final_phases", ph);
+  char dbuf[32];
+  snprintf(dbuf, sizeof dbuf, "%016llx", (unsigned long long)digest);
+  out.set("digest", Json(std::string(dbuf)));
+  return ret_json(out, result_json_out);
+}

@@ -225,6 +225,71 @@ static bool parse_url(const std::string& url, std::string* host, int* port, std:
   return !host->empty();
 }
 
+// One persistent connection per worker thread and endpoint, like Go's http.Transport keep-alive
+// pool that langchaingo's openai client uses.
+namespace {
+struct Conn {
+  int fd = -1;
+  std::string key;
+  std::string acc;
+  ~Conn() { if (fd >= 0) close(fd); }
+};
+thread_local Conn t_conn;
+
+bool conn_open(Conn& c, const std::string& host, int port) {
+  const std::string key = host + ":" + std::to_string(port);
+  if (c.fd >= 0 && c.key == key) return true;
+  if (c.fd >= 0) { close(c.fd); c.fd = -1; }
+  c.acc.clear();
+  int fd = socket(AF_INET, SOCK_STREAM, 0);
+  if (fd < 0) return false;
+  int one = 1;
+  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+  sockaddr_in addr;
+  memset(&addr, 0, sizeof addr);
+  addr.sin_family = AF_INET;
+  addr.sin_port = htons((uint16_t)port);
+  if (inet_pton(AF_INET, host == "localhost" ? "127.0.0.1" : host.c_str(), &addr.sin_addr) != 1 ||
+      connect(fd, (sockaddr*)&addr, sizeof addr) != 0) {
+    close(fd);
+    return false;
+  }
+  c.fd = fd;
+  c.key = key;
+  return true;
+}
+
+// returns false on transport failure; *status / *body filled on success
+bool round_trip(Conn& c, const std::string& req, int* status, std::string* body) {
+  size_t off = 0;
+  while (off < req.size()) {
+    ssize_t n = send(c.fd, req.data() + off, req.size() - off, MSG_NOSIGNAL);
+    if (n <= 0) return false;
+    off += (size_t)n;
+  }
+  char buf[16384];
+  size_t he;
+  while ((he = c.acc.find("\r\n\r\n")) == std::string::npos) {
+    ssize_t n = recv(c.fd, buf, sizeof buf, 0);
+    if (n <= 0) return false;
+    c.acc.append(buf, (size_t)n);
+  }
+  if (c.acc.size() < 12) return false;
+  *status = atoi(c.acc.c_str() + 9);
+  size_t cl = c.acc.find("Content-Length:");
+  const size_t len = (cl == std::string::npos || cl > he) ? 0 : (size_t)atoll(c.acc.c_str() + cl + 15);
+  const size_t need = he + 4 + len;
+  while (c.acc.size() < need) {
+    ssize_t n = recv(c.fd, buf, sizeof buf, 0);
+    if (n <= 0) return false;
+    c.acc.append(buf, (size_t)n);
+  }
+  *body = c.acc.substr(he + 4, len);
+  c.acc.erase(0, need);
+  return true;
+}
+}  // namespace
+
 bool HTTPClient::SendRequest(const Context&, const std::vector<Message>& messages,
                              const std::vector<Tool>& tools, Message* out, Error* err) {
   std::string host, path;
@@ -234,48 +299,21 @@ bool HTTPClient::SendRequest(const Context&, const std::vector<Message>& message
     return false;
   }
   const std::string body = build_chat_request_json(cfg_.Model, messages, tools, 0, nullptr);
-  std::string req = "POST " + path + "/chat/completions HTTP/1.1\r\nHost: " + host + ":" + std::to_string(port) +
-                    "\r\nContent-Type: application/json\r\nAuthorization: Bearer " + api_key_ +
-                    "\r\nConnection: close\r\nContent-Length: " + std::to_string(body.size()) + "\r\n\r\n" + body;
-  int fd = socket(AF_INET, SOCK_STREAM, 0);
-  if (fd < 0) { err->Message = "model API call failed: socket()"; return false; }
-  int one = 1;
-  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
-  sockaddr_in addr;
-  memset(&addr, 0, sizeof addr);
-  addr.sin_family = AF_INET;
-  addr.sin_port = htons((uint16_t)port);
-  if (inet_pton(AF_INET, host == "localhost" ? "127.0.0.1" : host.c_str(), &addr.sin_addr) != 1) {
-    close(fd);
-    err->Message = "model API call failed: cannot resolve " + host;
-    return false;
+  const std::string req = "POST " + path + "/chat/completions HTTP/1.1\r\nHost: " + host + ":" + std::to_string(port) +
+                          "\r\nContent-Type: application/json\r\nAuthorization: Bearer " + api_key_ +
+                          "\r\nContent-Length: " + std::to_string(body.size()) + "\r\n\r\n" + body;
+  int status = 0;
+  std::string rbody;
+  bool ok = false;
+  for (int attempt = 0; attempt < 2 && !ok; ++attempt) {  // one reconnect if a pooled conn went stale
+    if (!conn_open(t_conn, host, port)) {
+      err->Message = "model API call failed: connect " + host + ":" + std::to_string(port) + " failed";
+      return false;
+    }
+    ok = round_trip(t_conn, req, &status, &rbody);
+    if (!ok) { close(t_conn.fd); t_conn.fd = -1; }
   }
-  if (connect(fd, (sockaddr*)&addr, sizeof addr) != 0) {
-    close(fd);
-    err->Message = "model API call failed: connect " + host + ":" + std::to_string(port) + " failed";
-    return false;
-  }
-  size_t off = 0;
-  while (off < req.size()) {
-    ssize_t n = send(fd, req.data() + off, req.size() - off, MSG_NOSIGNAL);
-    if (n <= 0) { close(fd); err->Message = "model API call failed: send failed"; return false; }
-    off += (size_t)n;
-  }
-  std::string resp;
-  char buf[8192];
-  while (true) {
-    ssize_t n = recv(fd, buf, sizeof buf, 0);
-    if (n <= 0) break;
-    resp.append(buf, (size_t)n);
-  }
-  close(fd);
-  size_t hdr_end = resp.find("\r\n\r\n");
-  if (hdr_end == std::string::npos || resp.size() < 12) {
-    err->Message = "model API call failed: malformed HTTP response";
-    return false;
-  }
-  const int status = atoi(resp.c_str() + 9);
-  const std::string rbody = resp.substr(hdr_end + 4);
+  if (!ok) { err->Message = "model API call failed: connection reset"; return false; }
   if (status != 200) {
     // NOTE: the reference wraps every provider failure as a plain error (langchaingo_client.go:
     // 103-105) and never builds an LLMRequestError itself; restated faithfully.

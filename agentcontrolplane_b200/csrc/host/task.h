@@ -1,0 +1,116 @@
+// host/task.h — C++ mirror of the Task reconciler's LLM step (the caller side of the boundary):
+//   StateMachine.sendLLMRequest   acp/internal/controller/task/state_machine.go:162-288
+//   processLLMResponse            :605-674      createToolCalls   :676-731
+//   handleLLMError                :733-790      checkToolCalls    :291-341
+//   buildInitialContextWindow     task_helpers.go:13-44    buildToolTypeMap :48-54
+//   validation.*                  acp/internal/validation/task_validation.go:16-87
+// Kubernetes itself is out of scope: the API server is emulated by an in-memory
+// object store that JSON-(de)serialises every object on Get / Update / Create, so the per-step
+// API traffic of the reference (>= 4 writes + M ToolCall creates) stays on the clock.
+#pragma once
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "llmclient.h"
+
+namespace acp {
+namespace task {
+
+using llmclient::Message;
+using llmclient::Tool;
+
+constexpr double DefaultRequeueDelay = 5.0;  // task_controller.go:23
+
+struct Result {  // ctrl.Result
+  bool Requeue = false;
+  double RequeueAfter = 0;
+  bool IsZero() const { return !Requeue && RequeueAfter == 0; }
+};
+
+struct Event { std::string Type, Reason, Message; };
+struct Recorder {
+  std::mutex mu;
+  std::vector<Event> events;
+  void Emit(const std::string& type, const std::string& reason, const std::string& message) {
+    std::lock_guard<std::mutex> lk(mu);
+    events.push_back(Event{type, reason, message});
+  }
+};
+
+struct TaskStatus {  // acp.TaskStatus (acp/api/v1alpha1/task_types.go:108-158), fields on this path
+  bool Ready = false;
+  std::string Status, StatusDetail, Phase, Output, Error, ToolCallRequestID;
+  std::vector<Message> ContextWindow;
+};
+struct Task {
+  std::string Name, Namespace = "default", UID, AgentName, UserMessage;
+  std::map<std::string, std::string> Labels;
+  TaskStatus Status;
+};
+struct ToolCall {  // acp.ToolCall (toolcall_types.go:26-45) as created by createToolCalls
+  std::string Name, Namespace;
+  std::map<std::string, std::string> Labels;
+  std::string OwnerName, OwnerUID;
+  std::string ToolCallID, TaskRef, ToolRef, ToolType, Arguments;
+  std::string StatusStatus, StatusResult;  // filled by the (out of scope) ToolCall controller
+};
+
+Json task_to_json(const Task& t);
+bool task_from_json(const Json& j, Task* t);
+Json toolcall_to_json(const ToolCall& tc);
+bool toolcall_from_json(const Json& j, ToolCall* tc);
+
+// In-memory stand-in for the kube-apiserver: objects live as serialised JSON strings.
+class ObjectStore {
+ public:
+  bool Get(const std::string& kind, const std::string& name, Json* out);
+  void Put(const std::string& kind, const std::string& name, const Json& obj);  // create or update
+  bool Delete(const std::string& kind, const std::string& name);
+  std::vector<Json> ListToolCalls(const std::string& task, const std::string& request_id);
+  long long writes() const { return writes_; }
+  long long reads() const { return reads_; }
+
+ private:
+  std::mutex mu_;
+  std::map<std::string, std::string> objs_;  // "kind/name" -> JSON text
+  long long writes_ = 0, reads_ = 0;
+};
+
+// pure helpers
+std::vector<Message> buildInitialContextWindow(const std::vector<Message>& contextWindow,
+                                               const std::string& systemPrompt,
+                                               const std::string& userMessage);
+std::map<std::string, std::string> buildToolTypeMap(const std::vector<Tool>& tools);
+std::string ValidateTaskMessageInput(const std::string& userMessage, const std::vector<Message>& cw);
+std::string GetUserMessagePreview(const std::string& userMessage, const std::vector<Message>& cw);
+std::string GenerateK8sRandomString(int n);
+std::vector<Tool> ConvertSubAgents(const std::vector<std::pair<std::string, std::string>>& agents);
+std::vector<Tool> ConvertMCPTools(const std::vector<Json>& mcpTools, const std::string& serverName);
+
+using ClientFactory = std::function<std::unique_ptr<llmclient::LLMClient>(std::string* err)>;
+
+class StateMachine {
+ public:
+  StateMachine(ObjectStore* store, Recorder* recorder) : store_(store), recorder_(recorder) {}
+  // The LLM step.  `err` receives the returned Go error text ("" = nil).
+  Result sendLLMRequest(const llmclient::Context& ctx, Task* task, const std::vector<Tool>& tools,
+                        const ClientFactory& factory, std::string* err);
+  Result processLLMResponse(const Message& output, Task* task, Task* statusUpdate,
+                            const std::vector<Tool>& tools, std::string* err);
+  Result createToolCalls(Task* task, Task* statusUpdate, const std::vector<llmclient::MessageToolCall>& toolCalls,
+                         const std::vector<Tool>& tools, std::string* err);
+  Result handleLLMError(Task* statusUpdate, const llmclient::Error& e, std::string* err);
+  Result checkToolCalls(Task* task, std::string* err);
+  // when true the per-step Lease create/delete of acquireTaskLease/releaseTaskLease
+  // (state_machine.go:1069-1145) is emulated as two store writes (reference behaviour)
+  bool emulate_lease = true;
+
+ private:
+  ObjectStore* store_;
+  Recorder* recorder_;
+};
+
+}  // namespace task
+}  // namespace acp

@@ -274,6 +274,7 @@ int Model::forward(const StepInput& in) {
     return -1;
   ACP_CUDA_CHECK(cudaSetDevice(device_));
   ACP_CUDA_CHECK(cudaMemcpyAsync(d_ints_, h_ints_, ints_used_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  h2d_bytes_ += (long long)(ints_used_ * sizeof(int));
   auto dev = [&](const int* hp) { return d_ints_ + (hp - h_ints_); };
   const int* d_tok = dev(in.tok);
   const int* d_pos = dev(in.pos);
@@ -349,10 +350,13 @@ int Model::forward(const StepInput& in) {
     } else {
       ACP_CUDA_CHECK(cudaMemcpyAsync(d_sparams_, h_sparams_, in.n_sample * sizeof(SampleParams),
                                      cudaMemcpyHostToDevice, stream_));
+      h2d_bytes_ += (long long)(in.n_sample * sizeof(SampleParams));
       ACP_TRY(launch_sample(logits_, c.vocab, in.n_sample, d_sparams_, d_tokens_, stream_));
     }
     ++launches_;
     ACP_CUDA_CHECK(cudaMemcpyAsync(h_tokens_, d_tokens_, in.n_sample * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    d2h_bytes_ += (long long)(in.n_sample * sizeof(int));
+    if (in.want_logits) d2h_bytes_ += (long long)in.n_sample * c.vocab * (long long)sizeof(float);
     if (in.want_logits)
       ACP_CUDA_CHECK(cudaMemcpyAsync(h_logits_, logits_, (size_t)in.n_sample * c.vocab * sizeof(float),
                                      cudaMemcpyDeviceToHost, stream_));

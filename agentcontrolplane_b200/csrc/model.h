@@ -86,6 +86,8 @@ class Model {
   const ModelLimits& limits() const { return lim_; }
   int device() const { return device_; }
   long long launches() const { return launches_; }
+  long long h2d_bytes() const { return h2d_bytes_; }
+  long long d2h_bytes() const { return d2h_bytes_; }
   // test hooks: copy tensors back to the host
   int debug_read_weight(int layer, int which, uint16_t* out, size_t n, size_t offset);
 
@@ -99,7 +101,7 @@ class Model {
   ModelLimits lim_;
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
-  long long launches_ = 0;
+  long long launches_ = 0, h2d_bytes_ = 0, d2h_bytes_ = 0;
 
   struct Layer {
     __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;

@@ -1,0 +1,254 @@
+"""CPU tests of the product's host side (C++ mirror of the reference's llmclient + Task LLM step,
+chat template, tokenizer, tool-call extraction) against the oracle and the reference's goldens.
+No GPU: only JSON-in/JSON-out hooks of include/acp_host.h are called."""
+import copy
+import json
+import os
+import re
+
+import pytest
+
+from agentcontrolplane_b200 import host
+from oracle import boundary as B
+from oracle import chat_oracle as C
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_goldens.json")))
+FX = G["fixtures"]
+
+TOOLS_WIRE = [{"type": "function", "function": {"name": "fetch__fetch", "description": "Fetch a URL",
+                                                 "parameters": {"type": "object", "properties": {"url": {"type": "string"}}, "required": ["url"]}}}]
+
+
+def _task(phase="ReadyForLLM", window=None, name=None):
+    return {"metadata": {"name": name or FX["task_name"], "namespace": "default", "uid": "uid-1"},
+            "spec": {"agentRef": {"name": FX["agent_name"]}},
+            "status": {"phase": phase, "status": "Ready", "contextWindow": window if window is not None else [
+                {"role": "system", "content": FX["system_prompt"]}, {"role": "user", "content": FX["user_message"]}]}}
+
+
+def _reasons(out):
+    return [e["reason"] for e in out["events"]]
+
+
+def _oracle_step(task, tools, mock):
+    class Cl:
+        def send_request(self, messages, tools):
+            if "error" in mock:
+                raise RuntimeError(mock["error"])
+            if "request_error" in mock:
+                raise B.LLMRequestError(mock["request_error"]["status"], mock["request_error"]["message"])
+            return copy.deepcopy(mock["message"])
+    t, rec, tcs = copy.deepcopy(task), B.Recorder(), []
+    res, err = B.send_llm_request(t, tools, Cl(), rec, tcs)
+    return t, res, err, rec, tcs
+
+
+# ------------------------------------------------------------------ Task step: goldens + oracle
+def test_G1_final_answer_host_matches_reference_and_oracle():
+    g = G["G1_final_answer"]
+    out = host.task_step({"op": "sendLLMRequest", "task": _task(), "tools": [],
+                          "llm": {"provider": "mock", "mock": {"message": g["llm_output"]}}})
+    st = out["task"]["status"]
+    assert st["phase"] == "FinalAnswer" and "LLM final response received" in st["statusDetail"]
+    assert st["output"] == g["llm_output"]["content"]
+    assert len(st["contextWindow"]) == 3 and st["contextWindow"][2]["role"] == "assistant"
+    assert out["result"] == {"requeue": False, "requeueAfter": 0} and out["error"] == ""
+    assert "SendingContextWindowToLLM" in _reasons(out) and "LLMFinalAnswer" in _reasons(out)
+    ot, _, _, orec, _ = _oracle_step(_task(), [], {"message": g["llm_output"]})
+    for k in ("phase", "output", "statusDetail", "status"):
+        assert st[k] == ot["status"][k]
+    assert st["contextWindow"] == ot["status"]["contextWindow"]
+    assert _reasons(out) == [r for (_, r, _) in orec.events]
+    # API traffic of the reference: lease create, status write, final status write, lease delete
+    assert out["store_writes"] == 4
+
+
+def test_G2_tool_call_host():
+    g = G["G2_tool_call"]
+    tools = B.convert_mcp_tools([{"name": "fetch", "description": "d"}], "fetch")
+    out = host.task_step({"op": "sendLLMRequest", "task": _task(window=[]), "tools": tools,
+                          "llm": {"provider": "mock", "mock": {"message": g["llm_output"]}}})
+    st = out["task"]["status"]
+    assert st["phase"] == "ToolCallsPending" and out["result"]["requeueAfter"] == 5
+    assert len(out["toolcalls"]) == 1
+    tc = out["toolcalls"][0]
+    assert tc["spec"]["toolRef"]["name"] == "fetch__fetch"
+    assert tc["spec"]["arguments"] == g["expect"]["arguments"]            # byte-identical
+    assert tc["spec"]["toolType"] == "MCP" and tc["spec"]["toolCallId"] == "1"
+    rid = st["toolCallRequestId"]
+    assert re.match(G["G10_id_format"]["regex"], rid) and len(rid) == 7
+    assert tc["metadata"]["name"] == "%s-%s-tc-%02d" % (FX["task_name"], rid, 1)
+    assert tc["metadata"]["labels"] == {"acp.humanlayer.dev/task": FX["task_name"], "acp.humanlayer.dev/toolcallrequest": rid}
+    assert tc["metadata"]["ownerReferences"][0]["controller"] is True
+    assert "ToolCallsPending" in _reasons(out) and "ToolCallCreated" in _reasons(out)
+
+
+def test_G3_G4_errors_host():
+    g3 = G["G3_generic_error"]
+    out = host.task_step({"op": "sendLLMRequest", "task": _task(), "tools": [],
+                          "llm": {"provider": "mock", "mock": {"error": g3["error"]}}})
+    st = out["task"]["status"]
+    assert out["error"] == g3["error"] and out["result"]["requeueAfter"] == 5
+    assert st["status"] == "Error" and st["phase"] == "ReadyForLLM" and st["error"] == g3["error"]
+    assert "LLMRequestFailed" in _reasons(out)
+    g4 = G["G4_4xx_error"]
+    out = host.task_step({"op": "sendLLMRequest", "task": _task(), "tools": [],
+                          "llm": {"provider": "mock", "mock": {"request_error": {"status": g4["status_code"], "message": g4["message"]}}}})
+    st = out["task"]["status"]
+    assert out["error"] == "" and out["result"] == {"requeue": False, "requeueAfter": 0}
+    assert st["status"] == "Error" and st["phase"] == "Failed"
+    assert g4["expect"]["error_contains"] in st["error"] and "LLMRequestFailed4xx" in _reasons(out)
+    ot, _, _, _, _ = _oracle_step(_task(), [], {"request_error": {"status": 400, "message": g4["message"]}})
+    assert st["error"] == ot["status"]["error"] and st["statusDetail"] == ot["status"]["statusDetail"]
+
+
+def test_G5_check_tool_calls_host():
+    g = G["G5_tool_results_fold_back"]
+    window = [{"role": "system", "content": FX["system_prompt"]}, {"role": "user", "content": FX["user_message"]},
+              {"role": "assistant", "content": "", "toolCalls": [
+                  {"id": "1", "type": "function", "function": {"name": "fetch__fetch", "arguments": "{}"}},
+                  {"id": "2", "type": "function", "function": {"name": "fetch__fetch", "arguments": "{}"}}]}]
+    task = _task(phase="ToolCallsPending", window=window)
+    task["status"]["toolCallRequestId"] = "abc1234"
+
+    def tcs(statuses):
+        return [{"metadata": {"name": f"{FX['task_name']}-abc1234-tc-{i + 1:02d}", "namespace": "default",
+                              "labels": {"acp.humanlayer.dev/task": FX["task_name"], "acp.humanlayer.dev/toolcallrequest": "abc1234"}},
+                 "spec": {"toolCallId": t["spec"]["toolCallId"], "taskRef": {"name": FX["task_name"]},
+                          "toolRef": {"name": "fetch__fetch"}, "toolType": "MCP", "arguments": "{}"},
+                 "status": {"status": s, "result": t["status"]["result"]}} for i, (t, s) in enumerate(zip(g["toolcalls"], statuses))]
+    out = host.task_step({"op": "checkToolCalls", "task": task, "toolcalls": tcs(["Succeeded", "Running"])})
+    assert out["result"]["requeueAfter"] == 5 and out["task"]["status"]["phase"] == "ToolCallsPending"
+    out = host.task_step({"op": "checkToolCalls", "task": task, "toolcalls": tcs(["Succeeded", "Error"])})
+    st = out["task"]["status"]
+    assert out["result"]["requeue"] is True and st["phase"] == "ReadyForLLM" and len(st["contextWindow"]) == 5
+    for t, m in zip(g["toolcalls"], st["contextWindow"][3:]):
+        assert m == {"role": "tool", "content": t["status"]["result"], "toolCallId": t["spec"]["toolCallId"]}
+
+
+def test_unsupported_provider_fails_like_the_reference():
+    out = host.task_step({"op": "sendLLMRequest", "task": _task(), "tools": [], "llm": {"provider": "bogus"}})
+    st = out["task"]["status"]
+    assert st["phase"] == "Failed" and "unsupported provider: bogus" in st["error"]
+    assert "LLMClientCreationFailed" in _reasons(out)
+    out = host.task_step({"op": "sendLLMRequest", "task": _task(), "tools": [], "llm": {"provider": "local"}})
+    assert out["task"]["status"]["phase"] == "Failed"      # no engine in this process: loud, no fallback
+
+
+# ------------------------------------------------------------------ wire conversion
+def test_request_body_matches_oracle():
+    window = [{"role": "system", "content": "s"}, {"role": "user", "content": "u \"q\" é"},
+              {"role": "assistant", "content": "", "toolCalls": [{"id": "1", "type": "function", "function": {"name": "f__g", "arguments": "{\"a\": 1}"}}]},
+              {"role": "tool", "content": "42", "toolCallId": "1"}, {"role": "weird", "content": "w"}]
+    tools = B.convert_mcp_tools([{"name": "g", "description": "d", "inputSchema": {"type": "object", "properties": {"a": {"type": "number"}}}}], "f")
+    got = host.build_chat_request("m", window, tools)
+    want = B.build_chat_request("m", window, tools)
+    assert got == want
+    assert "acpToolType" not in json.dumps(got)
+    assert "tools" not in host.build_chat_request("m", window, [])
+
+
+def test_response_flattening_matches_reference_fixtures():
+    g = G["G8_wire_fixtures"]
+    assert host.convert_response(g["content_body"]["body"]) == {"role": "assistant", "content": "test"}
+    m = host.convert_response(g["tool_body"]["body"])
+    e = g["tool_body"]["expect_tool"]
+    assert m["content"] == "" and m["toolCalls"] == [{"id": e["id"], "function": {"name": e["name"], "arguments": e["arguments"]}, "type": e["type"]}]
+    both = {"choices": [{"message": {"content": "hi"}}, {"message": {"content": "x", "tool_calls": [{"id": "a", "type": "function", "function": {"name": "n", "arguments": "{}"}}]}}]}
+    assert host.convert_response(both) == {k: v for k, v in B.convert_from_response(both).items()} | {"toolCalls": [{"id": "a", "function": {"name": "n", "arguments": "{}"}, "type": "function"}]}
+    assert host.convert_response({"choices": []}) == {"role": "assistant", "content": ""}
+
+
+# ------------------------------------------------------------------ template / tokenizer / parser
+CASES = [
+    ([{"role": "system", "content": "You are a helpful test assistant."}, {"role": "user", "content": "What is the capital of France?"}], []),
+    ([{"role": "user", "content": "no system"}], []),
+    ([{"role": "system", "content": "sys"}, {"role": "user", "content": "use a tool ☃"},
+      {"role": "assistant", "content": None, "tool_calls": [{"id": "c1", "type": "function", "function": {"name": "fetch__fetch", "arguments": "{\"url\": \"https://api.example.com/data\"}"}}]},
+      {"role": "tool", "tool_call_id": "c1", "content": "{\"data\": \"test-data\"}"}], TOOLS_WIRE),
+    ([{"role": "user", "content": "a"}, {"role": "assistant", "content": "b"}, {"role": "system", "content": "mid"}, {"role": "odd", "content": "c"}], TOOLS_WIRE),
+]
+
+
+@pytest.mark.parametrize("messages,tools", CASES)
+def test_template_matches_oracle(messages, tools):
+    req = {"messages": messages}
+    if tools:
+        req["tools"] = tools
+    got = host.render_prompt(req)
+    ids, text = C.render(messages, tools)
+    assert got["text"] == text
+    assert got["token_ids"] == ids
+    assert ids[0] == 128000 and ids[-3:] == [128007, 10, 10]
+    # byte-level tokenizer: every non-special id is the UTF-8 byte
+    assert bytes(t for t in ids if t < 256).decode() == re.sub(r"<\|[a-z_]+\|>", "", text)
+
+
+def test_request_validation_statuses():
+    assert host.render_prompt({"messages": []})["status"] == 400
+    assert host.render_prompt({"messages": [{"content": "x"}]})["status"] == 400
+    assert host.render_prompt({"messages": [{"role": "user", "content": "x"}], "stream": True})["status"] == 400
+    assert host.render_prompt({"messages": [{"role": "user", "content": "x"}], "max_tokens": 0})["status"] == 400
+    assert host.render_prompt({"messages": [{"role": "user", "content": "x"}], "temperature": -1})["status"] == 400
+    r = host.render_prompt({"messages": [{"role": "user", "content": [{"type": "text", "text": "parts"}]}]})
+    assert "parts" in r["text"]
+
+
+def test_decode_tokens_matches_oracle():
+    ids = list(range(0, 300)) + [1000, 65791, 65792, 127999, 128000, 128009, 128255, 33709, 42410]
+    assert host.decode_tokens(ids) == C.decode_tokens(ids)
+    assert host.decode_tokens([72, 105]) == b"Hi"
+
+
+PARSE_CASES = [
+    '{"name": "fetch__fetch", "parameters": {"url": "https://api.example.com/data"}}',
+    '  {"name":"fetch__fetch","parameters":{"url":  "x", "n": [1, 2, {"a": "}"}]}}\n',
+    '{"name": "fetch__fetch", "parameters": {"url": "a"}}\n{"name": "fetch__fetch", "parameters": {"url": "b"}}',
+    '{"name": "unknown_tool", "parameters": {}}',
+    '{"name": "fetch__fetch", "parameters": "not an object"}',
+    'The answer is {"name": "fetch__fetch"}',
+    '{"name": "fetch__fetch", "parameters": {"url": "a"}} trailing words',
+    'plain final answer', '', '{"broken": ',
+    '{"name": "fetch__fetch", "arguments": {"url": "\\u00e9\\n"}}',
+]
+
+
+@pytest.mark.parametrize("text", PARSE_CASES)
+def test_parse_completion_matches_oracle(text):
+    got = host.parse_completion(text, TOOLS_WIRE, "call_7_")
+    want = C.parse_completion(text, TOOLS_WIRE, "call_7_")
+    assert got == want
+    if "tool_calls" in got:
+        for tc in got["tool_calls"]:
+            assert tc["function"]["arguments"] in text            # verbatim substring
+            assert isinstance(json.loads(tc["function"]["arguments"]), dict)
+    assert host.parse_completion(text, [], "c") == {"content": text}   # no tools -> always content
+
+
+# ------------------------------------------------------------------ CPU reconcile loop over the stub server
+def test_config0_plumbing_over_stub_server():
+    """BASELINE config 0: 1 Task, stub completion server returning the reference's fixture body,
+    the reference's own (restated) openai path — no GPU anywhere."""
+    with host.StubServer() as srv:
+        out = host.task_step({"op": "sendLLMRequest", "task": _task(window=[
+            {"role": "system", "content": G["G8_wire_fixtures"]["window"]["system"]},
+            {"role": "user", "content": G["G8_wire_fixtures"]["window"]["user"]}]), "tools": [],
+            "llm": {"provider": "openai", "model": "gpt-4o", "baseURL": srv.base_url}})
+        st = out["task"]["status"]
+        assert st["phase"] == "FinalAnswer" and st["output"] == "test" and len(st["contextWindow"]) == 3
+        r = host.hostsim_run({"tasks": 200, "workers": 4, "provider": "openai", "model": "gpt-4o", "baseURL": srv.base_url})
+        assert r["reconciles"] == 200 and r["final_phases"] == {"FinalAnswer": 200}
+        assert r["store_writes"] >= 4 * 200 and r["reconciles_per_s"] > 0
+    tool_body = G["G8_wire_fixtures"]["tool_body"]["body"]
+    with host.StubServer(tool_body) as srv:
+        out = host.task_step({"op": "sendLLMRequest", "task": _task(), "tools": B.convert_mcp_tools([{"name": "fetch"}], "fetch"),
+                              "llm": {"provider": "openai", "model": "gpt-4o", "baseURL": srv.base_url}})
+        assert out["task"]["status"]["phase"] == "ToolCallsPending"
+        assert out["toolcalls"][0]["spec"]["arguments"] == G["G8_wire_fixtures"]["tool_body"]["expect_tool"]["arguments"]
+        assert out["toolcalls"][0]["spec"]["toolCallId"] == "tool-call-1"
+
+
+def test_connection_refused_is_a_retryable_error():
+    out = host.task_step({"op": "sendLLMRequest", "task": _task(), "tools": [],
+                          "llm": {"provider": "openai", "model": "m", "baseURL": "http://127.0.0.1:9/v1"}})
+    assert out["error"].startswith("model API call failed") and out["task"]["status"]["phase"] == "ReadyForLLM"
