@@ -369,7 +369,8 @@ bool Engine::step() {
       sp.temperature = s.sampling.temperature;
       sp.top_k = s.sampling.top_k;
       sp.top_p = s.sampling.top_p;
-      sp.seed = s.sampling.seed ^ (s.ticket * 0x9E3779B97F4A7C15ull);
+      // OpenAI `seed`: same seed + same request => same sample; without one, a per-ticket stream
+      sp.seed = s.sampling.seed ? s.sampling.seed : (s.ticket * 0x9E3779B97F4A7C15ull);
       sp.step = (uint32_t)gen_idx;
       if (s.sampling.temperature > 0.f) all_greedy = false;
       if (gen_idx < s.return_logits) want_logits = true;

@@ -107,9 +107,15 @@ def run_reference(args) -> dict:
     with host.StubServer() as srv:
         cfg = {"tasks": 2000, "workers": cores, "provider": "openai", "model": "gpt-4o", "baseURL": srv.base_url,
                "prompt_tokens": WORKLOAD["prompt_tokens"], "seed": 1}
-        probe = host.hostsim_run(dict(cfg, tasks=400))
-        # size one step to ~2 s of CPU work
-        cfg["tasks"] = max(200, min(200000, int(probe["reconciles_per_s"] * 2.0)))
+        # size one step to >= ~2 s of CPU work
+        cfg["tasks"] = 2000
+        while True:
+            t0 = time.perf_counter()
+            host.hostsim_run(cfg)
+            w = time.perf_counter() - t0
+            if w >= 1.5 or cfg["tasks"] >= 1000000:
+                break
+            cfg["tasks"] = int(cfg["tasks"] * max(2.0, min(16.0, 2.5 / max(w, 1e-3))))
         for _ in range(args.warmup):
             host.hostsim_run(cfg)
         t0 = time.perf_counter()
@@ -141,11 +147,15 @@ def cpu_baseline_sample() -> dict:
     with host.StubServer() as srv:
         cfg = {"tasks": 400, "workers": cores, "provider": "openai", "model": "gpt-4o", "baseURL": srv.base_url,
                "prompt_tokens": WORKLOAD["prompt_tokens"], "seed": 7}
-        probe = host.hostsim_run(cfg)
-        cfg["tasks"] = max(400, min(400000, int(probe["reconciles_per_s"] * 8.0)))  # ~8 s of CPU work
-        t0 = time.perf_counter()
-        r = host.hostsim_run(cfg)
-        wall = time.perf_counter() - t0
+        # grow the sample until it is ~10 s of CPU work (thread start-up dominates tiny samples)
+        cfg["tasks"] = 2000
+        while True:
+            t0 = time.perf_counter()
+            r = host.hostsim_run(cfg)
+            wall = time.perf_counter() - t0
+            if wall >= 8.0 or cfg["tasks"] >= 2000000:
+                break
+            cfg["tasks"] = int(cfg["tasks"] * max(2.0, min(16.0, 10.0 / max(wall, 1e-3))))
         one = host.hostsim_run(dict(cfg, workers=1, tasks=max(200, cfg["tasks"] // (2 * cores))))
     return {"value": r["reconciles"] / wall, "unit": "reconciles/s", "cores": cores, "kind": "port",
             "sample": f"{cfg['tasks']} Task reconciles ({WORKLOAD['prompt_tokens']}-token windows) of the restated Go loop "

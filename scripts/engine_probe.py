@@ -21,7 +21,7 @@ if len(sys.argv) > 5:
 t0 = time.time()
 eng = Engine(cfg)
 print("init s:", round(time.time() - t0, 2), flush=True)
-for rep in range(3):
+for rep in range(int(os.environ.get('REPS', '3'))):
     eng.stats_reset()
     rng = np.random.default_rng(rep)
     t0 = time.time()
