@@ -245,6 +245,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   const int n_tiles = tile_end - tile_begin;
   const int n_splits = (ctx + a.split_tokens - 1) / a.split_tokens;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
@@ -255,6 +256,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();  // K/V pages and q were written by the previous kernel (rope_kv)
 
   if (warp == CONSUMER_WARPS) {
     if (lane == 0)
@@ -341,6 +343,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
 // merge split partials: one CTA (128 threads = dims) per (sequence, head)
 __global__ void __launch_bounds__(128)
 attn_merge_kernel(AttnDecodeArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
   const int ctx = a.ctx_len[b];
   const int n_splits = (ctx + a.split_tokens - 1) / a.split_tokens;
@@ -379,6 +383,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   const int last_pos = pos0 + tq0 + blk_tokens - 1;
   const int n_tiles = last_pos / TILE_TOK + 1;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
@@ -389,6 +394,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
   if (warp == CONSUMER_WARPS) {
     if (lane == 0)
       produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
@@ -475,12 +481,10 @@ int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const A
   const int n_splits = (max_ctx + a.split_tokens - 1) / a.split_tokens;
   if (n_splits > a.max_splits) return -1;
   dim3 grid(num_seqs, a.kv_heads, n_splits);
-  attn_decode_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, s>>>(tm_k, tm_v, a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = acp_launch(attn_decode_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode launch: %s\n", cudaGetErrorString(e)); return -5; }
   if (n_splits > 1) {
-    attn_merge_kernel<<<dim3(num_seqs, a.heads), 128, 0, s>>>(a);
-    e = cudaGetLastError();
+    e = acp_launch(attn_merge_kernel, dim3(num_seqs, a.heads), dim3(128), 0, s, a);
     if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_merge launch: %s\n", cudaGetErrorString(e)); return -5; }
   }
   return 0;
@@ -494,8 +498,7 @@ int launch_attn_prefill(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const 
   const int G = a.heads / a.kv_heads;
   if (a.heads % a.kv_heads != 0 || G > 16 || (16 % G) != 0) return -1;
   dim3 grid(num_blocks, a.kv_heads);
-  attn_prefill_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, s>>>(tm_k, tm_v, a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = acp_launch(attn_prefill_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_prefill launch: %s\n", cudaGetErrorString(e)); return -5; }
   return 0;
 }

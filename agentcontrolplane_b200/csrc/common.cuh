@@ -26,6 +26,33 @@
   } while (0)
 
 // ---------------------------------------------------------------------------------
+// launch helper: cudaLaunchKernelEx with the programmatic-stream-serialization attribute
+// (ACP_PDL=0 in the environment turns the attribute off for A/B measurements)
+// ---------------------------------------------------------------------------------
+#include <stdlib.h>
+#include <utility>
+static inline bool acp_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACP_PDL"); v = (e && *e == '0') ? 0 : 1; }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t acp_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = acp_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// ---------------------------------------------------------------------------------
 // bf16 helpers.  Rounding is round-to-nearest-even everywhere, which is what the
 // oracle's bf16_round() does (oracle/llama_oracle.py).
 // ---------------------------------------------------------------------------------
@@ -65,6 +92,16 @@ ACP_DEVINL bool elect_one() {
 ACP_DEVINL uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
+
+// ---------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of a step calls pdl_launch_dependents() at
+// its top (the next kernel's CTAs may then be scheduled as soon as SM resources free up, so its
+// prologue — barrier init, TMEM alloc, descriptor prefetch, and for the GEMM the first weight
+// tiles — overlaps this kernel's tail) and pdl_wait() before touching anything a previous kernel
+// wrote.  Because every kernel waits, "my predecessor completed" holds transitively.
+// ---------------------------------------------------------------------------------
+ACP_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+ACP_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------
 // mbarrier

@@ -316,15 +316,18 @@ bool Engine::step() {
   std::vector<Sequence*> part;   // sequences in this step
   std::vector<int> take;
   bool prefill = false;
+  // A sequence is in prefill while prompt tokens remain un-cached (even a single one): prompt
+  // tokens always take the prefill arithmetic path, generated tokens always the decode path, so a
+  // sequence's result never depends on batch composition or chunk boundaries.
   for (auto& s : running_)
-    if ((int)s->tokens.size() - s->n_cached > 1) { prefill = true; break; }
+    if (s->n_cached < s->prompt_len) { prefill = true; break; }
   int T = 0, n_blocks = 0;
   const int blk_tokens = attn_prefill_block_tokens(model_.config().heads, model_.config().kv_heads);
   if (prefill) {
     int budget = lim.max_tokens;
     for (auto& s : running_) {
-      const int pending = (int)s->tokens.size() - s->n_cached;
-      if (pending <= 1) continue;
+      const int pending = s->prompt_len - s->n_cached;
+      if (pending <= 0) continue;
       if (budget == 0 || (int)part.size() == lim.max_batch) break;
       const int t = std::min(pending, budget);
       part.push_back(s.get());

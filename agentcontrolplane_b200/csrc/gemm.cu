@@ -77,8 +77,8 @@ static int launch_one(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t s
   a.M = g.M; a.N = g.N; a.K = g.K; a.splits = g.splits; a.ld = g.ld; a.n_cap = g.n_cap;
   a.out = g.out; a.amax_val = g.amax_val; a.amax_idx = g.amax_idx; a.n_dev = g.n_dev;
   dim3 grid((g.M + GEMM_BM - 1) / GEMM_BM, (g.N + BN - 1) / BN, g.splits);
-  gemm_wx_kernel<BN, EPI><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(*g.w, tx, a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = acp_launch(gemm_wx_kernel<BN, EPI>, grid, dim3(GEMM_THREADS), GemmCfg<BN>::kSmemBytes,
+                             stream, *g.w, tx, a);
   if (e != cudaSuccess) {
     fprintf(stderr, "[acp_infer] gemm launch failed BN=%d EPI=%d: %s\n", BN, EPI,
             cudaGetErrorString(e));
@@ -93,6 +93,7 @@ static int launch_bn(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t st
     case EPI_BF16: return launch_one<BN, EPI_BF16>(g, tx, stream);
     case EPI_F32: return launch_one<BN, EPI_F32>(g, tx, stream);
     case EPI_ARGMAX: return launch_one<BN, EPI_ARGMAX>(g, tx, stream);
+    case EPI_SWIGLU: return launch_one<BN, EPI_SWIGLU>(g, tx, stream);
   }
   return -1;
 }
@@ -120,7 +121,8 @@ static int set_attr() {
 }
 template <int BN>
 static int set_attr_bn() {
-  return set_attr<BN, EPI_BF16>() | set_attr<BN, EPI_F32>() | set_attr<BN, EPI_ARGMAX>();
+  return set_attr<BN, EPI_BF16>() | set_attr<BN, EPI_F32>() | set_attr<BN, EPI_ARGMAX>() |
+         set_attr<BN, EPI_SWIGLU>();
 }
 int gemm_setup_attributes() {
   int rc = set_attr_bn<16>() | set_attr_bn<32>() | set_attr_bn<64>() | set_attr_bn<128>() |

@@ -36,6 +36,7 @@ enum GemmEpi : int {
   EPI_BF16 = 0,     // out_bf16[n*ld + m]
   EPI_F32 = 1,      // out_f32[(split*n_cap + n)*ld + m]      (split-K partials, logits)
   EPI_ARGMAX = 2,   // per (n, m-tile): max value + lowest index; optional fp32 logits
+  EPI_SWIGLU = 3,   // rows interleaved (gate_j, up_j): out_bf16[n*ld + m/2] = bf16(bf16(silu(g))*u)
 };
 
 struct GemmArgs {
@@ -85,6 +86,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   const int kb_end = (int)(((long long)nkb_total * (split + 1)) / args.splits);
   const int nkb = kb_end - kb_begin;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
@@ -104,9 +106,20 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      // Phase A: the first ring-full of WEIGHT tiles does not depend on the previous kernel, so
+      // it is issued before the grid-dependency wait (hides the HBM ramp under that kernel's tail).
+      const int pre = nkb < STAGES ? nkb : STAGES;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_arrive_expect_tx(&full_bar[kb], Cfg::kStageBytes);
+        tma_load_2d(smem + kb * Cfg::kStageBytes, &tmap_w, &full_bar[kb], (kb_begin + kb) * GEMM_BK, m0, kEvictFirst);
+      }
+      pdl_wait();  // activations come from the previous kernel
+      for (int kb = 0; kb < pre; ++kb)
+        tma_load_2d(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tmap_x, &full_bar[kb],
+                    (kb_begin + kb) * GEMM_BK, n0, kEvictLast);
+      int s = pre % STAGES;
+      uint32_t ph = (pre == STAGES) ? 1u : 0u;
+      for (int kb = pre; kb < nkb; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* a_dst = smem + s * Cfg::kStageBytes;
         uint8_t* b_dst = a_dst + Cfg::kABytes;
@@ -120,6 +133,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
+    pdl_wait();
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
       int s = 0;
@@ -147,6 +161,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     // ===== epilogue warps 2..5 =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int m = m0 + q * 32 + lane;
+    pdl_wait();  // outputs may still be read by the previous kernels until they complete
     int n_valid = args.n_dev ? *args.n_dev : args.N;
     if (nkb > 0) {
       mbar_wait(accum_bar, 0);
@@ -177,6 +192,20 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           const int n = n0 + c + j;
           if (n < n_valid && m < args.M)
             out[((size_t)split * args.n_cap + n) * args.ld + m] = __uint_as_float(r[j]);
+        }
+      } else if constexpr (EPI == EPI_SWIGLU) {
+        // W rows are stored interleaved: even row = gate_j, odd row = up_j (j = row / 2), so the
+        // pair sits in adjacent TMEM lanes = adjacent threads of this warp.
+        __nv_bfloat16* out = (__nv_bfloat16*)args.out;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c + j;
+          const float v = bf16_round(__uint_as_float(r[j]));      // the GEMM's bf16 rounding point
+          const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+          if ((lane & 1) == 0 && n < n_valid && m < args.M) {
+            const float act = bf16_round(v / (1.0f + expf(-v)));
+            out[(size_t)n * args.ld + (m >> 1)] = __float2bfloat16_rn(act * other);
+          }
         }
       } else {  // EPI_ARGMAX
         float* out = (float*)args.out;

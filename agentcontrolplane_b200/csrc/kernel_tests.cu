@@ -46,6 +46,7 @@ extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int 
   size_t out_bytes = 0;
   if (epi == EPI_BF16) out_bytes = (size_t)N * M * 2;
   else if (epi == EPI_F32) out_bytes = (size_t)splits * N * M * 4;
+  else if (epi == EPI_SWIGLU) out_bytes = (size_t)N * (M / 2) * 2;
   else if (out != nullptr) out_bytes = (size_t)N * M * 4;
   if (dout.alloc(out_bytes)) return -5;
   ACP_CUDA_CHECK(cudaMemset(dout.p, 0xff, out_bytes ? out_bytes : 1));
@@ -57,7 +58,7 @@ extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int 
   if (tma_make_act(&mx, dx.p, n_pad, K) != 0) return -5;
   GemmLaunch g;
   g.w = &mw.w; g.x = &mx; g.M = M; g.N = N; g.K = K; g.splits = splits; g.epi = epi;
-  g.ld = M; g.n_cap = N;
+  g.ld = (epi == EPI_SWIGLU) ? M / 2 : M; g.n_cap = N;
   g.out = (epi == EPI_ARGMAX && out == nullptr) ? nullptr : dout.p;
   g.amax_val = (float*)dval.p; g.amax_idx = (int*)didx.p; g.bn_override = bn;
   int rc = gemm_launch(g, 0);

@@ -7,6 +7,14 @@
 
 namespace acp {
 
+#define ACP_LAUNCH(name, call)                                                         \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      fprintf(stderr, "[acp_infer] launch %s failed: %s\n", name, cudaGetErrorString(_e)); \
+      return -5;                                                                       \
+    }                                                                                  \
+  } while (0)
 #define ACP_LAUNCH_CHECK(name)                                                         \
   do {                                                                                 \
     cudaError_t _e = cudaGetLastError();                                               \
@@ -31,10 +39,20 @@ ACP_DEVINL void gemm_out_load4(const GemmOutDev& g, int t, int m, float (&v)[4])
     v[0] = bf16_lo(raw.x); v[1] = bf16_hi(raw.x); v[2] = bf16_lo(raw.y); v[3] = bf16_hi(raw.y);
   } else {
     const float* p = (const float*)g.ptr + (size_t)t * g.ld + m;
-    float4 acc = *reinterpret_cast<const float4*>(p);
-    for (int s = 1; s < g.splits; ++s) {  // fixed order => deterministic
-      const float4 q = *reinterpret_cast<const float4*>(p + (size_t)s * g.n_cap * g.ld);
-      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    const size_t plane = (size_t)g.n_cap * g.ld;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // Planes are loaded 8 at a time (all loads in flight together), then added in index order:
+    // the sum is ((((0 + p0) + p1) + p2) ...) regardless of the batching => deterministic.
+    for (int s0 = 0; s0 < g.splits; s0 += 8) {
+      float4 q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        q[j] = (s0 + j < g.splits) ? *reinterpret_cast<const float4*>(p + (size_t)(s0 + j) * plane)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (s0 + j < g.splits) { acc.x += q[j].x; acc.y += q[j].y; acc.z += q[j].z; acc.w += q[j].w; }
+      }
     }
     v[0] = bf16_round(acc.x); v[1] = bf16_round(acc.y); v[2] = bf16_round(acc.z); v[3] = bf16_round(acc.w);
   }
@@ -45,6 +63,8 @@ ACP_DEVINL void gemm_out_load4(const GemmOutDev& g, int t, int m, float (&v)[4])
 // ---------------------------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ tok, const __nv_bfloat16* __restrict__ E,
                              __nv_bfloat16* __restrict__ x, int hidden) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(E + (size_t)tok[t] * hidden);
   uint4* dst = reinterpret_cast<uint4*>(x + (size_t)t * hidden);
@@ -53,8 +73,7 @@ __global__ void embed_kernel(const int* __restrict__ tok, const __nv_bfloat16* _
 int launch_embed(const int* tok, const __nv_bfloat16* E, __nv_bfloat16* x, int T, int hidden,
                  cudaStream_t s) {
   if (T <= 0) return 0;
-  embed_kernel<<<T, 128, 0, s>>>(tok, E, x, hidden);
-  ACP_LAUNCH_CHECK("embed");
+  ACP_LAUNCH("embed", acp_launch(embed_kernel, dim3(T), dim3(128), 0, s, tok, E, x, hidden));
   return 0;
 }
 
@@ -65,6 +84,8 @@ __global__ void __launch_bounds__(256)
 add_rmsnorm_kernel(__nv_bfloat16* __restrict__ x, GemmOutDev add, const __nv_bfloat16* __restrict__ gain,
                    __nv_bfloat16* __restrict__ xn, const int* __restrict__ row_map, int hidden,
                    float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float row[];
   __shared__ float red[8];
   const int out_row = blockIdx.x;
@@ -112,9 +133,8 @@ int launch_add_rmsnorm(__nv_bfloat16* x, const GemmOut& add, const __nv_bfloat16
                        __nv_bfloat16* xn, const int* row_map, int T, int hidden, float eps,
                        cudaStream_t s) {
   if (T <= 0) return 0;
-  add_rmsnorm_kernel<<<T, 256, hidden * sizeof(float), s>>>(x, to_dev(add), gain, xn, row_map,
-                                                              hidden, eps);
-  ACP_LAUNCH_CHECK("add_rmsnorm");
+  ACP_LAUNCH("add_rmsnorm", acp_launch(add_rmsnorm_kernel, dim3(T), dim3(256), hidden * sizeof(float), s, x,
+                                       to_dev(add), gain, xn, row_map, hidden, eps));
   return 0;
 }
 
@@ -128,6 +148,8 @@ rope_kv_kernel(GemmOutDev qkv, const int* __restrict__ pos, const int* __restric
                const float* __restrict__ sin_tab, __nv_bfloat16* __restrict__ qbuf,
                __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache, int heads,
                int kv_heads) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x;
   const int p = pos[t];
   const int seq = seq_of_row[t];
@@ -179,10 +201,9 @@ rope_kv_kernel(GemmOutDev qkv, const int* __restrict__ pos, const int* __restric
 }
 int launch_rope_kv(const RopeKvArgs& a, cudaStream_t s) {
   if (a.T <= 0) return 0;
-  rope_kv_kernel<<<a.T, 256, 0, s>>>(to_dev(a.qkv), a.pos, a.seq_of_row, a.page_table, a.max_pages,
-                                     a.cos_tab, a.sin_tab, a.qbuf, a.k_cache, a.v_cache, a.heads,
-                                     a.kv_heads);
-  ACP_LAUNCH_CHECK("rope_kv");
+  ACP_LAUNCH("rope_kv", acp_launch(rope_kv_kernel, dim3(a.T), dim3(256), 0, s, to_dev(a.qkv), a.pos,
+                                   a.seq_of_row, a.page_table, a.max_pages, a.cos_tab, a.sin_tab, a.qbuf,
+                                   a.k_cache, a.v_cache, a.heads, a.kv_heads));
   return 0;
 }
 
@@ -191,6 +212,8 @@ int launch_rope_kv(const RopeKvArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 swiglu_kernel(GemmOutDev gu, __nv_bfloat16* __restrict__ h, int ffn) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.y;
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (j >= ffn) return;
@@ -210,8 +233,7 @@ swiglu_kernel(GemmOutDev gu, __nv_bfloat16* __restrict__ h, int ffn) {
 int launch_swiglu(const GemmOut& gu, __nv_bfloat16* h, int T, int ffn, cudaStream_t s) {
   if (T <= 0) return 0;
   dim3 grid((ffn / 4 + 255) / 256, T);
-  swiglu_kernel<<<grid, 256, 0, s>>>(to_dev(gu), h, ffn);
-  ACP_LAUNCH_CHECK("swiglu");
+  ACP_LAUNCH("swiglu", acp_launch(swiglu_kernel, grid, dim3(256), 0, s, to_dev(gu), h, ffn));
   return 0;
 }
 
@@ -221,6 +243,8 @@ int launch_swiglu(const GemmOut& gu, __nv_bfloat16* h, int T, int ffn, cudaStrea
 __global__ void __launch_bounds__(128)
 argmax_finish_kernel(const float* __restrict__ tile_val, const int* __restrict__ tile_idx,
                      int m_tiles, int* __restrict__ token_out, float* __restrict__ val_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sv[4];
   __shared__ int si[4];
   const int n = blockIdx.x;
@@ -249,8 +273,8 @@ argmax_finish_kernel(const float* __restrict__ tile_val, const int* __restrict__
 int launch_argmax_finish(const float* tile_val, const int* tile_idx, int m_tiles, int N,
                          int* token_out, float* val_out, cudaStream_t s) {
   if (N <= 0) return 0;
-  argmax_finish_kernel<<<N, 128, 0, s>>>(tile_val, tile_idx, m_tiles, token_out, val_out);
-  ACP_LAUNCH_CHECK("argmax_finish");
+  ACP_LAUNCH("argmax_finish", acp_launch(argmax_finish_kernel, dim3(N), dim3(128), 0, s, tile_val, tile_idx,
+                                         m_tiles, token_out, val_out));
   return 0;
 }
 
@@ -290,6 +314,8 @@ ACP_DEVINL uint64_t splitmix64(uint64_t z) {
 __global__ void __launch_bounds__(1024)
 sample_kernel(const float* __restrict__ logits, int V, const SampleParams* __restrict__ params,
               int* __restrict__ token_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   __shared__ float s_prefix[1024];
   const int n = blockIdx.x;
@@ -381,20 +407,28 @@ sample_kernel(const float* __restrict__ logits, int V, const SampleParams* __res
 int launch_sample(const float* logits, int V, int N, const SampleParams* params_dev,
                   int* token_out, cudaStream_t s) {
   if (N <= 0) return 0;
-  sample_kernel<<<N, 1024, 0, s>>>(logits, V, params_dev, token_out);
-  ACP_LAUNCH_CHECK("sample");
+  ACP_LAUNCH("sample", acp_launch(sample_kernel, dim3(N), dim3(1024), 0, s, logits, V, params_dev, token_out));
   return 0;
 }
 
 // ---------------------------------------------------------------------------------
 // synthetic weights (bit-identical to oracle/synth.py)
 // ---------------------------------------------------------------------------------
+// interleave_half > 0: the tensor is STORED with rows interleaved (storage row 2j = logical row j,
+// storage row 2j+1 = logical row interleave_half + j) while element values follow the logical
+// [gate rows; up rows] tensor of the oracle.
 __global__ void synth_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n, uint64_t base,
-                                    float scale, int plus_one) {
+                                    float scale, int plus_one, int cols, int interleave_half) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    const uint64_t z = splitmix64(base + (uint64_t)i * 0xD1B54A32D192ED03ull);
+    size_t li = i;
+    if (interleave_half > 0) {
+      const size_t r = i / (size_t)cols, c = i % (size_t)cols;
+      const size_t lr = (r & 1) ? (size_t)interleave_half + (r >> 1) : (r >> 1);
+      li = lr * (size_t)cols + c;
+    }
+    const uint64_t z = splitmix64(base + (uint64_t)li * 0xD1B54A32D192ED03ull);
     const int s = (int)(z & 0xffff) + (int)((z >> 16) & 0xffff) + (int)((z >> 32) & 0xffff) +
                   (int)(z >> 48) - 131070;
     float w = __fmul_rn((float)s, scale);
@@ -403,11 +437,11 @@ __global__ void synth_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n, u
   }
 }
 int launch_synth(__nv_bfloat16* out, size_t n, uint64_t seed, uint32_t tid, double std,
-                 int plus_one, cudaStream_t s) {
+                 int plus_one, cudaStream_t s, int cols, int interleave_half) {
   if (n == 0) return 0;
   const uint64_t base = seed + (uint64_t)tid * 0x9E3779B97F4A7C15ull;
   const float scale = (float)(std / 37837.22671196048);
-  synth_weight_kernel<<<148 * 8, 256, 0, s>>>(out, n, base, scale, plus_one);
+  synth_weight_kernel<<<148 * 8, 256, 0, s>>>(out, n, base, scale, plus_one, cols, interleave_half);
   ACP_LAUNCH_CHECK("synth");
   return 0;
 }

@@ -66,7 +66,7 @@ int launch_sample(const float* logits, int V, int N, const SampleParams* params_
 
 // Seeded synthetic tensor (bit-identical to oracle/synth.py)
 int launch_synth(__nv_bfloat16* out, size_t n, uint64_t seed, uint32_t tid, double std,
-                 int plus_one, cudaStream_t s);
+                 int plus_one, cudaStream_t s, int cols = 1, int interleave_half = 0);
 
 constexpr int KV_PAGE = 32;   // tokens per KV page
 constexpr int HEAD_DIM = 128;

@@ -77,8 +77,11 @@ static int dmalloc_t(std::vector<void*>& allocs, T** p, size_t count, bool zero 
   return dmalloc(allocs, (void**)p, count * sizeof(T), zero);
 }
 
+// Split-K factor of a DECODE-step GEMM.  It depends only on (M, K), never on the batch size, so
+// a sequence's arithmetic does not change with what it happens to be batched with (prefill steps
+// never split: see gemm()).
 int Model::choose_splits(int M, int K, int N) const {
-  if (N > 256) return 1;
+  (void)N;
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int nkb = (K + GEMM_BK - 1) / GEMM_BK;
   int s = (lim_.splitk_target_ctas + m_tiles / 2) / m_tiles;
@@ -155,15 +158,11 @@ int Model::alloc_all() {
   ACP_TRY(tma_make_act(&m_attn_, attn_, T, c.q_dim()));
   ACP_TRY(tma_make_act(&m_h_, h_, T, c.ffn));
   ACP_TRY(tma_make_act(&m_xs_, xs_, Bp, H));
-  // split-K workspace: worst case over the four GEMMs at N = 256 rows
+  // split-K workspace: worst case over the four GEMMs of a decode step with max_batch rows
   size_t ws = 0;
   const int shapes[4][2] = {{c.qkv_dim(), c.hidden}, {c.hidden, c.q_dim()}, {2 * c.ffn, c.hidden}, {c.hidden, c.ffn}};
   for (auto& s : shapes) {
-    size_t b = (size_t)choose_splits(s[0], s[1], 256) * 256 * s[0] * sizeof(float);
-    for (int n = 16; n <= 256; n *= 2) {
-      size_t bb = (size_t)choose_splits(s[0], s[1], n) * n * s[0] * sizeof(float);
-      if (bb > b) b = bb;
-    }
+    size_t b = (size_t)choose_splits(s[0], s[1], 0) * lim_.max_batch * s[0] * sizeof(float);
     if (b > ws) ws = b;
   }
   ws_bytes_ = ws;
@@ -201,7 +200,8 @@ int Model::gen_weights() {
     const uint32_t base = 16 + (uint32_t)l * 16;
     ACP_TRY(launch_synth(L.wqkv, (size_t)c.qkv_dim() * H, c.seed, base + 0, c.w_std, 0, stream_));
     ACP_TRY(launch_synth(L.wo, H * c.q_dim(), c.seed, base + 1, c.w_std, 0, stream_));
-    ACP_TRY(launch_synth(L.wgu, (size_t)2 * c.ffn * H, c.seed, base + 2, c.w_std, 0, stream_));
+    // gate/up rows stored interleaved for the fused SwiGLU epilogue (values = oracle's [gate; up])
+    ACP_TRY(launch_synth(L.wgu, (size_t)2 * c.ffn * H, c.seed, base + 2, c.w_std, 0, stream_, (int)H, c.ffn));
     ACP_TRY(launch_synth(L.wdown, H * c.ffn, c.seed, base + 3, c.w_std, 0, stream_));
     ACP_TRY(launch_synth(L.attn_norm, H, c.seed, base + 4, 0.1, 1, stream_));
     ACP_TRY(launch_synth(L.ffn_norm, H, c.seed, base + 5, 0.1, 1, stream_));
@@ -252,11 +252,11 @@ StepInput& Model::stage_begin(int T, int B, int n_blocks) {
   return s;
 }
 
-int Model::gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, GemmOut* out) {
+int Model::gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool decode, GemmOut* out) {
   GemmLaunch g;
   g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
   const int splits = choose_splits(M, K, N);
-  if (N <= 256) {
+  if (decode) {
     g.epi = EPI_F32; g.splits = splits; g.out = ws_; g.ld = M; g.n_cap = N;
     if ((size_t)splits * N * M * sizeof(float) > ws_bytes_) return -4;
     out->ptr = ws_; out->splits = splits; out->n_cap = N; out->ld = M;
@@ -296,8 +296,8 @@ int Model::forward(const StepInput& in) {
   ++launches_;
   for (int l = 0; l < c.layers; ++l) {
     Layer& L = layers_[l];
-    GemmOut qkv, o, gu, dn;
-    ACP_TRY(gemm(L.m_qkv, m_xn_, c.qkv_dim(), c.hidden, T, &qkv));
+    GemmOut qkv, o, dn;
+    ACP_TRY(gemm(L.m_qkv, m_xn_, c.qkv_dim(), c.hidden, T, in.decode, &qkv));
     RopeKvArgs ra;
     ra.qkv = qkv; ra.pos = d_pos; ra.seq_of_row = d_seq; ra.page_table = d_pt;
     ra.max_pages = lim_.max_pages_per_seq; ra.cos_tab = cos_; ra.sin_tab = sin_; ra.qbuf = qbuf_;
@@ -308,10 +308,15 @@ int Model::forward(const StepInput& in) {
       AttnDecodeArgs aa;
       aa.q = qbuf_; aa.out = attn_; aa.ctx_len = d_ctx; aa.q_rows = nullptr; aa.page_table = d_pt;
       aa.max_pages = lim_.max_pages_per_seq; aa.heads = c.heads; aa.kv_heads = c.kv_heads;
-      aa.scale = scale; aa.split_tokens = lim_.split_tokens; aa.max_splits = max_splits_;
+      // KV splits only when (sequences x kv heads) alone cannot fill the machine (2 CTAs / SM)
+      int want = (2 * 148 + in.B * c.kv_heads - 1) / (in.B * c.kv_heads);
+      if (want < 1) want = 1;
+      int st = ((in.max_ctx + want - 1) / want + 63) / 64 * 64;
+      if (st < lim_.split_tokens) st = lim_.split_tokens;
+      aa.scale = scale; aa.split_tokens = st; aa.max_splits = max_splits_;
       aa.ws_o = attn_ws_o_; aa.ws_m = attn_ws_m_; aa.ws_l = attn_ws_l_;
       ACP_TRY(launch_attn_decode(L.tm_k, L.tm_v, aa, in.B, in.max_ctx, stream_));
-      launches_ += (in.max_ctx > lim_.split_tokens) ? 2 : 1;
+      launches_ += (in.max_ctx > st) ? 2 : 1;
     } else {
       AttnPrefillArgs pa;
       pa.q = qbuf_; pa.out = attn_; pa.blk_seq = d_bseq; pa.blk_tok0 = d_btok0; pa.q_start = d_qstart;
@@ -320,13 +325,17 @@ int Model::forward(const StepInput& in) {
       ACP_TRY(launch_attn_prefill(L.tm_k, L.tm_v, pa, in.n_blocks, stream_));
       ++launches_;
     }
-    ACP_TRY(gemm(L.m_o, m_attn_, c.hidden, c.q_dim(), T, &o));
+    ACP_TRY(gemm(L.m_o, m_attn_, c.hidden, c.q_dim(), T, in.decode, &o));
     ACP_TRY(launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
     ++launches_;
-    ACP_TRY(gemm(L.m_gu, m_xn_, 2 * c.ffn, c.hidden, T, &gu));
-    ACP_TRY(launch_swiglu(gu, h_, T, c.ffn, stream_));
-    ++launches_;
-    ACP_TRY(gemm(L.m_down, m_h_, c.hidden, c.ffn, T, &dn));
+    {  // gate/up GEMM with the SwiGLU fused into the epilogue: h never round-trips as fp32
+      GemmLaunch g;
+      g.w = &L.m_gu.w; g.x = &m_xn_; g.M = 2 * c.ffn; g.N = T; g.K = c.hidden; g.splits = 1;
+      g.epi = EPI_SWIGLU; g.out = h_; g.ld = c.ffn; g.n_cap = T;
+      ACP_TRY(gemm_launch(g, stream_));
+      ++launches_;
+    }
+    ACP_TRY(gemm(L.m_down, m_h_, c.hidden, c.ffn, T, in.decode, &dn));
     if (l + 1 < c.layers) {
       ACP_TRY(launch_add_rmsnorm(x_, dn, layers_[l + 1].attn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
     } else {

@@ -39,7 +39,7 @@ struct ModelLimits {
   int max_tokens = 8192;     // token rows per step (prefill chunk budget)
   int num_pages = 2048;      // KV pages (32 tokens each) in the pool, page 0 is reserved
   int max_pages_per_seq = 256;
-  int split_tokens = 512;    // decode attention KV split
+  int split_tokens = 256;    // minimum KV tokens per decode-attention split (multiple of 64)
   int splitk_target_ctas = 222;
 };
 
@@ -94,7 +94,7 @@ class Model {
  private:
   int alloc_all();
   int gen_weights();
-  int gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, GemmOut* out);
+  int gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool decode, GemmOut* out);
   int choose_splits(int M, int K, int N) const;
 
   ModelConfig cfg_;

@@ -21,6 +21,8 @@ def _gemm(w_bits, x_bits, splits=1, epi=0, bn=0, want_logits=True, iters=0):
     amax_i = np.zeros(N, np.int32)
     if epi == 0:
         out = np.zeros((N, M), np.uint16)
+    elif epi == 3:
+        out = np.zeros((N, M // 2), np.uint16)
     elif epi == 1:
         out = np.zeros((splits, N, M), np.float32)
     else:
@@ -105,3 +107,19 @@ def test_gemm_deterministic():
     a, _, _, _ = _gemm(w, x, splits=4, epi=1)
     b, _, _, _ = _gemm(w, x, splits=4, epi=1)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 16, 128), (2048, 64, 512), (512, 300, 256)])
+def test_gemm_fused_swiglu_epilogue(M, N, K):
+    """epi 3: interleaved (gate_j, up_j) rows -> bf16(bf16(silu(g)) * u), the oracle's expression."""
+    from oracle.bf16 import bf16_round
+    rng = np.random.default_rng(M + N)
+    w = _rand_bits(rng, (M, K), 0.08)
+    x = _rand_bits(rng, (N, K), 1.0)
+    out, _, _, _ = _gemm(w, x, epi=3)
+    gu = bf16_round(bits_to_f32(x) @ bits_to_f32(w).T)
+    g, u = gu[:, 0::2], gu[:, 1::2]
+    ref = bf16_round(bf16_round(g / (np.float32(1.0) + np.exp(-g))) * u)
+    got = bits_to_f32(out)
+    tol = np.maximum(np.abs(ref) * 2.0 ** -6, 2e-3)
+    assert np.all(np.abs(got - ref) <= tol), float(np.max(np.abs(got - ref)))
