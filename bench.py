@@ -227,13 +227,9 @@ def main():
     clocks = sampler.stop() if sampler else None
     s1 = eng.stats()
     dev_s = (s1["decode_ms"] + s1["prefill_ms"]) / 1e3
-    times = torch.tensor([wall, dev_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-    counts = torch.tensor([float(reconciles), float(s1["decode_tokens"])], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    wall_max, dev_max = float(times[0]), float(times[1])
-    total_reconciles, total_decode_tokens = float(counts[0]), float(counts[1])
+    from agentcontrolplane_b200.replicas import aggregate
+    wall_max, dev_max, (total_reconciles, total_decode_tokens) = aggregate(
+        dist, f"cuda:{local_rank}", wall, dev_s, [float(reconciles), float(s1["decode_tokens"])])
 
     if rank == 0:
         peak, peak_src = measured_peaks()
