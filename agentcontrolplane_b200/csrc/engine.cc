@@ -469,6 +469,11 @@ std::string Engine::stats_json() {
   }
   j.set("kv_pages_free", Json((int)free_pages_.size()));
   j.set("kv_pages_total", Json(model_.limits().num_pages - 1));
+  {
+    Json prof;
+    std::string perr;
+    if (Json::parse(model_.profile_json(), &prof, &perr)) j.set("profile", prof);
+  }
   j.set("running", Json((int)running_.size()));
   j.set("waiting", Json((int)waiting_.size()));
   return j.dump();

@@ -49,6 +49,60 @@ static bool debug_sync_enabled() {
     }                                                                                      \
   } while (0)
 
+static bool profile_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACP_PROFILE"); v = (e && *e && *e != '0') ? 1 : 0; }
+  return v == 1;
+}
+bool Model::prof_begin(const char* name) {
+  if (!profile_enabled()) return false;
+  while (prof_pool_.size() < prof_used_ + 2) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    prof_pool_.push_back(e);
+  }
+  ProfSeg seg{name, prof_pool_[prof_used_], prof_pool_[prof_used_ + 1]};
+  prof_used_ += 2;
+  cudaEventRecord(seg.a, stream_);
+  prof_segs_.push_back(seg);
+  return true;
+}
+void Model::prof_end() { cudaEventRecord(prof_segs_.back().b, stream_); }
+void Model::prof_collect(bool decode) {
+  auto& acc = prof_acc_[decode ? 1 : 0];
+  for (auto& seg : prof_segs_) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, seg.a, seg.b) != cudaSuccess) continue;
+    bool found = false;
+    for (auto& kv : acc)
+      if (kv.first == seg.name) { kv.second.n++; kv.second.ms += ms; found = true; break; }
+    if (!found) { ProfAcc a; a.n = 1; a.ms = ms; acc.emplace_back(seg.name, a); }
+  }
+  prof_segs_.clear();
+  prof_used_ = 0;
+}
+std::string Model::profile_json() {
+  std::string out = "{";
+  for (int d = 0; d < 2; ++d) {
+    out += d ? ",\"decode\":{" : "\"prefill\":{";
+    bool first = true;
+    for (auto& kv : prof_acc_[d]) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "%s\"%s\":{\"n\":%lld,\"ms\":%.4f}", first ? "" : ",", kv.first.c_str(), kv.second.n, kv.second.ms);
+      out += buf;
+      first = false;
+    }
+    out += "}";
+  }
+  return out + "}";
+}
+#define PROF(name, expr)                         \
+  do {                                           \
+    const bool _p = prof_begin(name);            \
+    ACP_TRY(expr);                               \
+    if (_p) prof_end();                          \
+  } while (0)
+
 Model::~Model() {
   if (stream_) cudaStreamSynchronize(stream_);
   for (void* p : allocs_) cudaFree(p);
@@ -289,20 +343,20 @@ int Model::forward(const StepInput& in) {
   const int T = in.T;
   const float scale = 1.0f / sqrtf((float)HEAD_DIM);
 
-  ACP_TRY(launch_embed(d_tok, embed_, x_, T, c.hidden, stream_));
+  PROF("embed", launch_embed(d_tok, embed_, x_, T, c.hidden, stream_));
   ++launches_;
   GemmOut none;
-  ACP_TRY(launch_add_rmsnorm(x_, none, layers_[0].attn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
+  PROF("rmsnorm_first", launch_add_rmsnorm(x_, none, layers_[0].attn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
   ++launches_;
   for (int l = 0; l < c.layers; ++l) {
     Layer& L = layers_[l];
     GemmOut qkv, o, dn;
-    ACP_TRY(gemm(L.m_qkv, m_xn_, c.qkv_dim(), c.hidden, T, in.decode, &qkv));
+    PROF("gemm_qkv", gemm(L.m_qkv, m_xn_, c.qkv_dim(), c.hidden, T, in.decode, &qkv));
     RopeKvArgs ra;
     ra.qkv = qkv; ra.pos = d_pos; ra.seq_of_row = d_seq; ra.page_table = d_pt;
     ra.max_pages = lim_.max_pages_per_seq; ra.cos_tab = cos_; ra.sin_tab = sin_; ra.qbuf = qbuf_;
     ra.k_cache = L.k_cache; ra.v_cache = L.v_cache; ra.T = T; ra.heads = c.heads; ra.kv_heads = c.kv_heads;
-    ACP_TRY(launch_rope_kv(ra, stream_));
+    PROF("rope_kv", launch_rope_kv(ra, stream_));
     ++launches_;
     if (in.decode) {
       AttnDecodeArgs aa;
@@ -315,32 +369,32 @@ int Model::forward(const StepInput& in) {
       if (st < lim_.split_tokens) st = lim_.split_tokens;
       aa.scale = scale; aa.split_tokens = st; aa.max_splits = max_splits_;
       aa.ws_o = attn_ws_o_; aa.ws_m = attn_ws_m_; aa.ws_l = attn_ws_l_;
-      ACP_TRY(launch_attn_decode(L.tm_k, L.tm_v, aa, in.B, in.max_ctx, stream_));
+      PROF("attn_decode", launch_attn_decode(L.tm_k, L.tm_v, aa, in.B, in.max_ctx, stream_));
       launches_ += (in.max_ctx > st) ? 2 : 1;
     } else {
       AttnPrefillArgs pa;
       pa.q = qbuf_; pa.out = attn_; pa.blk_seq = d_bseq; pa.blk_tok0 = d_btok0; pa.q_start = d_qstart;
       pa.q_len = d_qlen; pa.ctx_len = d_ctx; pa.page_table = d_pt; pa.max_pages = lim_.max_pages_per_seq;
       pa.heads = c.heads; pa.kv_heads = c.kv_heads; pa.scale = scale;
-      ACP_TRY(launch_attn_prefill(L.tm_k, L.tm_v, pa, in.n_blocks, stream_));
+      PROF("attn_prefill", launch_attn_prefill(L.tm_k, L.tm_v, pa, in.n_blocks, stream_));
       ++launches_;
     }
-    ACP_TRY(gemm(L.m_o, m_attn_, c.hidden, c.q_dim(), T, in.decode, &o));
-    ACP_TRY(launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
+    PROF("gemm_o", gemm(L.m_o, m_attn_, c.hidden, c.q_dim(), T, in.decode, &o));
+    PROF("add_rmsnorm_o", launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
     ++launches_;
     {  // gate/up GEMM with the SwiGLU fused into the epilogue: h never round-trips as fp32
       GemmLaunch g;
       g.w = &L.m_gu.w; g.x = &m_xn_; g.M = 2 * c.ffn; g.N = T; g.K = c.hidden; g.splits = 1;
       g.epi = EPI_SWIGLU; g.out = h_; g.ld = c.ffn; g.n_cap = T;
-      ACP_TRY(gemm_launch(g, stream_));
+      PROF("gemm_gateup_swiglu", gemm_launch(g, stream_));
       ++launches_;
     }
-    ACP_TRY(gemm(L.m_down, m_h_, c.hidden, c.ffn, T, in.decode, &dn));
+    PROF("gemm_down", gemm(L.m_down, m_h_, c.hidden, c.ffn, T, in.decode, &dn));
     if (l + 1 < c.layers) {
-      ACP_TRY(launch_add_rmsnorm(x_, dn, layers_[l + 1].attn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
+      PROF("add_rmsnorm_down", launch_add_rmsnorm(x_, dn, layers_[l + 1].attn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
     } else {
       // final norm only on the rows that are sampled (residual add folded in, not written back)
-      ACP_TRY(launch_add_rmsnorm(x_, dn, final_norm_, xs_, d_srows, in.n_sample, c.hidden, c.eps, stream_));
+      PROF("add_rmsnorm_final", launch_add_rmsnorm(x_, dn, final_norm_, xs_, d_srows, in.n_sample, c.hidden, c.eps, stream_));
     }
     ++launches_;
   }
@@ -352,10 +406,10 @@ int Model::forward(const StepInput& in) {
     const bool logits = in.want_logits || !in.all_greedy;
     g.out = logits ? logits_ : nullptr;
     g.amax_val = amax_val_; g.amax_idx = amax_idx_;
-    ACP_TRY(gemm_launch(g, stream_));
+    PROF("gemm_lm_head_argmax", gemm_launch(g, stream_));
     ++launches_;
     if (in.all_greedy) {
-      ACP_TRY(launch_argmax_finish(amax_val_, amax_idx_, m_tiles, in.n_sample, d_tokens_, nullptr, stream_));
+      PROF("argmax_finish", launch_argmax_finish(amax_val_, amax_idx_, m_tiles, in.n_sample, d_tokens_, nullptr, stream_));
     } else {
       ACP_CUDA_CHECK(cudaMemcpyAsync(d_sparams_, h_sparams_, in.n_sample * sizeof(SampleParams),
                                      cudaMemcpyHostToDevice, stream_));
@@ -379,6 +433,7 @@ int Model::sync() {
     fprintf(stderr, "[acp_infer] step failed: %s\n", cudaGetErrorString(e));
     return -5;
   }
+  if (profile_enabled()) prof_collect(stage_.decode);
   return 0;
 }
 

@@ -90,6 +90,8 @@ class Model {
   long long d2h_bytes() const { return d2h_bytes_; }
   // test hooks: copy tensors back to the host
   int debug_read_weight(int layer, int which, uint16_t* out, size_t n, size_t offset);
+  // ACP_PROFILE=1: CUDA events around every launch of decode steps (breaks PDL overlap; warm caches)
+  std::string profile_json();
 
  private:
   int alloc_all();
@@ -131,6 +133,16 @@ class Model {
   float* h_logits_ = nullptr;
   StepInput stage_;
   std::vector<void*> allocs_;
+  // per-kernel profile (ACP_PROFILE=1)
+  struct ProfSeg { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfSeg> prof_segs_;
+  std::vector<cudaEvent_t> prof_pool_;
+  size_t prof_used_ = 0;
+  struct ProfAcc { long long n = 0; double ms = 0; };
+  std::vector<std::pair<std::string, ProfAcc>> prof_acc_[2];  // [0] prefill steps, [1] decode steps
+  bool prof_begin(const char* name);
+  void prof_end();
+  void prof_collect(bool decode);
 };
 
 }  // namespace acp

@@ -48,4 +48,12 @@ for rep in range(int(os.environ.get('REPS', '3'))):
                       "prefill_ms": round(s["prefill_ms"], 2), "prefill_tokens": s["prefill_tokens"],
                       "prefill_tok_per_s": round(s["prefill_tokens"] / (s["prefill_ms"] / 1e3), 1) if s["prefill_ms"] else 0,
                       "decode_ms": round(s["decode_ms"], 2), "decode_steps": s["decode_steps"]}), flush=True)
+if os.environ.get("ACP_PROFILE"):
+    prof = eng.stats().get("profile", {})
+    for phase in ("decode", "prefill"):
+        items = sorted(prof.get(phase, {}).items(), key=lambda kv: -kv[1]["ms"])
+        tot = sum(v["ms"] for _, v in items) or 1.0
+        print(f"--- {phase} profile (CUDA events per launch, warm cache, PDL overlap broken) total {tot:.2f} ms")
+        for k, v in items:
+            print(f"{k:24s} n={v['n']:6d} total={v['ms']:9.2f} ms  avg={1e3 * v['ms'] / v['n']:8.2f} us  {100 * v['ms'] / tot:5.1f}%")
 eng.close()
