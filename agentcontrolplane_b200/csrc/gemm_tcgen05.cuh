@@ -78,8 +78,11 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GEMM_BM;
-  const int n0 = blockIdx.y * BN;
+  // blockIdx.x = n-tile (fastest): the CTAs that run together share ONE weight tile and sweep the
+  // activation rows, so W streams from HBM once and X (<= 67 MB at 8192 x 4096) is served by L2.
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * GEMM_BM;
+  const int m_tile = blockIdx.y, m_tiles = gridDim.y;
   const int split = blockIdx.z;
   const int nkb_total = (args.K + GEMM_BK - 1) / GEMM_BK;
   const int kb_begin = (int)(((long long)nkb_total * split) / args.splits);
@@ -239,8 +242,8 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           }
           const int n = n0 + c + lane;
           if (n < n_valid) {
-            args.amax_val[(size_t)n * gridDim.x + blockIdx.x] = v;
-            args.amax_idx[(size_t)n * gridDim.x + blockIdx.x] = idx;
+            args.amax_val[(size_t)n * m_tiles + m_tile] = v;
+            args.amax_idx[(size_t)n * m_tiles + m_tile] = idx;
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");

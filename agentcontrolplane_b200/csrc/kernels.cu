@@ -33,6 +33,12 @@ struct GemmOutDev {
 };
 static inline GemmOutDev to_dev(const GemmOut& g) { return GemmOutDev{g.ptr, g.splits, g.n_cap, g.ld}; }
 
+ACP_DEVINL float4 ld_nc_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 ACP_DEVINL void gemm_out_load4(const GemmOutDev& g, int t, int m, float (&v)[4]) {
   if (g.splits == 0) {
     const uint2 raw = *reinterpret_cast<const uint2*>((const __nv_bfloat16*)g.ptr + (size_t)t * g.ld + m);
@@ -41,14 +47,15 @@ ACP_DEVINL void gemm_out_load4(const GemmOutDev& g, int t, int m, float (&v)[4])
     const float* p = (const float*)g.ptr + (size_t)t * g.ld + m;
     const size_t plane = (size_t)g.n_cap * g.ld;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // Planes are loaded 8 at a time (all loads in flight together), then added in index order:
-    // the sum is ((((0 + p0) + p1) + p2) ...) regardless of the batching => deterministic.
+    // 8 planes per batch: the loads are UNCONDITIONAL (index clamped) so that all of them are in
+    // flight together; only the adds are predicated.  Sum order is plane 0,1,2,... => deterministic.
     for (int s0 = 0; s0 < g.splits; s0 += 8) {
       float4 q[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        q[j] = (s0 + j < g.splits) ? *reinterpret_cast<const float4*>(p + (size_t)(s0 + j) * plane)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 8; ++j) {
+        const int sj = (s0 + j < g.splits) ? s0 + j : g.splits - 1;
+        q[j] = ld_nc_f4(p + (size_t)sj * plane);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (s0 + j < g.splits) { acc.x += q[j].x; acc.y += q[j].y; acc.z += q[j].z; acc.w += q[j].w; }
@@ -80,14 +87,14 @@ int launch_embed(const int* tok, const __nv_bfloat16* E, __nv_bfloat16* x, int T
 // ---------------------------------------------------------------------------------
 // (residual add +) RMSNorm.  One CTA per output row, row staged in shared memory as fp32.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 add_rmsnorm_kernel(__nv_bfloat16* __restrict__ x, GemmOutDev add, const __nv_bfloat16* __restrict__ gain,
                    __nv_bfloat16* __restrict__ xn, const int* __restrict__ row_map, int hidden,
                    float eps) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float row[];
-  __shared__ float red[8];
+  __shared__ float red[32];
   const int out_row = blockIdx.x;
   const int src_row = row_map ? row_map[out_row] : out_row;
   __nv_bfloat16* xr = x + (size_t)src_row * hidden;
@@ -133,7 +140,10 @@ int launch_add_rmsnorm(__nv_bfloat16* x, const GemmOut& add, const __nv_bfloat16
                        __nv_bfloat16* xn, const int* row_map, int T, int hidden, float eps,
                        cudaStream_t s) {
   if (T <= 0) return 0;
-  ACP_LAUNCH("add_rmsnorm", acp_launch(add_rmsnorm_kernel, dim3(T), dim3(256), hidden * sizeof(float), s, x,
+  // one thread per 4 elements (single trip through the loads => one L2 round trip per phase)
+  int threads = ((hidden / 4 + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  ACP_LAUNCH("add_rmsnorm", acp_launch(add_rmsnorm_kernel, dim3(T), dim3(threads), hidden * sizeof(float), s, x,
                                        to_dev(add), gain, xn, row_map, hidden, eps));
   return 0;
 }
@@ -142,7 +152,7 @@ int launch_add_rmsnorm(__nv_bfloat16* x, const GemmOut& add, const __nv_bfloat16
 // RoPE + paged-KV scatter.  One CTA per token row; each thread handles 4 consecutive "i"
 // (frequency indices) of one head: elements (i, i+64) of the 128-wide head vector.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 rope_kv_kernel(GemmOutDev qkv, const int* __restrict__ pos, const int* __restrict__ seq_of_row,
                const int* __restrict__ page_table, int max_pages, const float* __restrict__ cos_tab,
                const float* __restrict__ sin_tab, __nv_bfloat16* __restrict__ qbuf,
@@ -201,7 +211,10 @@ rope_kv_kernel(GemmOutDev qkv, const int* __restrict__ pos, const int* __restric
 }
 int launch_rope_kv(const RopeKvArgs& a, cudaStream_t s) {
   if (a.T <= 0) return 0;
-  ACP_LAUNCH("rope_kv", acp_launch(rope_kv_kernel, dim3(a.T), dim3(256), 0, s, to_dev(a.qkv), a.pos,
+  int threads = (a.heads + a.kv_heads) * 16;   // one thread per 4 rotated pairs
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  ACP_LAUNCH("rope_kv", acp_launch(rope_kv_kernel, dim3(a.T), dim3(threads), 0, s, to_dev(a.qkv), a.pos,
                                    a.seq_of_row, a.page_table, a.max_pages, a.cos_tab, a.sin_tab, a.qbuf,
                                    a.k_cache, a.v_cache, a.heads, a.kv_heads));
   return 0;
@@ -214,12 +227,14 @@ __global__ void __launch_bounds__(256)
 swiglu_kernel(GemmOutDev gu, __nv_bfloat16* __restrict__ h, int ffn) {
   pdl_launch_dependents();
   pdl_wait();
+  // gate/up columns are interleaved: column 2j = gate_j, 2j+1 = up_j.  4 outputs per thread.
   const int t = blockIdx.y;
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (j >= ffn) return;
-  float g[4], u[4], o[4];
-  gemm_out_load4(gu, t, j, g);
-  gemm_out_load4(gu, t, ffn + j, u);
+  float a[4], b[4], o[4];
+  gemm_out_load4(gu, t, 2 * j, a);       // g0 u0 g1 u1
+  gemm_out_load4(gu, t, 2 * j + 4, b);   // g2 u2 g3 u3
+  const float g[4] = {a[0], a[2], b[0], b[2]}, u[4] = {a[1], a[3], b[1], b[3]};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float act = bf16_round(g[k] / (1.0f + expf(-g[k])));

@@ -46,7 +46,7 @@ struct RopeKvArgs {
 };
 int launch_rope_kv(const RopeKvArgs& a, cudaStream_t s);
 
-// h[t][j] = bf16( bf16(silu(g)) * u ), g = gu[t][j], u = gu[t][ffn + j]
+// h[t][j] = bf16( bf16(silu(g)) * u ), g = gu[t][2j], u = gu[t][2j+1]  (interleaved gate/up columns)
 int launch_swiglu(const GemmOut& gu, __nv_bfloat16* h, int T, int ffn, cudaStream_t s);
 
 // token[n] = argmax over m-tiles of the fused GEMM arg-max epilogue (lowest index on ties)

@@ -156,6 +156,8 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device) {
   }
   const char* env = getenv("ACP_SPLITK_TARGET");
   if (env) lim_.splitk_target_ctas = atoi(env);
+  env = getenv("ACP_FUSE_SWIGLU");
+  fuse_swiglu_ = env && *env == '1';
   ACP_CUDA_CHECK(cudaSetDevice(device));
   ACP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   ACP_TRY(tma_init());
@@ -382,11 +384,19 @@ int Model::forward(const StepInput& in) {
     PROF("gemm_o", gemm(L.m_o, m_attn_, c.hidden, c.q_dim(), T, in.decode, &o));
     PROF("add_rmsnorm_o", launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
     ++launches_;
-    {  // gate/up GEMM with the SwiGLU fused into the epilogue: h never round-trips as fp32
+    if (fuse_swiglu_) {
+      // optional: SwiGLU in the GEMM epilogue (measured SLOWER on B200 with this non-persistent
+      // kernel: the expf/div epilogue is exposed at the end of every CTA; kept for the persistent
+      // kernel of a later round, ACP_FUSE_SWIGLU=1 to try it)
       GemmLaunch g;
       g.w = &L.m_gu.w; g.x = &m_xn_; g.M = 2 * c.ffn; g.N = T; g.K = c.hidden; g.splits = 1;
       g.epi = EPI_SWIGLU; g.out = h_; g.ld = c.ffn; g.n_cap = T;
       PROF("gemm_gateup_swiglu", gemm_launch(g, stream_));
+      ++launches_;
+    } else {
+      GemmOut gu;
+      PROF("gemm_gateup", gemm(L.m_gu, m_xn_, 2 * c.ffn, c.hidden, T, in.decode, &gu));
+      PROF("swiglu", launch_swiglu(gu, h_, T, c.ffn, stream_));
       ++launches_;
     }
     PROF("gemm_down", gemm(L.m_down, m_h_, c.hidden, c.ffn, T, in.decode, &dn));

@@ -104,6 +104,7 @@ class Model {
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   long long launches_ = 0, h2d_bytes_ = 0, d2h_bytes_ = 0;
+  bool fuse_swiglu_ = false;
 
   struct Layer {
     __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;
