@@ -46,8 +46,18 @@ int tma_encode_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64
   return 0;
 }
 
+// Weights are stored TILED in HBM: tile (m_tile, kb) = 128 rows x 64 bf16 = 16 KiB CONTIGUOUS,
+// tiles ordered [m_tile][kb].  One TMA box is then one contiguous 16 KiB read (DRAM-page friendly)
+// instead of 128 segments of 128 B strided by a whole weight row.  Seen by TMA as a 2-D tensor
+// [(M/128)*(K/64)*128 rows][64 cols].
 int tma_make_weight(TmaMaps* m, const void* base, uint64_t rows, uint64_t cols) {
-  int rc = tma_encode_2d_bf16(&m->w, base, rows, cols, GEMM_BM);
+  if (rows % GEMM_BM != 0 || cols % GEMM_BK != 0) {
+    fprintf(stderr, "[acp_infer] tiled weight needs M %% 128 == 0 and K %% 64 == 0 (got %llu x %llu)\n",
+            (unsigned long long)rows, (unsigned long long)cols);
+    return -1;
+  }
+  const uint64_t tiles = (rows / GEMM_BM) * (cols / GEMM_BK);
+  int rc = tma_encode_2d_bf16(&m->w, base, tiles * GEMM_BM, GEMM_BK, GEMM_BM);
   m->has_w = (rc == 0);
   return rc;
 }

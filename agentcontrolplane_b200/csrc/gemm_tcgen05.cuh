@@ -1,6 +1,7 @@
 // gemm_tcgen05.cuh — the one dense-contraction kernel of the decode engine.
 //
-//   out[n][m] = sum_k W[m][k] * X[n][k]          (W: [M][K] bf16, X: [N][K] bf16, both K-major)
+//   out[n][m] = sum_k W[m][k] * X[n][k]          (W: [M][K] bf16 stored as contiguous 128x64 tiles,
+//                                                 X: [N][K] bf16 row-major; both K-major operands)
 //
 // "Swap-AB" orientation: the WEIGHT matrix is the UMMA A operand (M = 128 output features
 // per tile = 128 TMEM lanes) and the ACTIVATIONS are the B operand (N = sequences/tokens,
@@ -114,7 +115,8 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       const int pre = nkb < STAGES ? nkb : STAGES;
       for (int kb = 0; kb < pre; ++kb) {
         mbar_arrive_expect_tx(&full_bar[kb], Cfg::kStageBytes);
-        tma_load_2d(smem + kb * Cfg::kStageBytes, &tmap_w, &full_bar[kb], (kb_begin + kb) * GEMM_BK, m0, kEvictFirst);
+        tma_load_2d(smem + kb * Cfg::kStageBytes, &tmap_w, &full_bar[kb], 0,
+                    (m_tile * nkb_total + kb_begin + kb) * GEMM_BM, kEvictFirst);  // one contiguous 16 KiB tile
       }
       pdl_wait();  // activations come from the previous kernel
       for (int kb = 0; kb < pre; ++kb)
@@ -129,7 +131,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
         const int kcoord = (kb_begin + kb) * GEMM_BK;
         // weights are read once per step: evict-first; activations are re-read by every m-tile
-        tma_load_2d(a_dst, &tmap_w, &full_bar[s], kcoord, m0, kEvictFirst);
+        tma_load_2d(a_dst, &tmap_w, &full_bar[s], 0, (m_tile * nkb_total + kb_begin + kb) * GEMM_BM, kEvictFirst);
         tma_load_2d(b_dst, &tmap_x, &full_bar[s], kcoord, n0, kEvictLast);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }

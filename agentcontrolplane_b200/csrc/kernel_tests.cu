@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "gemm_tcgen05.cuh"
+#include <string.h>
 #include <vector>
 
 using namespace acp;
@@ -39,10 +40,19 @@ extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int 
   DevBuf dw, dx, dout, dval, didx, dflush;
   // activation rows are padded to the largest N tile like the engine's buffers (zero rows)
   const int n_pad = ((N + 255) / 256) * 256;
-  if (dw.alloc((size_t)M * K * 2) || dx.alloc((size_t)n_pad * K * 2)) return -5;
-  ACP_CUDA_CHECK(cudaMemset(dx.p, 0, (size_t)n_pad * K * 2));
-  ACP_CUDA_CHECK(cudaMemcpy(dw.p, w, (size_t)M * K * 2, cudaMemcpyHostToDevice));
-  ACP_CUDA_CHECK(cudaMemcpy(dx.p, x, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+  // weights: zero-pad to (128, 64) multiples and re-order into the engine's tiled layout
+  const int Mp = ((M + GEMM_BM - 1) / GEMM_BM) * GEMM_BM, Kp = ((K + GEMM_BK - 1) / GEMM_BK) * GEMM_BK;
+  const int nkb_p = Kp / GEMM_BK;
+  std::vector<uint16_t> wt((size_t)Mp * Kp, 0), xp((size_t)N * Kp, 0);
+  for (int r = 0; r < M; ++r)
+    for (int c = 0; c < K; ++c)
+      wt[((size_t)(r / GEMM_BM) * nkb_p + c / GEMM_BK) * 8192 + (size_t)(r % GEMM_BM) * 64 + c % GEMM_BK] =
+          w[(size_t)r * K + c];
+  for (int r = 0; r < N; ++r) memcpy(&xp[(size_t)r * Kp], &x[(size_t)r * K], (size_t)K * 2);
+  if (dw.alloc(wt.size() * 2) || dx.alloc((size_t)n_pad * Kp * 2)) return -5;
+  ACP_CUDA_CHECK(cudaMemset(dx.p, 0, (size_t)n_pad * Kp * 2));
+  ACP_CUDA_CHECK(cudaMemcpy(dw.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+  ACP_CUDA_CHECK(cudaMemcpy(dx.p, xp.data(), xp.size() * 2, cudaMemcpyHostToDevice));
   size_t out_bytes = 0;
   if (epi == EPI_BF16) out_bytes = (size_t)N * M * 2;
   else if (epi == EPI_F32) out_bytes = (size_t)splits * N * M * 4;
@@ -54,10 +64,10 @@ extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int 
     if (dval.alloc((size_t)N * m_tiles * 4) || didx.alloc((size_t)N * m_tiles * 4)) return -5;
   }
   TmaMaps mw, mx;
-  if (tma_make_weight(&mw, dw.p, M, K) != 0) return -5;
-  if (tma_make_act(&mx, dx.p, n_pad, K) != 0) return -5;
+  if (tma_make_weight(&mw, dw.p, Mp, Kp) != 0) return -5;
+  if (tma_make_act(&mx, dx.p, n_pad, Kp) != 0) return -5;
   GemmLaunch g;
-  g.w = &mw.w; g.x = &mx; g.M = M; g.N = N; g.K = K; g.splits = splits; g.epi = epi;
+  g.w = &mw.w; g.x = &mx; g.M = M; g.N = N; g.K = Kp; g.splits = splits; g.epi = epi;
   g.ld = (epi == EPI_SWIGLU) ? M / 2 : M; g.n_cap = N;
   g.out = (epi == EPI_ARGMAX && out == nullptr) ? nullptr : dout.p;
   g.amax_val = (float*)dval.p; g.amax_idx = (int*)didx.p; g.bn_override = bn;

@@ -429,7 +429,9 @@ int launch_sample(const float* logits, int V, int N, const SampleParams* params_
 // ---------------------------------------------------------------------------------
 // synthetic weights (bit-identical to oracle/synth.py)
 // ---------------------------------------------------------------------------------
-// interleave_half > 0: the tensor is STORED with rows interleaved (storage row 2j = logical row j,
+// cols > 1: the tensor is a GEMM weight [rows][cols] STORED as contiguous 128x64 tiles (gemm.cu
+// tma_make_weight); cols == 1: flat vector (norm gains, embedding rows are handled separately).
+// interleave_half > 0: the tensor is additionally STORED with rows interleaved (storage row 2j = logical row j,
 // storage row 2j+1 = logical row interleave_half + j) while element values follow the logical
 // [gate rows; up rows] tensor of the oracle.
 __global__ void synth_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n, uint64_t base,
@@ -438,9 +440,13 @@ __global__ void synth_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n, u
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     size_t li = i;
-    if (interleave_half > 0) {
-      const size_t r = i / (size_t)cols, c = i % (size_t)cols;
-      const size_t lr = (r & 1) ? (size_t)interleave_half + (r >> 1) : (r >> 1);
+    if (cols > 1) {
+      // storage is tiled: [m_tile][kb][128 rows][64 cols]  ->  storage (row, col) of element i
+      const size_t nkb = (size_t)cols / 64;
+      const size_t tile = i / 8192, in_tile = i % 8192;
+      const size_t r = (tile / nkb) * 128 + in_tile / 64, c = (tile % nkb) * 64 + in_tile % 64;
+      size_t lr = r;
+      if (interleave_half > 0) lr = (r & 1) ? (size_t)interleave_half + (r >> 1) : (r >> 1);
       li = lr * (size_t)cols + c;
     }
     const uint64_t z = splitmix64(base + (uint64_t)li * 0xD1B54A32D192ED03ull);

@@ -150,7 +150,7 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device) {
   cfg_ = cfg;
   lim_ = lim;
   device_ = device;
-  if (cfg.hidden % 64 || cfg.ffn % 64 || cfg.vocab % 8 || cfg.heads % cfg.kv_heads) {
+  if (cfg.hidden % 128 || cfg.ffn % 64 || cfg.vocab % 128 || cfg.heads % cfg.kv_heads) {
     fprintf(stderr, "[acp_infer] unsupported model dims\n");
     return -1;
   }
@@ -249,16 +249,16 @@ int Model::gen_weights() {
   const size_t H = c.hidden;
   // tensor ids shared with oracle/synth.py
   ACP_TRY(launch_synth(embed_, (size_t)c.vocab * H, c.seed, 1, c.w_std, 0, stream_));
-  ACP_TRY(launch_synth(lm_head_, (size_t)c.vocab * H, c.seed, 2, c.w_std, 0, stream_));
+  ACP_TRY(launch_synth(lm_head_, (size_t)c.vocab * H, c.seed, 2, c.w_std, 0, stream_, (int)H, 0));
   ACP_TRY(launch_synth(final_norm_, H, c.seed, 3, 0.1, 1, stream_));
   for (int l = 0; l < c.layers; ++l) {
     Layer& L = layers_[l];
     const uint32_t base = 16 + (uint32_t)l * 16;
-    ACP_TRY(launch_synth(L.wqkv, (size_t)c.qkv_dim() * H, c.seed, base + 0, c.w_std, 0, stream_));
-    ACP_TRY(launch_synth(L.wo, H * c.q_dim(), c.seed, base + 1, c.w_std, 0, stream_));
+    ACP_TRY(launch_synth(L.wqkv, (size_t)c.qkv_dim() * H, c.seed, base + 0, c.w_std, 0, stream_, (int)H, 0));
+    ACP_TRY(launch_synth(L.wo, H * c.q_dim(), c.seed, base + 1, c.w_std, 0, stream_, c.q_dim(), 0));
     // gate/up rows stored interleaved for the fused SwiGLU epilogue (values = oracle's [gate; up])
     ACP_TRY(launch_synth(L.wgu, (size_t)2 * c.ffn * H, c.seed, base + 2, c.w_std, 0, stream_, (int)H, c.ffn));
-    ACP_TRY(launch_synth(L.wdown, H * c.ffn, c.seed, base + 3, c.w_std, 0, stream_));
+    ACP_TRY(launch_synth(L.wdown, H * c.ffn, c.seed, base + 3, c.w_std, 0, stream_, c.ffn, 0));
     ACP_TRY(launch_synth(L.attn_norm, H, c.seed, base + 4, 0.1, 1, stream_));
     ACP_TRY(launch_synth(L.ffn_norm, H, c.seed, base + 5, 0.1, 1, stream_));
   }
@@ -275,19 +275,6 @@ int Model::gen_weights() {
   ACP_CUDA_CHECK(cudaMemcpyAsync(cos_, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice, stream_));
   ACP_CUDA_CHECK(cudaMemcpyAsync(sin_, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, stream_));
   ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
-  return 0;
-}
-
-int Model::debug_read_weight(int layer, int which, uint16_t* out, size_t n, size_t offset) {
-  const __nv_bfloat16* src = nullptr;
-  if (layer < 0) src = which == 1 ? embed_ : which == 2 ? lm_head_ : final_norm_;
-  else {
-    Layer& L = layers_[layer];
-    const __nv_bfloat16* t[6] = {L.wqkv, L.wo, L.wgu, L.wdown, L.attn_norm, L.ffn_norm};
-    if (which < 0 || which > 5) return -1;
-    src = t[which];
-  }
-  ACP_CUDA_CHECK(cudaMemcpy(out, src + offset, n * 2, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -312,7 +299,7 @@ int Model::gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool de
   GemmLaunch g;
   g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
   const int splits = choose_splits(M, K, N);
-  if (decode) {
+  if (decode && splits > 1) {  // a single split writes bf16 directly (same rounding, half the bytes)
     g.epi = EPI_F32; g.splits = splits; g.out = ws_; g.ld = M; g.n_cap = N;
     if ((size_t)splits * N * M * sizeof(float) > ws_bytes_) return -4;
     out->ptr = ws_; out->splits = splits; out->n_cap = N; out->ld = M;

@@ -88,8 +88,6 @@ class Model {
   long long launches() const { return launches_; }
   long long h2d_bytes() const { return h2d_bytes_; }
   long long d2h_bytes() const { return d2h_bytes_; }
-  // test hooks: copy tensors back to the host
-  int debug_read_weight(int layer, int which, uint16_t* out, size_t n, size_t offset);
   // ACP_PROFILE=1: CUDA events around every launch of decode steps (breaks PDL overlap; warm caches)
   std::string profile_json();
 
