@@ -58,8 +58,38 @@ int Engine::init(const char* config_json) {
     return -1;
   }
   model_name_ = name;
-  int rc = model_.init(mc, lim, device);
-  if (rc != 0) return rc;
+  tp_ = (int)cfg.get("tp").as_int(1);
+  if (tp_ < 1 || device + tp_ > ndev) {
+    fprintf(stderr, "[acp_infer] tp=%d needs devices %d..%d but %d are visible\n", tp_, device, device + tp_ - 1, ndev);
+    return -1;
+  }
+  int rc = 0;
+  if (tp_ == 1) {
+    rc = model_.init(mc, lim, device);
+    if (rc != 0) return rc;
+  } else {
+    // tensor parallel inside ONE process: a communicator and a host thread per GPU
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) { fprintf(stderr, "[acp_infer] tp > 1 needs libnccl.so.2\n"); return -5; }
+    std::vector<int> devs;
+    for (int i = 0; i < tp_; ++i) devs.push_back(device + i);
+    comms_.resize(tp_);
+    int nrc = nc.CommInitAll(comms_.data(), tp_, devs.data());
+    if (nrc != 0) { fprintf(stderr, "[acp_infer] ncclCommInitAll: %s\n", nc.GetErrorString(nrc)); return -5; }
+    // shards initialise concurrently (weight generation is per GPU)
+    std::vector<int> rcs(tp_, 0);
+    std::vector<std::thread> inits;
+    for (int i = 1; i < tp_; ++i) extra_.emplace_back(new Model());
+    for (int i = 0; i < tp_; ++i)
+      inits.emplace_back([&, i] {
+        Model* m = i == 0 ? &model_ : extra_[i - 1].get();
+        rcs[i] = m->init(mc, lim, devs[i], i, tp_, comms_[i], i == 0 ? nullptr : &model_);
+      });
+    for (auto& t : inits) t.join();
+    for (int r : rcs) if (r != 0) return r;
+    for (int i = 1; i < tp_; ++i) tp_threads_.emplace_back([this, i] { tp_worker(i - 1); });
+  }
+  cudaSetDevice(device);
   if (cudaEventCreate(&ev0_) != cudaSuccess || cudaEventCreate(&ev1_) != cudaSuccess) return -5;
   max_ctx_tokens_ = std::min(lim.max_pages_per_seq * KV_PAGE, mc.max_pos);
   for (int p = lim.num_pages - 1; p >= 1; --p) free_pages_.push_back(p);  // page 0 reserved
@@ -76,6 +106,19 @@ void Engine::shutdown() {
   }
   cv_work_.notify_all();
   if (thread_.joinable()) thread_.join();
+  {
+    std::lock_guard<std::mutex> lk(tp_mu_);
+    tp_stop_ = true;
+  }
+  tp_cv_.notify_all();
+  for (auto& t : tp_threads_) if (t.joinable()) t.join();
+  tp_threads_.clear();
+  extra_.clear();
+  if (!comms_.empty()) {
+    const NcclApi& nc = nccl_api();
+    for (NcclComm c : comms_) if (c) nc.CommDestroy(c);
+    comms_.clear();
+  }
   std::lock_guard<std::mutex> lk(mu_);
   for (auto& kv : all_) {
     if (!kv.second->done) {
@@ -387,10 +430,24 @@ bool Engine::step() {
   in.want_logits = want_logits;
   in.max_ctx = max_ctx;
 
-  cudaEventRecord(ev0_, model_.stream());
-  int rc = model_.forward(in);
-  cudaEventRecord(ev1_, model_.stream());
-  if (rc == 0) rc = model_.sync();
+  if (tp_ > 1 && (!all_greedy || want_logits)) {
+    // vocab-parallel LM head: sampling / logits need an all-gather of logits (not built yet)
+    std::lock_guard<std::mutex> lk(mu_);
+    for (int i = 0; i < ns; ++i) {
+      Sequence& s = *part[sample_seq[i]];
+      if (s.sampling.temperature > 0.f || s.return_logits > 0)
+        for (auto it = running_.begin(); it != running_.end(); ++it)
+          if (it->get() == &s) {
+            auto sp = *it;
+            running_.erase(it);
+            finish(sp, 400, "invalid_request_error", "temperature > 0 and return_logits are not supported by a tensor-parallel engine", "");
+            break;
+          }
+    }
+    cv_done_.notify_all();
+    return true;
+  }
+  int rc = run_forward(in);
   if (rc != 0) { fail_all_running("CUDA step failed (see stderr)"); return true; }
   float step_ms = 0.f;
   cudaEventElapsedTime(&step_ms, ev0_, ev1_);
@@ -436,6 +493,52 @@ bool Engine::step() {
   return true;
 }
 
+void Engine::tp_worker(int idx) {
+  Model& m = *extra_[idx];
+  cudaSetDevice(m.device());
+  uint64_t seen = 0;
+  while (true) {
+    const StepInput* in = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(tp_mu_);
+      tp_cv_.wait(lk, [&] { return tp_stop_ || tp_gen_ != seen; });
+      if (tp_stop_) return;
+      seen = tp_gen_;
+      in = tp_in_;
+    }
+    int rc = m.forward(*in);
+    if (rc == 0) rc = m.sync();
+    {
+      std::lock_guard<std::mutex> lk(tp_mu_);
+      if (rc != 0) tp_rc_ = rc;
+      --tp_pending_;
+    }
+    tp_done_cv_.notify_all();
+  }
+}
+
+// One engine step on every shard.  Device time is measured on shard 0's stream.
+int Engine::run_forward(const StepInput& in) {
+  if (tp_ > 1) {
+    std::lock_guard<std::mutex> lk(tp_mu_);
+    tp_in_ = &in;
+    tp_pending_ = (int)extra_.size();
+    tp_rc_ = 0;
+    ++tp_gen_;
+  }
+  if (tp_ > 1) tp_cv_.notify_all();
+  cudaEventRecord(ev0_, model_.stream());
+  int rc = model_.forward(in);
+  cudaEventRecord(ev1_, model_.stream());
+  if (rc == 0) rc = model_.sync();
+  if (tp_ > 1) {
+    std::unique_lock<std::mutex> lk(tp_mu_);
+    tp_done_cv_.wait(lk, [&] { return tp_pending_ == 0; });
+    if (rc == 0) rc = tp_rc_;
+  }
+  return rc;
+}
+
 std::string Engine::stats_json() {
   std::lock_guard<std::mutex> lk(mu_);
   const ModelConfig& c = model_.config();
@@ -454,12 +557,15 @@ std::string Engine::stats_json() {
   j.set("kernel_launches", Json(model_.launches()));
   j.set("h2d_bytes", Json(model_.h2d_bytes()));
   j.set("d2h_bytes", Json(model_.d2h_bytes()));
+  j.set("tp", Json(tp_));
   j.set("weight_bytes_per_step", Json(c.weight_bytes()));
   j.set("kv_bytes_per_token", Json(c.kv_bytes_per_token()));
   // bytes_step = W + sum_seq ctx*K + B*K, summed over the decode steps so far
+  // (whole model; with tp > 1 each GPU streams 1/tp of it)
   const double bytes = (double)stats_.decode_steps * c.weight_bytes() +
                        c.kv_bytes_per_token() * ((double)stats_.decode_ctx_tokens + (double)stats_.decode_tokens);
   j.set("decode_bytes_algorithmic", Json(bytes));
+  j.set("decode_bytes_algorithmic_per_gpu", Json(bytes / tp_));
   std::vector<float> v = stats_.decode_step_ms;
   if (!v.empty()) {
     std::sort(v.begin(), v.end());

@@ -70,7 +70,20 @@ class Engine {
   void fail_all_running(const std::string& msg);
   void release_pages(Sequence& s);
 
-  Model model_;
+  int run_forward(const StepInput& in);
+  void tp_worker(int idx);
+
+  Model model_;                                  // shard 0 (the only one when tp == 1)
+  std::vector<std::unique_ptr<Model>> extra_;    // tensor-parallel shards 1..tp-1, one GPU each
+  std::vector<NcclComm> comms_;
+  std::vector<std::thread> tp_threads_;
+  std::mutex tp_mu_;
+  std::condition_variable tp_cv_, tp_done_cv_;
+  uint64_t tp_gen_ = 0;
+  int tp_pending_ = 0, tp_rc_ = 0;
+  const StepInput* tp_in_ = nullptr;
+  bool tp_stop_ = false;
+  int tp_ = 1;
   std::string model_name_;
   std::thread thread_;
   std::mutex mu_;

@@ -429,25 +429,29 @@ int launch_sample(const float* logits, int V, int N, const SampleParams* params_
 // ---------------------------------------------------------------------------------
 // synthetic weights (bit-identical to oracle/synth.py)
 // ---------------------------------------------------------------------------------
-// cols > 1: the tensor is a GEMM weight [rows][cols] STORED as contiguous 128x64 tiles (gemm.cu
-// tma_make_weight); cols == 1: flat vector (norm gains, embedding rows are handled separately).
-// interleave_half > 0: the tensor is additionally STORED with rows interleaved (storage row 2j = logical row j,
-// storage row 2j+1 = logical row interleave_half + j) while element values follow the logical
-// [gate rows; up rows] tensor of the oracle.
+// Local element i of a (possibly tiled / interleaved / sharded) tensor -> index in the logical
+// row-major tensor whose values oracle/synth.py defines.
 __global__ void synth_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n, uint64_t base,
-                                    float scale, int plus_one, int cols, int interleave_half) {
+                                    float scale, int plus_one, SynthMap mp) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     size_t li = i;
-    if (cols > 1) {
-      // storage is tiled: [m_tile][kb][128 rows][64 cols]  ->  storage (row, col) of element i
-      const size_t nkb = (size_t)cols / 64;
+    if (mp.local_cols > 1) {
+      // storage is tiled: [m_tile][kb][128 rows][64 cols]  ->  local (row, col) of element i
+      const size_t nkb = (size_t)mp.local_cols / 64;
       const size_t tile = i / 8192, in_tile = i % 8192;
       const size_t r = (tile / nkb) * 128 + in_tile / 64, c = (tile % nkb) * 64 + in_tile % 64;
-      size_t lr = r;
-      if (interleave_half > 0) lr = (r & 1) ? (size_t)interleave_half + (r >> 1) : (r >> 1);
-      li = lr * (size_t)cols + c;
+      size_t lr;
+      if (mp.interleave_half > 0) {
+        lr = (size_t)mp.seg_global[r & 1] + (r >> 1);
+      } else {
+        size_t rr = r;
+        int sg = 0;
+        while (sg + 1 < mp.nseg && rr >= (size_t)mp.seg_rows[sg]) { rr -= (size_t)mp.seg_rows[sg]; ++sg; }
+        lr = (size_t)mp.seg_global[sg] + rr;
+      }
+      li = lr * (size_t)mp.logical_cols + (size_t)mp.col0 + c;
     }
     const uint64_t z = splitmix64(base + (uint64_t)li * 0xD1B54A32D192ED03ull);
     const int s = (int)(z & 0xffff) + (int)((z >> 16) & 0xffff) + (int)((z >> 32) & 0xffff) +
@@ -458,12 +462,73 @@ __global__ void synth_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n, u
   }
 }
 int launch_synth(__nv_bfloat16* out, size_t n, uint64_t seed, uint32_t tid, double std,
-                 int plus_one, cudaStream_t s, int cols, int interleave_half) {
+                 int plus_one, cudaStream_t s, const SynthMap& map) {
   if (n == 0) return 0;
   const uint64_t base = seed + (uint64_t)tid * 0x9E3779B97F4A7C15ull;
   const float scale = (float)(std / 37837.22671196048);
-  synth_weight_kernel<<<148 * 8, 256, 0, s>>>(out, n, base, scale, plus_one, cols, interleave_half);
+  synth_weight_kernel<<<148 * 8, 256, 0, s>>>(out, n, base, scale, plus_one, map);
   ACP_LAUNCH_CHECK("synth");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// tensor-parallel helpers
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+reduce_planes_kernel(const float* __restrict__ planes, int splits, size_t plane_elems, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= plane_elems) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = 0; s0 < splits; s0 += 8) {
+    float4 q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int sj = (s0 + j < splits) ? s0 + j : splits - 1;
+      q[j] = ld_nc_f4(planes + (size_t)sj * plane_elems + i);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (s0 + j < splits) { acc.x += q[j].x; acc.y += q[j].y; acc.z += q[j].z; acc.w += q[j].w; }
+  }
+  *reinterpret_cast<float4*>(out + i) = acc;
+}
+int launch_reduce_planes(const float* planes, int splits, size_t plane_elems, float* out, cudaStream_t s) {
+  if (plane_elems == 0) return 0;
+  const unsigned blocks = (unsigned)((plane_elems / 4 + 255) / 256);
+  ACP_LAUNCH("reduce_planes", acp_launch(reduce_planes_kernel, dim3(blocks), dim3(256), 0, s, planes, splits, plane_elems, out));
+  return 0;
+}
+
+__global__ void pack_candidates_kernel(const float* __restrict__ val, const int* __restrict__ idx,
+                                       int idx_offset, int B, int* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { out[b] = __float_as_int(val[b]); out[B + b] = idx[b] + idx_offset; }
+}
+int launch_pack_candidates(const float* val, const int* idx, int idx_offset, int B, int* out, cudaStream_t s) {
+  if (B <= 0) return 0;
+  ACP_LAUNCH("pack_candidates", acp_launch(pack_candidates_kernel, dim3((B + 127) / 128), dim3(128), 0, s, val, idx, idx_offset, B, out));
+  return 0;
+}
+__global__ void argmax_ranks_kernel(const int* __restrict__ gathered, int P, int B, int* __restrict__ token_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float v = -INFINITY;
+  int idx = 0x7fffffff;
+  for (int r = 0; r < P; ++r) {  // fixed order; lowest id wins ties
+    const float ov = __int_as_float(gathered[(size_t)r * 2 * B + b]);
+    const int oi = gathered[(size_t)r * 2 * B + B + b];
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  token_out[b] = idx;
+}
+int launch_argmax_ranks(const int* gathered, int P, int B, int* token_out, cudaStream_t s) {
+  if (B <= 0) return 0;
+  argmax_ranks_kernel<<<(B + 127) / 128, 128, 0, s>>>(gathered, P, B, token_out);
+  ACP_LAUNCH_CHECK("argmax_ranks");
   return 0;
 }
 

@@ -64,9 +64,30 @@ struct SampleParams {  // per row
 int launch_sample(const float* logits, int V, int N, const SampleParams* params_dev,
                   int* token_out, cudaStream_t s);
 
-// Seeded synthetic tensor (bit-identical to oracle/synth.py)
+// Seeded synthetic tensor (values bit-identical to oracle/synth.py).  SynthMap says where the
+// LOCAL tensor (a tensor-parallel shard, stored as contiguous 128x64 tiles, optionally with
+// gate/up rows interleaved) sits inside the LOGICAL row-major tensor of the oracle.
+struct SynthMap {
+  int local_cols = 1;       // K of the local tensor; 1 = flat vector (no tiling)
+  int logical_cols = 1;     // row length of the logical tensor
+  int col0 = 0;             // first logical column held by this shard
+  int interleave_half = 0;  // > 0: local row 2j -> seg_global[0] + j, 2j+1 -> seg_global[1] + j
+  int nseg = 1;             // otherwise: consecutive local row ranges
+  int seg_rows[3] = {0x7fffffff, 0, 0};
+  int seg_global[3] = {0, 0, 0};
+};
 int launch_synth(__nv_bfloat16* out, size_t n, uint64_t seed, uint32_t tid, double std,
-                 int plus_one, cudaStream_t s, int cols = 1, int interleave_half = 0);
+                 int plus_one, cudaStream_t s, const SynthMap& map = SynthMap());
+
+// out[i] = sum_s planes[s][i] (index order), fp32 -> fp32: local split-K reduction in front of a
+// tensor-parallel all-reduce
+int launch_reduce_planes(const float* planes, int splits, size_t plane_elems, float* out, cudaStream_t s);
+
+// Tensor-parallel arg-max: gathered[P][2][B] (per rank: B fp32 maxima then B int32 global ids)
+// -> token[B], lowest id wins ties.
+int launch_argmax_ranks(const int* gathered, int P, int B, int* token_out, cudaStream_t s);
+// packs (val[B], idx[B] + idx_offset) into out[2][B] words
+int launch_pack_candidates(const float* val, const int* idx, int idx_offset, int B, int* out, cudaStream_t s);
 
 constexpr int KV_PAGE = 32;   // tokens per KV page
 constexpr int HEAD_DIM = 128;

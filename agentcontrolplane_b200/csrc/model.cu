@@ -104,6 +104,7 @@ std::string Model::profile_json() {
   } while (0)
 
 Model::~Model() {
+  cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (void* p : allocs_) cudaFree(p);
   if (h_ints_) cudaFreeHost(h_ints_);
@@ -146,13 +147,31 @@ int Model::choose_splits(int M, int K, int N) const {
   return s;
 }
 
-int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device) {
+int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int tp_rank, int tp_size,
+                NcclComm comm, Model* lead) {
   cfg_ = cfg;
   lim_ = lim;
   device_ = device;
+  tp_rank_ = tp_rank; tp_size_ = tp_size; comm_ = comm; lead_ = lead;
   if (cfg.hidden % 128 || cfg.ffn % 64 || cfg.vocab % 128 || cfg.heads % cfg.kv_heads) {
     fprintf(stderr, "[acp_infer] unsupported model dims\n");
     return -1;
+  }
+  if (cfg.heads % tp_size || cfg.kv_heads % tp_size || cfg.ffn % (64 * tp_size)) {
+    fprintf(stderr, "[acp_infer] tp=%d does not divide heads=%d / kv_heads=%d / ffn=%d\n", tp_size,
+            cfg.heads, cfg.kv_heads, cfg.ffn);
+    return -1;
+  }
+  heads_l_ = cfg.heads / tp_size; kvh_l_ = cfg.kv_heads / tp_size;
+  qdim_l_ = heads_l_ * HEAD_DIM; kvdim_l_ = kvh_l_ * HEAD_DIM; qkv_l_ = qdim_l_ + 2 * kvdim_l_;
+  ffn_l_ = cfg.ffn / tp_size;
+  {  // vocab-parallel LM head: whole 128-row tiles per rank
+    const int tiles = cfg.vocab / GEMM_BM, per = (tiles + tp_size - 1) / tp_size;
+    const int t0 = per * tp_rank < tiles ? per * tp_rank : tiles;
+    const int t1 = per * (tp_rank + 1) < tiles ? per * (tp_rank + 1) : tiles;
+    lm_row0_ = t0 * GEMM_BM;
+    lm_rows_l_ = (t1 - t0) * GEMM_BM;
+    if (lm_rows_l_ <= 0) { fprintf(stderr, "[acp_infer] tp too large for the vocabulary\n"); return -1; }
   }
   const char* env = getenv("ACP_SPLITK_TARGET");
   if (env) lim_.splitk_target_ctas = atoi(env);
@@ -175,62 +194,70 @@ int Model::alloc_all() {
   const int T = ((lim_.max_tokens + 255) / 256) * 256;
   const int Bp = ((lim_.max_batch + 255) / 256) * 256;
   layers_.resize(c.layers);
-  const size_t kv_elems = (size_t)lim_.num_pages * c.kv_heads * KV_PAGE * HEAD_DIM;
+  const size_t kv_elems = (size_t)lim_.num_pages * kvh_l_ * KV_PAGE * HEAD_DIM;
   for (int l = 0; l < c.layers; ++l) {
     Layer& L = layers_[l];
-    ACP_TRY(dmalloc_t(allocs_, &L.wqkv, (size_t)c.qkv_dim() * H));
-    ACP_TRY(dmalloc_t(allocs_, &L.wo, H * c.q_dim()));
-    ACP_TRY(dmalloc_t(allocs_, &L.wgu, (size_t)2 * c.ffn * H));
-    ACP_TRY(dmalloc_t(allocs_, &L.wdown, H * c.ffn));
+    ACP_TRY(dmalloc_t(allocs_, &L.wqkv, (size_t)qkv_l_ * H));
+    ACP_TRY(dmalloc_t(allocs_, &L.wo, H * qdim_l_));
+    ACP_TRY(dmalloc_t(allocs_, &L.wgu, (size_t)2 * ffn_l_ * H));
+    ACP_TRY(dmalloc_t(allocs_, &L.wdown, H * ffn_l_));
     ACP_TRY(dmalloc_t(allocs_, &L.attn_norm, H));
     ACP_TRY(dmalloc_t(allocs_, &L.ffn_norm, H));
     ACP_TRY(dmalloc_t(allocs_, &L.k_cache, kv_elems, true));
     ACP_TRY(dmalloc_t(allocs_, &L.v_cache, kv_elems, true));
-    ACP_TRY(tma_make_weight(&L.m_qkv, L.wqkv, c.qkv_dim(), H));
-    ACP_TRY(tma_make_weight(&L.m_o, L.wo, H, c.q_dim()));
-    ACP_TRY(tma_make_weight(&L.m_gu, L.wgu, 2 * c.ffn, H));
-    ACP_TRY(tma_make_weight(&L.m_down, L.wdown, H, c.ffn));
-    ACP_TRY(attn_make_kv_map(&L.tm_k, L.k_cache, lim_.num_pages, c.kv_heads));
-    ACP_TRY(attn_make_kv_map(&L.tm_v, L.v_cache, lim_.num_pages, c.kv_heads));
+    ACP_TRY(tma_make_weight(&L.m_qkv, L.wqkv, qkv_l_, H));
+    ACP_TRY(tma_make_weight(&L.m_o, L.wo, H, qdim_l_));
+    ACP_TRY(tma_make_weight(&L.m_gu, L.wgu, 2 * ffn_l_, H));
+    ACP_TRY(tma_make_weight(&L.m_down, L.wdown, H, ffn_l_));
+    ACP_TRY(attn_make_kv_map(&L.tm_k, L.k_cache, lim_.num_pages, kvh_l_));
+    ACP_TRY(attn_make_kv_map(&L.tm_v, L.v_cache, lim_.num_pages, kvh_l_));
   }
   ACP_TRY(dmalloc_t(allocs_, &embed_, (size_t)c.vocab * H));
-  ACP_TRY(dmalloc_t(allocs_, &lm_head_, (size_t)c.vocab * H));
+  ACP_TRY(dmalloc_t(allocs_, &lm_head_, (size_t)lm_rows_l_ * H));
   ACP_TRY(dmalloc_t(allocs_, &final_norm_, H));
-  ACP_TRY(tma_make_weight(&m_lm_, lm_head_, c.vocab, H));
+  ACP_TRY(tma_make_weight(&m_lm_, lm_head_, lm_rows_l_, H));
   ACP_TRY(dmalloc_t(allocs_, &cos_, (size_t)c.max_pos * 64));
   ACP_TRY(dmalloc_t(allocs_, &sin_, (size_t)c.max_pos * 64));
   // activations (rows padded to the largest N tile, zero initialised)
   ACP_TRY(dmalloc_t(allocs_, &x_, (size_t)T * H, true));
   ACP_TRY(dmalloc_t(allocs_, &xn_, (size_t)T * H, true));
-  ACP_TRY(dmalloc_t(allocs_, &qbuf_, (size_t)T * c.q_dim(), true));
-  ACP_TRY(dmalloc_t(allocs_, &attn_, (size_t)T * c.q_dim(), true));
-  ACP_TRY(dmalloc_t(allocs_, &h_, (size_t)T * c.ffn, true));
+  ACP_TRY(dmalloc_t(allocs_, &qbuf_, (size_t)T * qdim_l_, true));
+  ACP_TRY(dmalloc_t(allocs_, &attn_, (size_t)T * qdim_l_, true));
+  ACP_TRY(dmalloc_t(allocs_, &h_, (size_t)T * ffn_l_, true));
   ACP_TRY(dmalloc_t(allocs_, &xs_, (size_t)Bp * H, true));
-  int max_m = c.qkv_dim();
-  if (2 * c.ffn > max_m) max_m = 2 * c.ffn;
+  int max_m = qkv_l_;
+  if (2 * ffn_l_ > max_m) max_m = 2 * ffn_l_;
   if (c.hidden > max_m) max_m = c.hidden;
   ACP_TRY(dmalloc_t(allocs_, &gemm_bf16_, (size_t)T * max_m, true));
   ACP_TRY(tma_make_act(&m_xn_, xn_, T, H));
-  ACP_TRY(tma_make_act(&m_attn_, attn_, T, c.q_dim()));
-  ACP_TRY(tma_make_act(&m_h_, h_, T, c.ffn));
+  ACP_TRY(tma_make_act(&m_attn_, attn_, T, qdim_l_));
+  ACP_TRY(tma_make_act(&m_h_, h_, T, ffn_l_));
   ACP_TRY(tma_make_act(&m_xs_, xs_, Bp, H));
   // split-K workspace: worst case over the four GEMMs of a decode step with max_batch rows
   size_t ws = 0;
-  const int shapes[4][2] = {{c.qkv_dim(), c.hidden}, {c.hidden, c.q_dim()}, {2 * c.ffn, c.hidden}, {c.hidden, c.ffn}};
+  const int shapes[4][2] = {{qkv_l_, c.hidden}, {c.hidden, qdim_l_}, {2 * ffn_l_, c.hidden}, {c.hidden, ffn_l_}};
   for (auto& s : shapes) {
     size_t b = (size_t)choose_splits(s[0], s[1], 0) * lim_.max_batch * s[0] * sizeof(float);
     if (b > ws) ws = b;
   }
+  if (tp_size_ > 1) {  // row-parallel GEMMs write fp32 (one rounding after the all-reduce), prefill too
+    const size_t b = (size_t)T * H * sizeof(float);
+    if (b > ws) ws = b;
+    ACP_TRY(dmalloc_t(allocs_, &ar_buf_, (size_t)T * H));
+    ACP_TRY(dmalloc_t(allocs_, &cand_local_, (size_t)2 * Bp));
+    ACP_TRY(dmalloc_t(allocs_, &cand_all_, (size_t)2 * Bp * tp_size_));
+    ACP_TRY(dmalloc_t(allocs_, &amax_val_row_, (size_t)Bp));
+  }
   ws_bytes_ = ws;
   ACP_TRY(dmalloc(allocs_, (void**)&ws_, ws_bytes_));
-  const int m_tiles_lm = (c.vocab + GEMM_BM - 1) / GEMM_BM;
+  const int m_tiles_lm = (lm_rows_l_ + GEMM_BM - 1) / GEMM_BM;
   ACP_TRY(dmalloc_t(allocs_, &amax_val_, (size_t)Bp * m_tiles_lm));
   ACP_TRY(dmalloc_t(allocs_, &amax_idx_, (size_t)Bp * m_tiles_lm));
-  ACP_TRY(dmalloc_t(allocs_, &logits_, (size_t)lim_.max_batch * c.vocab));
+  ACP_TRY(dmalloc_t(allocs_, &logits_, (size_t)lim_.max_batch * lm_rows_l_));
   max_splits_ = (lim_.max_pages_per_seq * KV_PAGE + lim_.split_tokens - 1) / lim_.split_tokens;
-  ACP_TRY(dmalloc_t(allocs_, &attn_ws_o_, (size_t)lim_.max_batch * c.heads * max_splits_ * HEAD_DIM));
-  ACP_TRY(dmalloc_t(allocs_, &attn_ws_m_, (size_t)lim_.max_batch * c.heads * max_splits_));
-  ACP_TRY(dmalloc_t(allocs_, &attn_ws_l_, (size_t)lim_.max_batch * c.heads * max_splits_));
+  ACP_TRY(dmalloc_t(allocs_, &attn_ws_o_, (size_t)lim_.max_batch * heads_l_ * max_splits_ * HEAD_DIM));
+  ACP_TRY(dmalloc_t(allocs_, &attn_ws_m_, (size_t)lim_.max_batch * heads_l_ * max_splits_));
+  ACP_TRY(dmalloc_t(allocs_, &attn_ws_l_, (size_t)lim_.max_batch * heads_l_ * max_splits_));
   // step staging
   ints_cap_ = (size_t)5 * lim_.max_tokens + (size_t)4 * lim_.max_batch +
               (size_t)lim_.max_batch * lim_.max_pages_per_seq + 64;
@@ -240,25 +267,47 @@ int Model::alloc_all() {
   ACP_CUDA_CHECK(cudaMallocHost((void**)&h_sparams_, lim_.max_batch * sizeof(SampleParams)));
   ACP_TRY(dmalloc_t(allocs_, &d_tokens_, (size_t)lim_.max_batch));
   ACP_CUDA_CHECK(cudaMallocHost((void**)&h_tokens_, lim_.max_batch * sizeof(int)));
-  ACP_CUDA_CHECK(cudaMallocHost((void**)&h_logits_, (size_t)lim_.max_batch * c.vocab * sizeof(float)));
+  ACP_CUDA_CHECK(cudaMallocHost((void**)&h_logits_, (size_t)lim_.max_batch * lm_rows_l_ * sizeof(float)));
   return 0;
 }
 
 int Model::gen_weights() {
   const ModelConfig& c = cfg_;
   const size_t H = c.hidden;
-  // tensor ids shared with oracle/synth.py
-  ACP_TRY(launch_synth(embed_, (size_t)c.vocab * H, c.seed, 1, c.w_std, 0, stream_));
-  ACP_TRY(launch_synth(lm_head_, (size_t)c.vocab * H, c.seed, 2, c.w_std, 0, stream_, (int)H, 0));
+  // tensor ids shared with oracle/synth.py; SynthMap places this shard inside the logical tensors
+  const int r = tp_rank_;
+  auto tiled = [&](int local_cols, int logical_cols, int col0) {
+    SynthMap m;
+    m.local_cols = local_cols; m.logical_cols = logical_cols; m.col0 = col0;
+    return m;
+  };
+  ACP_TRY(launch_synth(embed_, (size_t)c.vocab * H, c.seed, 1, c.w_std, 0, stream_));  // replicated, row-major
+  {
+    SynthMap m = tiled((int)H, (int)H, 0);
+    m.nseg = 1; m.seg_rows[0] = lm_rows_l_; m.seg_global[0] = lm_row0_;
+    ACP_TRY(launch_synth(lm_head_, (size_t)lm_rows_l_ * H, c.seed, 2, c.w_std, 0, stream_, m));
+  }
   ACP_TRY(launch_synth(final_norm_, H, c.seed, 3, 0.1, 1, stream_));
   for (int l = 0; l < c.layers; ++l) {
     Layer& L = layers_[l];
     const uint32_t base = 16 + (uint32_t)l * 16;
-    ACP_TRY(launch_synth(L.wqkv, (size_t)c.qkv_dim() * H, c.seed, base + 0, c.w_std, 0, stream_, (int)H, 0));
-    ACP_TRY(launch_synth(L.wo, H * c.q_dim(), c.seed, base + 1, c.w_std, 0, stream_, c.q_dim(), 0));
-    // gate/up rows stored interleaved for the fused SwiGLU epilogue (values = oracle's [gate; up])
-    ACP_TRY(launch_synth(L.wgu, (size_t)2 * c.ffn * H, c.seed, base + 2, c.w_std, 0, stream_, (int)H, c.ffn));
-    ACP_TRY(launch_synth(L.wdown, H * c.ffn, c.seed, base + 3, c.w_std, 0, stream_, c.ffn, 0));
+    {  // [q heads of this rank | k heads | v heads] rows of the logical [q | k | v] tensor
+      SynthMap m = tiled((int)H, (int)H, 0);
+      m.nseg = 3;
+      m.seg_rows[0] = qdim_l_; m.seg_global[0] = r * qdim_l_;
+      m.seg_rows[1] = kvdim_l_; m.seg_global[1] = c.q_dim() + r * kvdim_l_;
+      m.seg_rows[2] = kvdim_l_; m.seg_global[2] = c.q_dim() + c.kv_dim() + r * kvdim_l_;
+      ACP_TRY(launch_synth(L.wqkv, (size_t)qkv_l_ * H, c.seed, base + 0, c.w_std, 0, stream_, m));
+    }
+    ACP_TRY(launch_synth(L.wo, H * qdim_l_, c.seed, base + 1, c.w_std, 0, stream_, tiled(qdim_l_, c.q_dim(), r * qdim_l_)));
+    {  // gate/up rows interleaved (2j = gate_j, 2j+1 = up_j); values = oracle's [gate; up] tensor
+      SynthMap m = tiled((int)H, (int)H, 0);
+      m.interleave_half = ffn_l_;
+      m.seg_global[0] = r * ffn_l_;
+      m.seg_global[1] = c.ffn + r * ffn_l_;
+      ACP_TRY(launch_synth(L.wgu, (size_t)2 * ffn_l_ * H, c.seed, base + 2, c.w_std, 0, stream_, m));
+    }
+    ACP_TRY(launch_synth(L.wdown, H * ffn_l_, c.seed, base + 3, c.w_std, 0, stream_, tiled(ffn_l_, c.ffn, r * ffn_l_)));
     ACP_TRY(launch_synth(L.attn_norm, H, c.seed, base + 4, 0.1, 1, stream_));
     ACP_TRY(launch_synth(L.ffn_norm, H, c.seed, base + 5, 0.1, 1, stream_));
   }
@@ -311,14 +360,43 @@ int Model::gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool de
   return gemm_launch(g, stream_);
 }
 
+// Row-parallel GEMM of a tensor-parallel shard (O and down projections): fp32 partial sums, local
+// split-K reduce, NCCL all-reduce (sum) across the group over NVLink, consumer rounds to bf16 ONCE.
+int Model::gemm_rowpar(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool decode, GemmOut* out) {
+  GemmLaunch g;
+  g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
+  const int splits = decode ? choose_splits(M, K, N) : 1;
+  g.epi = EPI_F32; g.splits = splits; g.out = ws_; g.ld = M; g.n_cap = N;
+  if ((size_t)splits * N * M * sizeof(float) > ws_bytes_) return -4;
+  ++launches_;
+  int rc = gemm_launch(g, stream_);
+  if (rc != 0) return rc;
+  float* ar = ws_;
+  if (splits > 1) {
+    rc = launch_reduce_planes(ws_, splits, (size_t)N * M, ar_buf_, stream_);
+    if (rc != 0) return rc;
+    ++launches_;
+    ar = ar_buf_;
+  }
+  const NcclApi& nc = nccl_api();
+  rc = nc.AllReduce(ar, ar, (size_t)N * M, kNcclFloat32, kNcclSum, comm_, stream_);
+  if (rc != 0) { fprintf(stderr, "[acp_infer] ncclAllReduce: %s\n", nc.GetErrorString(rc)); return -5; }
+  ++launches_;
+  out->ptr = ar; out->splits = 1; out->n_cap = N; out->ld = M;
+  return 0;
+}
+
 int Model::forward(const StepInput& in) {
   const ModelConfig& c = cfg_;
   if (in.T <= 0 || in.T > lim_.max_tokens || in.B > lim_.max_batch || in.n_sample > lim_.max_batch)
     return -1;
   ACP_CUDA_CHECK(cudaSetDevice(device_));
-  ACP_CUDA_CHECK(cudaMemcpyAsync(d_ints_, h_ints_, ints_used_ * sizeof(int), cudaMemcpyHostToDevice, stream_));
-  h2d_bytes_ += (long long)(ints_used_ * sizeof(int));
-  auto dev = [&](const int* hp) { return d_ints_ + (hp - h_ints_); };
+  // every tensor-parallel shard uploads the SAME pinned step descriptor (the lead shard's staging)
+  const int* src_ints = lead_ ? lead_->h_ints_ : h_ints_;
+  const size_t used = lead_ ? lead_->ints_used_ : ints_used_;
+  ACP_CUDA_CHECK(cudaMemcpyAsync(d_ints_, src_ints, used * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  h2d_bytes_ += (long long)(used * sizeof(int));
+  auto dev = [&](const int* hp) { return d_ints_ + (hp - src_ints); };
   const int* d_tok = dev(in.tok);
   const int* d_pos = dev(in.pos);
   const int* d_seq = dev(in.seq_of_row);
@@ -340,19 +418,19 @@ int Model::forward(const StepInput& in) {
   for (int l = 0; l < c.layers; ++l) {
     Layer& L = layers_[l];
     GemmOut qkv, o, dn;
-    PROF("gemm_qkv", gemm(L.m_qkv, m_xn_, c.qkv_dim(), c.hidden, T, in.decode, &qkv));
+    PROF("gemm_qkv", gemm(L.m_qkv, m_xn_, qkv_l_, c.hidden, T, in.decode, &qkv));
     RopeKvArgs ra;
     ra.qkv = qkv; ra.pos = d_pos; ra.seq_of_row = d_seq; ra.page_table = d_pt;
     ra.max_pages = lim_.max_pages_per_seq; ra.cos_tab = cos_; ra.sin_tab = sin_; ra.qbuf = qbuf_;
-    ra.k_cache = L.k_cache; ra.v_cache = L.v_cache; ra.T = T; ra.heads = c.heads; ra.kv_heads = c.kv_heads;
+    ra.k_cache = L.k_cache; ra.v_cache = L.v_cache; ra.T = T; ra.heads = heads_l_; ra.kv_heads = kvh_l_;
     PROF("rope_kv", launch_rope_kv(ra, stream_));
     ++launches_;
     if (in.decode) {
       AttnDecodeArgs aa;
       aa.q = qbuf_; aa.out = attn_; aa.ctx_len = d_ctx; aa.q_rows = nullptr; aa.page_table = d_pt;
-      aa.max_pages = lim_.max_pages_per_seq; aa.heads = c.heads; aa.kv_heads = c.kv_heads;
+      aa.max_pages = lim_.max_pages_per_seq; aa.heads = heads_l_; aa.kv_heads = kvh_l_;
       // KV splits only when (sequences x kv heads) alone cannot fill the machine (2 CTAs / SM)
-      int want = (2 * 148 + in.B * c.kv_heads - 1) / (in.B * c.kv_heads);
+      int want = (2 * 148 + in.B * kvh_l_ - 1) / (in.B * kvh_l_);
       if (want < 1) want = 1;
       int st = ((in.max_ctx + want - 1) / want + 63) / 64 * 64;
       if (st < lim_.split_tokens) st = lim_.split_tokens;
@@ -364,11 +442,12 @@ int Model::forward(const StepInput& in) {
       AttnPrefillArgs pa;
       pa.q = qbuf_; pa.out = attn_; pa.blk_seq = d_bseq; pa.blk_tok0 = d_btok0; pa.q_start = d_qstart;
       pa.q_len = d_qlen; pa.ctx_len = d_ctx; pa.page_table = d_pt; pa.max_pages = lim_.max_pages_per_seq;
-      pa.heads = c.heads; pa.kv_heads = c.kv_heads; pa.scale = scale;
+      pa.heads = heads_l_; pa.kv_heads = kvh_l_; pa.scale = scale;
       PROF("attn_prefill", launch_attn_prefill(L.tm_k, L.tm_v, pa, in.n_blocks, stream_));
       ++launches_;
     }
-    PROF("gemm_o", gemm(L.m_o, m_attn_, c.hidden, c.q_dim(), T, in.decode, &o));
+    if (tp_size_ > 1) PROF("gemm_o_allreduce", gemm_rowpar(L.m_o, m_attn_, c.hidden, qdim_l_, T, in.decode, &o));
+    else PROF("gemm_o", gemm(L.m_o, m_attn_, c.hidden, qdim_l_, T, in.decode, &o));
     PROF("add_rmsnorm_o", launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
     ++launches_;
     if (fuse_swiglu_) {
@@ -376,17 +455,18 @@ int Model::forward(const StepInput& in) {
       // kernel: the expf/div epilogue is exposed at the end of every CTA; kept for the persistent
       // kernel of a later round, ACP_FUSE_SWIGLU=1 to try it)
       GemmLaunch g;
-      g.w = &L.m_gu.w; g.x = &m_xn_; g.M = 2 * c.ffn; g.N = T; g.K = c.hidden; g.splits = 1;
-      g.epi = EPI_SWIGLU; g.out = h_; g.ld = c.ffn; g.n_cap = T;
+      g.w = &L.m_gu.w; g.x = &m_xn_; g.M = 2 * ffn_l_; g.N = T; g.K = c.hidden; g.splits = 1;
+      g.epi = EPI_SWIGLU; g.out = h_; g.ld = ffn_l_; g.n_cap = T;
       PROF("gemm_gateup_swiglu", gemm_launch(g, stream_));
       ++launches_;
     } else {
       GemmOut gu;
-      PROF("gemm_gateup", gemm(L.m_gu, m_xn_, 2 * c.ffn, c.hidden, T, in.decode, &gu));
-      PROF("swiglu", launch_swiglu(gu, h_, T, c.ffn, stream_));
+      PROF("gemm_gateup", gemm(L.m_gu, m_xn_, 2 * ffn_l_, c.hidden, T, in.decode, &gu));
+      PROF("swiglu", launch_swiglu(gu, h_, T, ffn_l_, stream_));
       ++launches_;
     }
-    PROF("gemm_down", gemm(L.m_down, m_h_, c.hidden, c.ffn, T, in.decode, &dn));
+    if (tp_size_ > 1) PROF("gemm_down_allreduce", gemm_rowpar(L.m_down, m_h_, c.hidden, ffn_l_, T, in.decode, &dn));
+    else PROF("gemm_down", gemm(L.m_down, m_h_, c.hidden, ffn_l_, T, in.decode, &dn));
     if (l + 1 < c.layers) {
       PROF("add_rmsnorm_down", launch_add_rmsnorm(x_, dn, layers_[l + 1].attn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
     } else {
@@ -396,16 +476,29 @@ int Model::forward(const StepInput& in) {
     ++launches_;
   }
   if (in.n_sample > 0) {
-    const int m_tiles = (c.vocab + GEMM_BM - 1) / GEMM_BM;
+    const int m_tiles = (lm_rows_l_ + GEMM_BM - 1) / GEMM_BM;
     GemmLaunch g;
-    g.w = &m_lm_.w; g.x = &m_xs_; g.M = c.vocab; g.N = in.n_sample; g.K = c.hidden; g.splits = 1;
-    g.epi = EPI_ARGMAX; g.ld = c.vocab; g.n_cap = in.n_sample;
+    g.w = &m_lm_.w; g.x = &m_xs_; g.M = lm_rows_l_; g.N = in.n_sample; g.K = c.hidden; g.splits = 1;
+    g.epi = EPI_ARGMAX; g.ld = lm_rows_l_; g.n_cap = in.n_sample;
     const bool logits = in.want_logits || !in.all_greedy;
+    if (logits && tp_size_ > 1) {
+      fprintf(stderr, "[acp_infer] logits / sampling are not available on a tensor-parallel engine yet\n");
+      return -1;
+    }
     g.out = logits ? logits_ : nullptr;
     g.amax_val = amax_val_; g.amax_idx = amax_idx_;
     PROF("gemm_lm_head_argmax", gemm_launch(g, stream_));
     ++launches_;
-    if (in.all_greedy) {
+    if (tp_size_ > 1) {
+      // vocab-parallel: local arg-max, all-gather the (max, global id) candidates, pick the best
+      ACP_TRY(launch_argmax_finish(amax_val_, amax_idx_, m_tiles, in.n_sample, d_tokens_, amax_val_row_, stream_));
+      ACP_TRY(launch_pack_candidates(amax_val_row_, d_tokens_, lm_row0_, in.n_sample, cand_local_, stream_));
+      const NcclApi& nc = nccl_api();
+      int rc = nc.AllGather(cand_local_, cand_all_, (size_t)2 * in.n_sample * sizeof(int), kNcclInt8, comm_, stream_);
+      if (rc != 0) { fprintf(stderr, "[acp_infer] ncclAllGather: %s\n", nc.GetErrorString(rc)); return -5; }
+      ACP_TRY(launch_argmax_ranks(cand_all_, tp_size_, in.n_sample, d_tokens_, stream_));
+      launches_ += 4;
+    } else if (in.all_greedy) {
       PROF("argmax_finish", launch_argmax_finish(amax_val_, amax_idx_, m_tiles, in.n_sample, d_tokens_, nullptr, stream_));
     } else {
       ACP_CUDA_CHECK(cudaMemcpyAsync(d_sparams_, h_sparams_, in.n_sample * sizeof(SampleParams),
@@ -414,12 +507,15 @@ int Model::forward(const StepInput& in) {
       ACP_TRY(launch_sample(logits_, c.vocab, in.n_sample, d_sparams_, d_tokens_, stream_));
     }
     ++launches_;
-    ACP_CUDA_CHECK(cudaMemcpyAsync(h_tokens_, d_tokens_, in.n_sample * sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    d2h_bytes_ += (long long)(in.n_sample * sizeof(int));
-    if (in.want_logits) d2h_bytes_ += (long long)in.n_sample * c.vocab * (long long)sizeof(float);
-    if (in.want_logits)
-      ACP_CUDA_CHECK(cudaMemcpyAsync(h_logits_, logits_, (size_t)in.n_sample * c.vocab * sizeof(float),
-                                     cudaMemcpyDeviceToHost, stream_));
+    if (tp_rank_ == 0) {
+      ACP_CUDA_CHECK(cudaMemcpyAsync(h_tokens_, d_tokens_, in.n_sample * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      d2h_bytes_ += (long long)(in.n_sample * sizeof(int));
+      if (in.want_logits) {
+        d2h_bytes_ += (long long)in.n_sample * c.vocab * (long long)sizeof(float);
+        ACP_CUDA_CHECK(cudaMemcpyAsync(h_logits_, logits_, (size_t)in.n_sample * c.vocab * sizeof(float),
+                                       cudaMemcpyDeviceToHost, stream_));
+      }
+    }
   }
   return 0;
 }

@@ -10,6 +10,7 @@
 #include "attention.h"
 #include "gemm.h"
 #include "kernels.cuh"
+#include "nccl_dyn.h"
 
 namespace acp {
 
@@ -71,7 +72,11 @@ class Model {
  public:
   Model() = default;
   ~Model();
-  int init(const ModelConfig& cfg, const ModelLimits& lim, int device);
+  // tp_size > 1: this Model is shard `tp_rank` of a tensor-parallel group (Megatron layout: QKV and
+  // gate/up column-parallel, O and down row-parallel + NCCL all-reduce, LM head vocab-parallel);
+  // `lead` is shard 0, whose pinned step staging every shard uploads from.
+  int init(const ModelConfig& cfg, const ModelLimits& lim, int device, int tp_rank = 0, int tp_size = 1,
+           NcclComm comm = nullptr, Model* lead = nullptr);
   // Runs one step on `stream()`: tokens for the n_sample rows land in host_tokens() after sync().
   int forward(const StepInput& in);
   int sync();
@@ -96,6 +101,7 @@ class Model {
   int gen_weights();
   int gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool decode, GemmOut* out);
   int choose_splits(int M, int K, int N) const;
+  int gemm_rowpar(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool decode, GemmOut* out);
 
   ModelConfig cfg_;
   ModelLimits lim_;
@@ -103,6 +109,16 @@ class Model {
   cudaStream_t stream_ = nullptr;
   long long launches_ = 0, h2d_bytes_ = 0, d2h_bytes_ = 0;
   bool fuse_swiglu_ = false;
+  // tensor parallel
+  int tp_rank_ = 0, tp_size_ = 1;
+  NcclComm comm_ = nullptr;
+  Model* lead_ = nullptr;
+  int heads_l_ = 0, kvh_l_ = 0, qdim_l_ = 0, kvdim_l_ = 0, qkv_l_ = 0, ffn_l_ = 0;
+  int lm_rows_l_ = 0, lm_row0_ = 0;
+  float* ar_buf_ = nullptr;      // [T][hidden] fp32 all-reduce buffer
+  int* cand_local_ = nullptr;    // [2][B] packed (max, id)
+  int* cand_all_ = nullptr;      // [P][2][B]
+  float* amax_val_row_ = nullptr;
 
   struct Layer {
     __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;
