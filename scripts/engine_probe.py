@@ -18,6 +18,8 @@ cfg = {"model": model, "max_batch": max(64, n_req), "kv_pages": n_req * ((plen +
        "max_tokens_per_step": 8192, "max_pages_per_seq": max(32, (plen + max_new) // 32 + 2)}
 if len(sys.argv) > 5:
     cfg["layers"] = int(sys.argv[5])
+if os.environ.get("TP"):
+    cfg["tp"] = int(os.environ["TP"])
 t0 = time.time()
 eng = Engine(cfg)
 print("init s:", round(time.time() - t0, 2), flush=True)
@@ -39,10 +41,10 @@ for rep in range(int(os.environ.get('REPS', '3'))):
         ntok += len(body["acp"]["token_ids"])
     s = eng.stats()
     dec_tps = s["decode_tokens"] / (s["decode_ms"] / 1e3) if s["decode_ms"] else 0
-    gbs = s["decode_bytes_algorithmic"] / (s["decode_ms"] / 1e3) / 1e9 if s["decode_ms"] else 0
+    gbs = s.get("decode_bytes_algorithmic_per_gpu", s["decode_bytes_algorithmic"]) / (s["decode_ms"] / 1e3) / 1e9 if s["decode_ms"] else 0
     print(json.dumps({"rep": rep, "wall_s": round(wall, 3), "gen_tokens": ntok,
                       "reconciles_per_s": round(n_req / wall, 2),
-                      "decode_tok_per_s": round(dec_tps, 1), "decode_GBps": round(gbs, 1),
+                      "tp": s.get("tp", 1), "decode_tok_per_s": round(dec_tps, 1), "decode_GBps_per_gpu": round(gbs, 1),
                       "frac_of_6590": round(gbs / 6590, 3),
                       "decode_step_ms_p50": s.get("decode_step_ms_p50"),
                       "prefill_ms": round(s["prefill_ms"], 2), "prefill_tokens": s["prefill_tokens"],
