@@ -7,20 +7,24 @@
 
 namespace acp {
 
+// Decode attention, flat-scheduled: the (sequence, kv head, 64-token tile) space is flattened
+// and cut into `n_ctas` equal contiguous chunks, one per persistent CTA, so every SM streams the
+// same number of K/V bytes whatever the mix of context lengths.  A (sequence, kv head) item cut
+// by a chunk boundary is finished by attn_merge_kernel (fixed piece order => deterministic).
+constexpr int ATTN_MAX_PIECES = 3;
 struct AttnDecodeArgs {
-  const __nv_bfloat16* q;   // [rows][heads*128]
-  __nv_bfloat16* out;       // [rows][heads*128]
+  const __nv_bfloat16* q;   // [B][heads*128] (row b = sequence b)
+  __nv_bfloat16* out;       // [B][heads*128]
   const int* ctx_len;       // [B] keys visible to the query of sequence b (incl. its own token)
-  const int* q_rows;        // [B] row of sequence b's query in q/out (nullptr => b)
+  const int* tile_cum;      // [B+1] prefix sum of ceil(ctx_len/64)
   const int* page_table;    // [B][max_pages]
   int max_pages;
   int heads, kv_heads;
+  int num_seqs;
+  int total_tiles;          // tile_cum[B] * kv_heads
+  int n_ctas;               // grid size
   float scale;              // 1/sqrt(128)
-  int split_tokens;         // KV tokens per split (multiple of 64)
-  int max_splits;           // capacity of the split workspace
-  float* ws_o;              // [B][heads][max_splits][128]
-  float* ws_m;              // [B][heads][max_splits]
-  float* ws_l;
+  float* ws;                // partials [(item*3 + piece)*4 + warp][G rows][130] fp32
 };
 
 struct AttnPrefillArgs {
@@ -39,8 +43,11 @@ struct AttnPrefillArgs {
 
 int attn_setup_attributes();
 int attn_make_kv_map(CUtensorMap* out, const void* base, uint64_t num_pages, int kv_heads);
+// picks n_ctas (<= 2 per SM, chunk >= half the longest item so an item spans <= 3 CTAs)
+int attn_decode_plan(int total_tiles, int max_item_tiles);
+size_t attn_decode_ws_floats(int max_batch, int heads, int kv_heads);
 int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnDecodeArgs& a,
-                       int num_seqs, int max_ctx, cudaStream_t s);
+                       cudaStream_t s);
 int attn_prefill_block_tokens(int heads, int kv_heads);
 int launch_attn_prefill(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnPrefillArgs& a,
                         int num_blocks, cudaStream_t s);

@@ -41,6 +41,7 @@ int Engine::init(const char* config_json) {
   lim.num_pages = (int)cfg.get("kv_pages").as_int(lim.num_pages);
   lim.max_pages_per_seq = (int)cfg.get("max_pages_per_seq").as_int(lim.max_pages_per_seq);
   lim.split_tokens = (int)cfg.get("attn_split_tokens").as_int(lim.split_tokens);
+  if (cfg.find("prefix_cache")) prefix_cache_on_ = cfg.get("prefix_cache").as_bool(true);
   if (cfg.find("splitk_target_ctas")) lim.splitk_target_ctas = (int)cfg.get("splitk_target_ctas").as_int(lim.splitk_target_ctas);
   if (lim.max_batch < 1 || lim.max_tokens < 16 || lim.num_pages < 2 || lim.split_tokens % 64 != 0 ||
       lim.max_pages_per_seq < 1) {
@@ -287,9 +288,35 @@ void Engine::release_pages(Sequence& s) {
 }
 
 // caller holds mu_
+bool Engine::evict_one_locked() {
+  if (prefix_cache_.empty()) return false;
+  size_t lru = 0;
+  for (size_t i = 1; i < prefix_cache_.size(); ++i)
+    if (prefix_cache_[i].last_use < prefix_cache_[lru].last_use) lru = i;
+  for (int p : prefix_cache_[lru].pages) free_pages_.push_back(p);
+  prefix_cache_[lru] = std::move(prefix_cache_.back());
+  prefix_cache_.pop_back();
+  return true;
+}
+
+// caller holds mu_.  Keeps the pages that hold the PROMPT's K/V; everything else goes back.
+void Engine::retain_prefix_locked(Sequence& s) {
+  const int keep_tokens = std::min(s.prompt_len, s.n_cached);
+  const int keep_pages = keep_tokens / KV_PAGE;  // whole pages only
+  if (!prefix_cache_on_ || keep_pages < 1 || (int)s.pages.size() < keep_pages) { release_pages(s); return; }
+  CachedPrefix e;
+  e.tokens.assign(s.tokens.begin(), s.tokens.begin() + keep_pages * KV_PAGE);
+  e.pages.assign(s.pages.begin(), s.pages.begin() + keep_pages);
+  e.last_use = ++use_clock_;
+  for (size_t i = keep_pages; i < s.pages.size(); ++i) free_pages_.push_back(s.pages[i]);
+  s.pages.clear();
+  if (prefix_cache_.size() >= prefix_cache_max_) evict_one_locked();
+  prefix_cache_.push_back(std::move(e));
+}
+
 void Engine::finish(const std::shared_ptr<Sequence>& s, int status, const std::string& type,
                     const std::string& msg, const std::string& finish_reason) {
-  release_pages(*s);
+  if (status == 200) retain_prefix_locked(*s); else release_pages(*s);
   s->done = true;
   s->status = status;
   s->error_type = type;
@@ -320,8 +347,44 @@ void Engine::admit_locked() {
   while (!waiting_.empty() && (int)running_.size() < max_batch) {
     auto& s = waiting_.front();
     const int need = (s->prompt_len + s->sampling.max_tokens + KV_PAGE - 1) / KV_PAGE;
-    if (need > (int)free_pages_.size()) break;  // FIFO: wait for pages to come back
-    for (int i = 0; i < need; ++i) { s->pages.push_back(free_pages_.back()); free_pages_.pop_back(); }
+    // longest retained prefix (page granular; at least one prompt token is always recomputed so
+    // that there are logits to sample from)
+    int best = -1, best_pages = 0;
+    if (prefix_cache_on_) {
+      for (size_t i = 0; i < prefix_cache_.size(); ++i) {
+        const CachedPrefix& e = prefix_cache_[i];
+        if (e.tokens[0] != s->tokens[0] || (int)e.tokens.size() <= best_pages * KV_PAGE) continue;
+        const int lim = std::min((int)e.tokens.size(), s->prompt_len - 1);
+        int common = 0;
+        while (common < lim && e.tokens[common] == s->tokens[common]) ++common;
+        const int pg = common / KV_PAGE;
+        if (pg > best_pages) { best_pages = pg; best = (int)i; }
+      }
+    }
+    const int fresh = need - best_pages;
+    while (fresh > (int)free_pages_.size() && !prefix_cache_.empty()) {
+      // evict retained prefixes (never the one about to be reused) to make room
+      size_t lru = prefix_cache_.size();
+      for (size_t i = 0; i < prefix_cache_.size(); ++i)
+        if ((int)i != best && (lru == prefix_cache_.size() || prefix_cache_[i].last_use < prefix_cache_[lru].last_use)) lru = i;
+      if (lru == prefix_cache_.size()) break;
+      for (int p : prefix_cache_[lru].pages) free_pages_.push_back(p);
+      if (best == (int)prefix_cache_.size() - 1) best = (int)lru;  // the reused entry moves into the hole
+      prefix_cache_[lru] = std::move(prefix_cache_.back());
+      prefix_cache_.pop_back();
+    }
+    if (fresh > (int)free_pages_.size()) break;  // FIFO: wait for pages to come back
+    if (best >= 0) {
+      CachedPrefix& e = prefix_cache_[best];
+      for (int i = 0; i < best_pages; ++i) s->pages.push_back(e.pages[i]);
+      for (size_t i = best_pages; i < e.pages.size(); ++i) free_pages_.push_back(e.pages[i]);
+      s->n_cached = best_pages * KV_PAGE;
+      ++stats_.prefix_hits;
+      stats_.prefix_tokens_reused += s->n_cached;
+      prefix_cache_[best] = std::move(prefix_cache_.back());
+      prefix_cache_.pop_back();
+    }
+    for (int i = 0; i < fresh; ++i) { s->pages.push_back(free_pages_.back()); free_pages_.pop_back(); }
     s->t_admit = clk::now();
     running_.push_back(s);
     waiting_.pop_front();
@@ -425,6 +488,8 @@ bool Engine::step() {
     }
     row += q;
   }
+  in.tile_cum[0] = 0;
+  for (int b = 0; b < B; ++b) in.tile_cum[b + 1] = in.tile_cum[b] + (in.ctx_len[b] + 63) / 64;
   in.n_sample = ns;
   in.all_greedy = all_greedy;
   in.want_logits = want_logits;
@@ -573,6 +638,9 @@ std::string Engine::stats_json() {
     j.set("decode_step_ms_min", Json((double)v.front()));
     j.set("decode_step_ms_max", Json((double)v.back()));
   }
+  j.set("prefix_hits", Json(stats_.prefix_hits));
+  j.set("prefix_tokens_reused", Json(stats_.prefix_tokens_reused));
+  j.set("prefix_cache_entries", Json((int)prefix_cache_.size()));
   j.set("kv_pages_free", Json((int)free_pages_.size()));
   j.set("kv_pages_total", Json(model_.limits().num_pages - 1));
   {

@@ -38,7 +38,19 @@ struct Sequence {
   std::chrono::steady_clock::time_point t_submit, t_admit, t_first, t_done;
 };
 
+// KV retained after a sequence finishes: the context window of a Task is
+// append-only, so the next LLM step of the same Task (after its tool calls) starts with the same
+// tokens.  Only the PROMPT part is kept (those K/V came from the prefill arithmetic path, so a
+// cache hit is bit-identical to recomputing).  Move semantics: a hit hands the pages to the new
+// sequence; nothing is shared, nothing needs copy-on-write.
+struct CachedPrefix {
+  std::vector<int> tokens;  // tokens whose K/V the pages hold (positions 0..size-1)
+  std::vector<int> pages;
+  uint64_t last_use = 0;
+};
+
 struct EngineStats {
+  long long prefix_hits = 0, prefix_tokens_reused = 0;
   long long decode_steps = 0, decode_tokens = 0, decode_ctx_tokens = 0;
   long long prefill_steps = 0, prefill_tokens = 0;
   double decode_ms = 0, prefill_ms = 0;
@@ -93,6 +105,12 @@ class Engine {
   std::unordered_map<uint64_t, std::shared_ptr<Sequence>> all_;
   std::deque<uint64_t> finished_unreported_;
   std::vector<int> free_pages_;
+  std::vector<CachedPrefix> prefix_cache_;
+  uint64_t use_clock_ = 0;
+  bool prefix_cache_on_ = true;
+  size_t prefix_cache_max_ = 4096;
+  bool evict_one_locked();
+  void retain_prefix_locked(Sequence& s);
   std::atomic<bool> stop_{false};
   bool broken_ = false;
   uint64_t next_ticket_ = 1;

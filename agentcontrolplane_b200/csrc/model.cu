@@ -254,12 +254,9 @@ int Model::alloc_all() {
   ACP_TRY(dmalloc_t(allocs_, &amax_val_, (size_t)Bp * m_tiles_lm));
   ACP_TRY(dmalloc_t(allocs_, &amax_idx_, (size_t)Bp * m_tiles_lm));
   ACP_TRY(dmalloc_t(allocs_, &logits_, (size_t)lim_.max_batch * lm_rows_l_));
-  max_splits_ = (lim_.max_pages_per_seq * KV_PAGE + lim_.split_tokens - 1) / lim_.split_tokens;
-  ACP_TRY(dmalloc_t(allocs_, &attn_ws_o_, (size_t)lim_.max_batch * heads_l_ * max_splits_ * HEAD_DIM));
-  ACP_TRY(dmalloc_t(allocs_, &attn_ws_m_, (size_t)lim_.max_batch * heads_l_ * max_splits_));
-  ACP_TRY(dmalloc_t(allocs_, &attn_ws_l_, (size_t)lim_.max_batch * heads_l_ * max_splits_));
+  ACP_TRY(dmalloc_t(allocs_, &attn_ws_, attn_decode_ws_floats(lim_.max_batch, heads_l_, kvh_l_)));
   // step staging
-  ints_cap_ = (size_t)5 * lim_.max_tokens + (size_t)4 * lim_.max_batch +
+  ints_cap_ = (size_t)5 * lim_.max_tokens + (size_t)6 * lim_.max_batch +
               (size_t)lim_.max_batch * lim_.max_pages_per_seq + 64;
   ACP_TRY(dmalloc_t(allocs_, &d_ints_, ints_cap_));
   ACP_CUDA_CHECK(cudaMallocHost((void**)&h_ints_, ints_cap_ * sizeof(int)));
@@ -339,6 +336,7 @@ StepInput& Model::stage_begin(int T, int B, int n_blocks) {
   s.q_start = carve(B); s.q_len = carve(B); s.ctx_len = carve(B); s.sample_rows = carve(B);
   s.blk_seq = carve(n_blocks); s.blk_tok0 = carve(n_blocks);
   s.page_table = carve((size_t)B * lim_.max_pages_per_seq);
+  s.tile_cum = carve((size_t)B + 1);
   ints_used_ = off;
   s.sample_params = h_sparams_;
   return s;
@@ -427,17 +425,14 @@ int Model::forward(const StepInput& in) {
     ++launches_;
     if (in.decode) {
       AttnDecodeArgs aa;
-      aa.q = qbuf_; aa.out = attn_; aa.ctx_len = d_ctx; aa.q_rows = nullptr; aa.page_table = d_pt;
+      aa.q = qbuf_; aa.out = attn_; aa.ctx_len = d_ctx; aa.tile_cum = dev(in.tile_cum); aa.page_table = d_pt;
       aa.max_pages = lim_.max_pages_per_seq; aa.heads = heads_l_; aa.kv_heads = kvh_l_;
-      // KV splits only when (sequences x kv heads) alone cannot fill the machine (2 CTAs / SM)
-      int want = (2 * 148 + in.B * kvh_l_ - 1) / (in.B * kvh_l_);
-      if (want < 1) want = 1;
-      int st = ((in.max_ctx + want - 1) / want + 63) / 64 * 64;
-      if (st < lim_.split_tokens) st = lim_.split_tokens;
-      aa.scale = scale; aa.split_tokens = st; aa.max_splits = max_splits_;
-      aa.ws_o = attn_ws_o_; aa.ws_m = attn_ws_m_; aa.ws_l = attn_ws_l_;
-      PROF("attn_decode", launch_attn_decode(L.tm_k, L.tm_v, aa, in.B, in.max_ctx, stream_));
-      launches_ += (in.max_ctx > st) ? 2 : 1;
+      aa.num_seqs = in.B;
+      aa.total_tiles = in.tile_cum[in.B] * kvh_l_;   // host copy of the prefix sum (filled by the engine)
+      aa.n_ctas = attn_decode_plan(aa.total_tiles, (in.max_ctx + 63) / 64);
+      aa.scale = scale; aa.ws = attn_ws_;
+      PROF("attn_decode", launch_attn_decode(L.tm_k, L.tm_v, aa, stream_));
+      launches_ += 2;
     } else {
       AttnPrefillArgs pa;
       pa.q = qbuf_; pa.out = attn_; pa.blk_seq = d_bseq; pa.blk_tok0 = d_btok0; pa.q_start = d_qstart;

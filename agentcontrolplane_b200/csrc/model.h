@@ -65,6 +65,7 @@ struct StepInput {
   int* blk_seq;     // [n_blocks]
   int* blk_tok0;    // [n_blocks]
   int* page_table;  // [B][max_pages_per_seq]
+  int* tile_cum;    // [B+1] prefix sum of ceil(ctx_len/64) (decode attention schedule)
   SampleParams* sample_params;  // [n_sample] (pinned, separate upload when !all_greedy)
 };
 
@@ -138,8 +139,7 @@ class Model {
   size_t ws_bytes_ = 0;
   float *amax_val_ = nullptr, *logits_ = nullptr;
   int* amax_idx_ = nullptr;
-  float *attn_ws_o_ = nullptr, *attn_ws_m_ = nullptr, *attn_ws_l_ = nullptr;
-  int max_splits_ = 1;
+  float* attn_ws_ = nullptr;
   int* d_ints_ = nullptr;     // packed step ints
   size_t ints_cap_ = 0, ints_used_ = 0;
   int* h_ints_ = nullptr;     // pinned mirror

@@ -41,8 +41,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = {"name": "llama-3-8b provider:local, 64 concurrent Task CRs, 512-token context, greedy, max_tokens 64",
-            "model": "llama-3-8b", "tasks": 64, "prompt_tokens": 512, "max_tokens": 64}
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
+    1: {"name": "llama-3-8b provider:local, 64 concurrent Task CRs, 512-token context, greedy, max_tokens 64",
+        "model": "llama-3-8b", "tasks": 64, "prompt_tokens": 512, "max_tokens": 64, "tp": 1, "tools": 0, "tool_loop": False},
+    # BASELINE.json configs[3]: 70B tensor-parallel over 8 GPUs of ONE process, tool-call loop
+    # (2 LLM steps per Task: scripted tool call -> ToolCall CR "executes" -> fold-back -> final answer)
+    3: {"name": "llama-3-70b TP=8 provider:local, 256 concurrent Task CRs with tool-call loop, 512-token context, greedy, max_tokens 64",
+        "model": "llama-3-70b", "tasks": 256, "prompt_tokens": 512, "max_tokens": 64, "tp": 8, "tools": 2, "tool_loop": True},
+}
+WORKLOAD = WORKLOADS[1]
 
 
 def measured_peaks():
@@ -171,7 +179,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default=WORKLOAD["model"])
     ap.add_argument("--layers", type=int, default=0, help="dev only: truncate depth (result is then NOT a bench value)")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(WORKLOADS),
+                    help="BASELINE.json config index (1 = default; 3 = 70B TP=8: run as ONE process on an 8-GPU box, --gpus 1)")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = WORKLOADS[args.config]
+    if args.config != 1:
+        args.model = WORKLOAD["model"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,13 +208,15 @@ def main():
 
     n_tasks, plen, max_new = WORKLOAD["tasks"], WORKLOAD["prompt_tokens"], WORKLOAD["max_tokens"]
     pages_per_seq = (plen + max_new) // 32 + 2
+    if WORKLOAD["tool_loop"]:
+        pages_per_seq += 12   # second LLM step: window + tool call + tool result
     ecfg = {"model": args.model, "device": local_rank, "max_batch": max(64, n_tasks), "max_tokens_per_step": 8192,
-            "kv_pages": n_tasks * pages_per_seq + 8, "max_pages_per_seq": max(32, pages_per_seq)}
+            "kv_pages": n_tasks * pages_per_seq * 2 + 8, "max_pages_per_seq": max(32, pages_per_seq), "tp": WORKLOAD["tp"]}
     if args.layers:
         ecfg["layers"] = args.layers
     eng = Engine(ecfg)
     sim = {"tasks": n_tasks, "workers": n_tasks, "provider": "local", "model": args.model, "max_tokens": max_new,
-           "prompt_tokens": plen, "tools": 0}
+           "prompt_tokens": plen, "tools": WORKLOAD["tools"], "tool_loop": WORKLOAD["tool_loop"]}
 
     def barrier():
         torch.cuda.synchronize(local_rank)
@@ -230,22 +246,26 @@ def main():
     from agentcontrolplane_b200.replicas import aggregate
     wall_max, dev_max, (total_reconciles, total_decode_tokens) = aggregate(
         dist, f"cuda:{local_rank}", wall, dev_s, [float(reconciles), float(s1["decode_tokens"])])
+    _, dec_max, _ = aggregate(dist, f"cuda:{local_rank}", 0.0, s1["decode_ms"] / 1e3, [0.0])
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         dec_s = s1["decode_ms"] / 1e3
-        achieved = s1["decode_bytes_algorithmic"] / dec_s / 1e9 if dec_s > 0 else 0.0
+        # per GPU: a tensor-parallel engine streams 1/tp of the bytes on each GPU
+        achieved = s1.get("decode_bytes_algorithmic_per_gpu", s1["decode_bytes_algorithmic"]) / dec_s / 1e9 if dec_s > 0 else 0.0
         launches = s1["kernel_launches"] - s0["kernel_launches"]
         line = {
             "metric": "task_reconciles_per_s", "value": total_reconciles / dev_max, "unit": "reconciles/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3,
+            "n_gpus": world * WORKLOAD["tp"], "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"] + (f" [DEV: layers={args.layers}]" if args.layers else ""),
                        "weights": "seeded synthetic bf16 at Llama-3-8B shapes (seed 0xACB200)",
-                       "parallelism": f"dp{world} (one engine replica per GPU, no collective)",
+                       "parallelism": (f"dp{world} (one engine replica per GPU, no collective)" if WORKLOAD["tp"] == 1 else
+                                       f"tp{WORKLOAD['tp']} (one process, NCCL all-reduce x2 per layer over NVLink)"),
+                       "prefix_hits": s1.get("prefix_hits", 0), "prefix_tokens_reused": s1.get("prefix_tokens_reused", 0),
                        "l2": "inputs larger than L2: every decode step streams 15.0 GB of weights + 4.3 GB of KV through a 126 MB L2",
                        "final_phases": phases},
-            "decode_tokens_per_s": total_decode_tokens / (dec_s if world == 1 else dev_max) if dec_s > 0 else 0.0,
+            "decode_tokens_per_s": total_decode_tokens / dec_max if dec_max > 0 else 0.0,  # all ranks / max decode time
             "decode_tokens_per_s_rank0": s1["decode_tokens"] / dec_s if dec_s > 0 else 0.0,
             "prefill_tokens_per_s_rank0": s1["prefill_tokens"] / (s1["prefill_ms"] / 1e3) if s1["prefill_ms"] else 0.0,
             "p50_decode_step_ms": s1.get("decode_step_ms_p50"),

@@ -128,3 +128,33 @@ def test_deterministic_across_runs(eng):
     b, lb, _ = _run(eng, prompt, 8, logits=2)
     assert a == b
     assert np.array_equal(la, lb)
+
+
+def test_prefix_retention_is_bit_identical_to_recompute(eng):
+    """§8(f) rank 1: the second LLM step of a Task re-sends its (append-only) window; the engine
+    reuses the K/V pages of the shared prompt prefix and must produce exactly what a cold engine
+    produces."""
+    rng = np.random.default_rng(11)
+    p1 = _prompt(rng, 200)
+    p2 = p1 + [int(t) for t in rng.integers(0, 256, size=57)]
+    eng.stats_reset()
+    a1, _, _ = _run(eng, p1, 4)
+    s0 = eng.stats()
+    a2, lg2, _ = _run(eng, p2, 6, logits=2)
+    s1 = eng.stats()
+    assert s1["prefix_hits"] - s0["prefix_hits"] == 1
+    assert s1["prefix_tokens_reused"] - s0["prefix_tokens_reused"] == 192      # 6 whole pages of p1
+    assert s1["prefill_tokens"] - s0["prefill_tokens"] == len(p2) - 192        # only the delta is prefilled
+    cold = Engine({"model": eng.model_name, "max_batch": 8, "kv_pages": 128, "max_tokens_per_step": 1024,
+                   "prefix_cache": False})
+    try:
+        cold.model_name = eng.model_name
+        b2, lgb, _ = _run(cold, p2, 6, logits=2)
+        assert cold.stats()["prefix_hits"] == 0
+    finally:
+        cold.close()
+    assert a2 == b2
+    assert np.array_equal(lg2, lgb)          # bit-identical logits, not just tokens
+    # an unrelated prompt does not hit
+    _run(eng, _prompt(rng, 100), 2)
+    assert eng.stats()["prefix_hits"] == s1["prefix_hits"]
