@@ -1,10 +1,10 @@
 // attention.cu — paged-KV GQA attention for the decode engine (decode + causal prefill).
 //
-// KV cache layout per layer:  K, V : [num_pages][kv_heads][KV_PAGE=32][128] bf16.  Seen by TMA as
-// a 2-D tensor [num_pages*kv_heads*32 rows][128 cols]; one (page, kv-head) block is 32 contiguous
-// rows, loaded as two boxes {64 cols x 32 rows} with the 128-byte swizzle, so each staged block
-// in shared memory is [32 rows][128 B] with 16-byte chunks XOR-ed by (row & 7): ldmatrix reads
-// are bank-conflict free with no padding.
+// KV cache layout per layer:  K, V : [num_pages][kv_heads][2 dim-halves][KV_PAGE=32][64] bf16: the
+// block of one (page, kv head) is 8 KiB CONTIGUOUS.  Seen by TMA as a 2-D tensor
+// [num_pages*kv_heads*64 rows][64 cols]; one box {64 cols x 64 rows} with the 128-byte swizzle
+// fetches the whole block, which lands in shared memory as two [32 rows][128 B] halves with
+// 16-byte chunks XOR-ed by (row & 7): ldmatrix reads are bank-conflict free with no padding.
 //
 // A CTA stages 64-token tiles (2 pages: K 16 KiB + V 16 KiB per stage) through a 3-deep ring
 // filled by a dedicated producer warp (cp.async.bulk.tensor + mbarrier complete_tx); consumer
@@ -198,12 +198,9 @@ ACP_DEVINL void produce_tiles(const CUtensorMap* tm_k, const CUtensorMap* tm_v, 
     uint8_t* vdst = kdst + K_TILE_BYTES;
     for (int p = 0; p < n_pages; ++p) {
       const int page = pt_row[tok0 / KV_PAGE + p];
-      const int row = (page * kv_heads + kh) * KV_PAGE;
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        tma_load_2d(kdst + (p * 2 + hf) * BLOCK_BYTES, tm_k, &full_bar[s], hf * 64, row, kEvictFirst);
-        tma_load_2d(vdst + (p * 2 + hf) * BLOCK_BYTES, tm_v, &full_bar[s], hf * 64, row, kEvictFirst);
-      }
+      const int row = (page * kv_heads + kh) * 2 * KV_PAGE;  // one contiguous 8 KiB block: both dim-halves
+      tma_load_2d(kdst + p * 2 * BLOCK_BYTES, tm_k, &full_bar[s], 0, row, kEvictFirst);
+      tma_load_2d(vdst + p * 2 * BLOCK_BYTES, tm_v, &full_bar[s], 0, row, kEvictFirst);
     }
   }
 }
@@ -289,12 +286,9 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         const int* pt_row = a.page_table + (size_t)b * a.max_pages;
         for (int p = 0; p < n_pages; ++p) {
           const int page = pt_row[tok0 / KV_PAGE + p];
-          const int row = (page * a.kv_heads + kh) * KV_PAGE;
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            tma_load_2d(kdst + (p * 2 + hf) * BLOCK_BYTES, &tm_k, &L.full_bar[s], hf * 64, row, kEvictFirst);
-            tma_load_2d(vdst + (p * 2 + hf) * BLOCK_BYTES, &tm_v, &L.full_bar[s], hf * 64, row, kEvictFirst);
-          }
+          const int row = (page * a.kv_heads + kh) * 2 * KV_PAGE;  // contiguous 8 KiB block
+          tma_load_2d(kdst + p * 2 * BLOCK_BYTES, &tm_k, &L.full_bar[s], 0, row, kEvictFirst);
+          tma_load_2d(vdst + p * 2 * BLOCK_BYTES, &tm_v, &L.full_bar[s], 0, row, kEvictFirst);
         }
         if (++tile == nt) {
           tile = 0;
@@ -528,8 +522,9 @@ int attn_setup_attributes() {
 }
 
 int attn_make_kv_map(CUtensorMap* out, const void* base, uint64_t num_pages, int kv_heads) {
-  // 2-D view [num_pages*kv_heads*KV_PAGE rows][128 cols]; box {64 cols, 32 rows}
-  return tma_encode_2d_bf16(out, base, num_pages * (uint64_t)kv_heads * KV_PAGE, HEAD_DIM, KV_PAGE);
+  // block of a (page, kv head) = [2 dim-halves][32 tokens][64 dims], 8 KiB contiguous; 2-D view
+  // [num_pages*kv_heads*64 rows][64 cols], ONE box {64 cols, 64 rows} per block and tensor
+  return tma_encode_2d_bf16(out, base, num_pages * (uint64_t)kv_heads * 2 * KV_PAGE, 64, 2 * KV_PAGE);
 }
 
 int attn_decode_plan(int total_tiles, int max_item_tiles) {

@@ -192,8 +192,12 @@ rope_kv_kernel(GemmOutDev qkv, const int* __restrict__ pos, const int* __restric
     if (head < heads) {
       dst = qbuf + (size_t)t * q_dim + head * HEAD_DIM;
     } else {
+      // K/V block of a (page, kv head): [2 dim-halves][32 tokens][64 dims] = 8 KiB contiguous
       const int kh = head - heads;
-      dst = k_cache + (((size_t)page * kv_heads + kh) * KV_PAGE + (p % KV_PAGE)) * HEAD_DIM;
+      dst = k_cache + ((size_t)page * kv_heads + kh) * (KV_PAGE * HEAD_DIM) + (p % KV_PAGE) * 64;
+      *reinterpret_cast<uint2*>(dst + i0) = plo;
+      *reinterpret_cast<uint2*>(dst + KV_PAGE * 64 + i0) = phi;
+      continue;
     }
     *reinterpret_cast<uint2*>(dst + i0) = plo;
     *reinterpret_cast<uint2*>(dst + 64 + i0) = phi;
@@ -206,7 +210,8 @@ rope_kv_kernel(GemmOutDev qkv, const int* __restrict__ pos, const int* __restric
     const int kh = e / HEAD_DIM, d = e % HEAD_DIM;
     uint2 pv;
     pv.x = pack_bf16x2(v[0], v[1]); pv.y = pack_bf16x2(v[2], v[3]);
-    *reinterpret_cast<uint2*>(v_cache + (((size_t)page * kv_heads + kh) * KV_PAGE + (p % KV_PAGE)) * HEAD_DIM + d) = pv;
+    *reinterpret_cast<uint2*>(v_cache + ((size_t)page * kv_heads + kh) * (KV_PAGE * HEAD_DIM) +
+                              (d >> 6) * (KV_PAGE * 64) + (p % KV_PAGE) * 64 + (d & 63)) = pv;
   }
 }
 int launch_rope_kv(const RopeKvArgs& a, cudaStream_t s) {
