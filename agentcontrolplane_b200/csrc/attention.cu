@@ -383,6 +383,102 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   if (have_seg) flush();
 }
 
+// Per-item variant: CTA = (sequence, kv head), the whole context of the item, cross-warp merge in
+// shared memory, final bf16 output written directly (no workspace, no merge kernel).  Used when
+// there are enough items to fill the machine and every item is short (launch_attn_decode picks).
+__global__ void __launch_bounds__(ATTN_THREADS, 2)
+attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                        AttnDecodeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout L = carve(smem_raw);
+  const int b = blockIdx.x, kh = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = a.heads / a.kv_heads;
+  const int ctx = a.ctx_len[b];
+  const int n_tiles = (ctx + TILE_TOK - 1) / TILE_TOK;
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&L.full_bar[s], 1);
+      mbar_init(&L.empty_bar[s], CONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+
+  if (warp == CONSUMER_WARPS) {
+    if (lane == 0)
+      produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
+                    a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, ctx);
+    return;
+  }
+  const int r_lo = lane >> 2;
+  const __nv_bfloat16* qbase = a.q + (size_t)b * a.heads * HEAD_DIM + (size_t)kh * G * HEAD_DIM;
+  uint32_t qf[8][4];
+  load_q_frags(qf, r_lo < G ? qbase + r_lo * HEAD_DIM : nullptr,
+               r_lo + 8 < G ? qbase + (r_lo + 8) * HEAD_DIM : nullptr, lane);
+  WarpState st;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) st.o[d][0] = st.o[d][1] = st.o[d][2] = st.o[d][3] = 0.f;
+  st.m[0] = st.m[1] = -INFINITY;
+  st.l[0] = st.l[1] = 0.f;
+  const float sl2e = a.scale * 1.4426950408889634f;
+  const int tok_off = warp * 16;
+  for (int it = 0; it < n_tiles; ++it) {
+    const int s = it % STAGES;
+    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+    mbar_wait(&L.full_bar[s], ph);
+    uint8_t* kt = L.stages + s * STAGE_BYTES;
+    uint8_t* vt = kt + K_TILE_BYTES;
+    const int tile_tok0 = it * TILE_TOK;
+    const int valid = ctx - tile_tok0;
+    if (valid > tok_off) {
+      if (valid < tok_off + 16) zero_v_tail(vt, valid, tok_off + 16, lane);
+      process_tile<2>(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_off, ctx, ctx, sl2e, lane);
+    }
+    __syncwarp();
+    if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }
+  }
+  // ---- merge the 4 warps through the (drained) ring, rows < G only ----
+  st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 1);
+  st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 2);
+  st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 1);
+  st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 2);
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // every consumer is done with the ring
+  float* scratch = reinterpret_cast<float*>(L.stages);
+  float* my = scratch + warp * 16 * 130;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int r = r_lo + hh * 8;
+    if (r < G) {
+      if ((lane & 3) == 0) { my[r * 130 + 128] = st.m[hh]; my[r * 130 + 129] = st.l[hh]; }
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        my[r * 130 + d * 8 + 2 * (lane & 3)] = st.o[d][hh * 2];
+        my[r * 130 + d * 8 + 2 * (lane & 3) + 1] = st.o[d][hh * 2 + 1];
+      }
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int d = threadIdx.x;  // 128 consumer threads <-> 128 dims
+  for (int r = 0; r < G; ++r) {
+    float M = -INFINITY;
+    for (int w = 0; w < CONSUMER_WARPS; ++w) M = fmaxf(M, scratch[(w * 16 + r) * 130 + 128]);
+    float num = 0.f, den = 0.f;
+    for (int w = 0; w < CONSUMER_WARPS; ++w) {  // fixed order
+      const float mw = scratch[(w * 16 + r) * 130 + 128];
+      const float wgt = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * sl2e);
+      num += wgt * scratch[(w * 16 + r) * 130 + d];
+      den += wgt * scratch[(w * 16 + r) * 130 + 129];
+    }
+    a.out[(size_t)b * a.heads * HEAD_DIM + (kh * G + r) * HEAD_DIM + d] = __float2bfloat16_rn(num / den);
+  }
+}
+
 // Finishes every (sequence, head): combines the <= 3 pieces x 4 warp partials in fixed order.
 __global__ void __launch_bounds__(128)
 attn_merge_kernel(AttnDecodeArgs a) {
@@ -512,6 +608,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
 }  // namespace
 
 int attn_setup_attributes() {
+  cudaError_t e0 = cudaFuncSetAttribute(attn_decode_item_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  if (e0 != cudaSuccess) { fprintf(stderr, "[acp_infer] attention cudaFuncSetAttribute failed\n"); return -5; }
   cudaError_t e1 = cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
   cudaError_t e2 = cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -543,6 +641,12 @@ int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const A
                        cudaStream_t s) {
   if (a.num_seqs <= 0 || a.total_tiles <= 0) return 0;
   if (a.heads % a.kv_heads != 0 || a.heads / a.kv_heads > 16 || a.n_ctas < 1) return -1;
+  if (a.per_item) {
+    cudaError_t e = acp_launch(attn_decode_item_kernel, dim3(a.num_seqs, a.kv_heads), dim3(ATTN_THREADS), ATTN_SMEM,
+                               s, tm_k, tm_v, a);
+    if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode_item launch: %s\n", cudaGetErrorString(e)); return -5; }
+    return 0;
+  }
   cudaError_t e = acp_launch(attn_decode_kernel, dim3(a.n_ctas), dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode launch: %s\n", cudaGetErrorString(e)); return -5; }
   e = acp_launch(attn_merge_kernel, dim3(a.num_seqs, a.heads), dim3(128), 0, s, a);

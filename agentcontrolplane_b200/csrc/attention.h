@@ -22,7 +22,8 @@ struct AttnDecodeArgs {
   int heads, kv_heads;
   int num_seqs;
   int total_tiles;          // tile_cum[B] * kv_heads
-  int n_ctas;               // grid size
+  int n_ctas;               // grid size (flat schedule)
+  int per_item;             // 1: one CTA per (sequence, kv head), no workspace / merge (short, uniform items)
   float scale;              // 1/sqrt(128)
   float* ws;                // partials [(item*3 + piece)*4 + warp][G rows][130] fp32
 };

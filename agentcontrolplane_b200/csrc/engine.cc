@@ -41,6 +41,10 @@ int Engine::init(const char* config_json) {
   lim.num_pages = (int)cfg.get("kv_pages").as_int(lim.num_pages);
   lim.max_pages_per_seq = (int)cfg.get("max_pages_per_seq").as_int(lim.max_pages_per_seq);
   lim.split_tokens = (int)cfg.get("attn_split_tokens").as_int(lim.split_tokens);
+  {
+    const std::string am = cfg.get("attn_decode_mode").as_string();
+    lim.attn_decode_mode = am == "item" ? 1 : am == "flat" ? 2 : 0;
+  }
   if (cfg.find("prefix_cache")) prefix_cache_on_ = cfg.get("prefix_cache").as_bool(true);
   if (cfg.find("splitk_target_ctas")) lim.splitk_target_ctas = (int)cfg.get("splitk_target_ctas").as_int(lim.splitk_target_ctas);
   if (lim.max_batch < 1 || lim.max_tokens < 16 || lim.num_pages < 2 || lim.split_tokens % 64 != 0 ||
@@ -88,6 +92,39 @@ int Engine::init(const char* config_json) {
       });
     for (auto& t : inits) t.join();
     for (int r : rcs) if (r != 0) return r;
+    // peer-memory exchange (default): every shard may load/store every other shard's buffers
+    const std::string comm = cfg.get("tp_comm").as_string();
+    if (comm != "nccl") {
+      bool ok = true;
+      for (int i = 0; i < tp_ && ok; ++i) {
+        cudaSetDevice(devs[i]);
+        for (int j = 0; j < tp_; ++j) {
+          if (i == j) continue;
+          int can = 0;
+          cudaDeviceCanAccessPeer(&can, devs[i], devs[j]);
+          if (!can) { ok = false; break; }
+          cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = false; break; }
+          cudaGetLastError();
+        }
+      }
+      if (ok) {
+        TpPeers peers;
+        peers.size = tp_;
+        for (int p = 0; p < TP_MAX; ++p) {
+          Model* m = p == 0 ? &model_ : (p < tp_ ? extra_[p - 1].get() : &model_);
+          peers.ar[p] = m->ar_buffer(); peers.x[p] = m->x_buffer(); peers.xn[p] = m->xn_buffer();
+          peers.flags[p] = m->tp_flags();
+        }
+        for (int i = 0; i < tp_; ++i) {
+          peers.rank = i;
+          (i == 0 ? &model_ : extra_[i - 1].get())->set_peers(peers);
+        }
+      } else {
+        fprintf(stderr, "[acp_infer] peer access unavailable: tensor-parallel exchange falls back to NCCL all-reduce\n");
+      }
+      cudaSetDevice(device);
+    }
     for (int i = 1; i < tp_; ++i) tp_threads_.emplace_back([this, i] { tp_worker(i - 1); });
   }
   cudaSetDevice(device);

@@ -247,6 +247,7 @@ int Model::alloc_all() {
     ACP_TRY(dmalloc_t(allocs_, &cand_local_, (size_t)2 * Bp));
     ACP_TRY(dmalloc_t(allocs_, &cand_all_, (size_t)2 * Bp * tp_size_));
     ACP_TRY(dmalloc_t(allocs_, &amax_val_row_, (size_t)Bp));
+    ACP_TRY(dmalloc_t(allocs_, &tp_flags_, (size_t)TP_MAX, true));
   }
   ws_bytes_ = ws;
   ACP_TRY(dmalloc(allocs_, (void**)&ws_, ws_bytes_));
@@ -384,6 +385,32 @@ int Model::gemm_rowpar(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, 
   return 0;
 }
 
+// Row-parallel GEMM + the fused peer-memory exchange of tp_comm.cu:
+//   GEMM (fp32 partial planes) -> local split-K reduce -> barrier -> pull/reduce/residual/RMSNorm/
+//   push -> barrier.  x_ and xn_ are updated on EVERY rank by the rank that owns the row.
+int Model::rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool decode, const __nv_bfloat16* gain) {
+  const int M = cfg_.hidden;
+  GemmLaunch g;
+  g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
+  const int splits = decode ? choose_splits(M, K, N) : 1;
+  g.epi = EPI_F32; g.splits = splits; g.ld = M; g.n_cap = N;
+  g.out = splits > 1 ? ws_ : ar_buf_;
+  if (splits > 1 && (size_t)splits * N * M * sizeof(float) > ws_bytes_) return -4;
+  int rc = gemm_launch(g, stream_);
+  if (rc != 0) return rc;
+  ++launches_;
+  if (splits > 1) {
+    rc = launch_reduce_planes(ws_, splits, (size_t)N * M, ar_buf_, stream_);
+    if (rc != 0) return rc;
+    ++launches_;
+  }
+  rc = launch_tp_barrier(peers_, ++tp_epoch_, stream_);                     // partial sums ready everywhere
+  if (rc == 0) rc = launch_tp_reduce_norm(peers_, N, M, gain, cfg_.eps, stream_);
+  if (rc == 0) rc = launch_tp_barrier(peers_, ++tp_epoch_, stream_);        // every rank's rows landed
+  launches_ += 3;
+  return rc;
+}
+
 int Model::forward(const StepInput& in) {
   const ModelConfig& c = cfg_;
   if (in.T <= 0 || in.T > lim_.max_tokens || in.B > lim_.max_batch || in.n_sample > lim_.max_batch)
@@ -430,9 +457,14 @@ int Model::forward(const StepInput& in) {
       aa.num_seqs = in.B;
       aa.total_tiles = in.tile_cum[in.B] * kvh_l_;   // host copy of the prefix sum (filled by the engine)
       aa.n_ctas = attn_decode_plan(aa.total_tiles, (in.max_ctx + 63) / 64);
+      // enough short items to fill the machine by themselves: one CTA per item, output written
+      // directly; otherwise (few or long / uneven items) the flat schedule balances the K/V bytes
+      aa.per_item = (in.B * kvh_l_ >= 2 * 148 && in.max_ctx <= 1536) ? 1 : 0;
+      if (lim_.attn_decode_mode == 1) aa.per_item = 1;
+      if (lim_.attn_decode_mode == 2) aa.per_item = 0;
       aa.scale = scale; aa.ws = attn_ws_;
       PROF("attn_decode", launch_attn_decode(L.tm_k, L.tm_v, aa, stream_));
-      launches_ += 2;
+      launches_ += aa.per_item ? 1 : 2;
     } else {
       AttnPrefillArgs pa;
       pa.q = qbuf_; pa.out = attn_; pa.blk_seq = d_bseq; pa.blk_tok0 = d_btok0; pa.q_start = d_qstart;
@@ -441,10 +473,14 @@ int Model::forward(const StepInput& in) {
       PROF("attn_prefill", launch_attn_prefill(L.tm_k, L.tm_v, pa, in.n_blocks, stream_));
       ++launches_;
     }
-    if (tp_size_ > 1) PROF("gemm_o_allreduce", gemm_rowpar(L.m_o, m_attn_, c.hidden, qdim_l_, T, in.decode, &o));
-    else PROF("gemm_o", gemm(L.m_o, m_attn_, c.hidden, qdim_l_, T, in.decode, &o));
-    PROF("add_rmsnorm_o", launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
-    ++launches_;
+    if (tp_size_ > 1 && have_peers_) {
+      PROF("gemm_o+p2p_allreduce_norm", rowpar_fused(L.m_o, m_attn_, qdim_l_, T, in.decode, L.ffn_norm));
+    } else {
+      if (tp_size_ > 1) PROF("gemm_o_allreduce", gemm_rowpar(L.m_o, m_attn_, c.hidden, qdim_l_, T, in.decode, &o));
+      else PROF("gemm_o", gemm(L.m_o, m_attn_, c.hidden, qdim_l_, T, in.decode, &o));
+      PROF("add_rmsnorm_o", launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
+      ++launches_;
+    }
     if (fuse_swiglu_) {
       // optional: SwiGLU in the GEMM epilogue (measured SLOWER on B200 with this non-persistent
       // kernel: the expf/div epilogue is exposed at the end of every CTA; kept for the persistent
@@ -459,6 +495,17 @@ int Model::forward(const StepInput& in) {
       PROF("gemm_gateup", gemm(L.m_gu, m_xn_, 2 * ffn_l_, c.hidden, T, in.decode, &gu));
       PROF("swiglu", launch_swiglu(gu, h_, T, ffn_l_, stream_));
       ++launches_;
+    }
+    if (tp_size_ > 1 && have_peers_) {
+      // fused exchange writes x_ and xn_ (with the next layer's gain; the last layer's xn_ is unused)
+      const __nv_bfloat16* gain = (l + 1 < c.layers) ? layers_[l + 1].attn_norm : final_norm_;
+      PROF("gemm_down+p2p_allreduce_norm", rowpar_fused(L.m_down, m_h_, ffn_l_, T, in.decode, gain));
+      if (l + 1 == c.layers) {
+        GemmOut nothing;
+        PROF("add_rmsnorm_final", launch_add_rmsnorm(x_, nothing, final_norm_, xs_, d_srows, in.n_sample, c.hidden, c.eps, stream_));
+        ++launches_;
+      }
+      continue;
     }
     if (tp_size_ > 1) PROF("gemm_down_allreduce", gemm_rowpar(L.m_down, m_h_, c.hidden, ffn_l_, T, in.decode, &dn));
     else PROF("gemm_down", gemm(L.m_down, m_h_, c.hidden, ffn_l_, T, in.decode, &dn));

@@ -11,6 +11,7 @@
 #include "gemm.h"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
+#include "tp_comm.h"
 
 namespace acp {
 
@@ -42,6 +43,7 @@ struct ModelLimits {
   int max_pages_per_seq = 256;
   int split_tokens = 256;    // minimum KV tokens per decode-attention split (multiple of 64)
   int splitk_target_ctas = 222;
+  int attn_decode_mode = 0;  // 0 = auto, 1 = one CTA per (sequence, kv head), 2 = flat schedule
 };
 
 // Host-side description of one engine step (all arrays in pinned host memory, sized by limits).
@@ -96,6 +98,12 @@ class Model {
   long long d2h_bytes() const { return d2h_bytes_; }
   // ACP_PROFILE=1: CUDA events around every launch of decode steps (breaks PDL overlap; warm caches)
   std::string profile_json();
+  // peer-memory exchange (set by the engine once every shard is initialised)
+  void set_peers(const TpPeers& p) { peers_ = p; have_peers_ = true; }
+  float* ar_buffer() const { return ar_buf_; }
+  __nv_bfloat16* x_buffer() const { return x_; }
+  __nv_bfloat16* xn_buffer() const { return xn_; }
+  int* tp_flags() const { return tp_flags_; }
 
  private:
   int alloc_all();
@@ -120,6 +128,11 @@ class Model {
   int* cand_local_ = nullptr;    // [2][B] packed (max, id)
   int* cand_all_ = nullptr;      // [P][2][B]
   float* amax_val_row_ = nullptr;
+  TpPeers peers_;
+  bool have_peers_ = false;
+  int* tp_flags_ = nullptr;
+  int tp_epoch_ = 0;
+  int rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool decode, const __nv_bfloat16* gain);
 
   struct Layer {
     __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;

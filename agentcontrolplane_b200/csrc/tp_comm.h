@@ -1,0 +1,33 @@
+// tp_comm.h — tensor-parallel all-reduce FUSED with the residual add and RMSNorm, over NVLink
+// peer memory (single process, cudaDeviceEnablePeerAccess: every shard can load/store every
+// other shard's buffers directly).
+//
+//   x   = bf16( x + bf16( sum_ranks partial ) )          (row-parallel O / down projection)
+//   xn  = g * bf16( x * rsqrt(mean(x^2) + eps) )
+//
+// Rank r owns a contiguous block of token rows.  For its rows it LOADS the fp32 partial sums of
+// all ranks straight from their HBM over NVLink (reduce-scatter by pull, fixed rank order =>
+// deterministic and bit-identical on every rank), applies residual + RMSNorm in registers, and
+// STORES the new bf16 residual and normed rows into every rank's buffers (all-gather by push).
+// The reduced fp32 activation never exists in HBM.  Two flag barriers (release/acquire at system
+// scope) bracket the exchange.  Replaces ncclAllReduce + add_rmsnorm of the NCCL baseline path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+namespace acp {
+
+constexpr int TP_MAX = 8;
+struct TpPeers {
+  int rank = 0, size = 1;
+  const float* ar[TP_MAX];        // [T][H] fp32 partial sums of each rank
+  __nv_bfloat16* x[TP_MAX];       // residual stream replica of each rank
+  __nv_bfloat16* xn[TP_MAX];      // normed activations replica of each rank
+  int* flags[TP_MAX];             // flags[p][r]: rank r's arrival counter as seen by rank p
+};
+
+int launch_tp_barrier(const TpPeers& p, int epoch, cudaStream_t s);
+int launch_tp_reduce_norm(const TpPeers& p, int T, int hidden, const __nv_bfloat16* gain, float eps,
+                          cudaStream_t s);
+
+}  // namespace acp

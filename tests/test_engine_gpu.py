@@ -158,3 +158,27 @@ def test_prefix_retention_is_bit_identical_to_recompute(eng):
     # an unrelated prompt does not hit
     _run(eng, _prompt(rng, 100), 2)
     assert eng.stats()["prefix_hits"] == s1["prefix_hits"]
+
+
+@pytest.mark.parametrize("mode", ["item", "flat"])
+def test_decode_attention_modes_agree(eng, mode):
+    """Both decode-attention schedules (one CTA per item / flat persistent) give the oracle's
+    tokens on mixed context lengths (the auto heuristic only picks between them)."""
+    cfg = PRESETS[eng.model_name]
+    rng = np.random.default_rng(21)
+    prompts = [_prompt(rng, n) for n in (2, 31, 64, 65, 129, 300, 513)]
+    e = Engine({"model": eng.model_name, "max_batch": 16, "kv_pages": 256, "max_tokens_per_step": 2048,
+                "attn_decode_mode": mode, "prefix_cache": False})
+    try:
+        ts = [e.submit({"model": eng.model_name, "max_tokens": 5, "acp": {"prompt_token_ids": p}}) for p in prompts]
+        outs = []
+        for t in ts:
+            assert e.wait(t, 120000)
+            st, body = e.result(t)
+            assert st == 200
+            outs.append(body["acp"]["token_ids"])
+    finally:
+        e.close()
+    for p, got in zip(prompts, outs):
+        want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(p, 5, eos=(128001, 128008, 128009))
+        assert_tokens_match(got, want, margins, where=(mode, len(p)))

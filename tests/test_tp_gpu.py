@@ -27,8 +27,10 @@ def _gen(eng, model, prompts, n_new):
     return out
 
 
-@pytest.mark.parametrize("tp", [2, 4, 8])
-def test_tp_matches_tp1_and_oracle(tp):
+@pytest.mark.parametrize("tp,comm", [(2, "p2p"), (2, "nccl"), (4, "p2p"), (8, "p2p")])
+def test_tp_matches_tp1_and_oracle(tp, comm):
+    """comm = "p2p": fused peer-memory all-reduce + residual + RMSNorm (tp_comm.cu, the default);
+    comm = "nccl": ncclAllReduce + add_rmsnorm (the baseline path)."""
     if _ngpu() < tp:
         pytest.skip(f"needs {tp} GPUs")
     model = "tiny-g2" if tp == 2 else "llama-3-8b-l2"
@@ -37,7 +39,7 @@ def test_tp_matches_tp1_and_oracle(tp):
     prompts = [[128000] + [int(t) for t in rng.integers(0, 256, size=n - 1)] for n in (5, 40, 97, 300)]
     n_new = 6
     base = {"model": model, "max_batch": 16, "kv_pages": 256, "max_tokens_per_step": 1024}
-    with Engine(dict(base, tp=tp)) as e:
+    with Engine(dict(base, tp=tp, tp_comm=comm)) as e:
         got_tp = _gen(e, model, prompts, n_new)
         s = e.stats()
         assert s["tp"] == tp
