@@ -136,10 +136,78 @@ add_rmsnorm_kernel(__nv_bfloat16* __restrict__ x, GemmOutDev add, const __nv_bfl
     *reinterpret_cast<uint2*>(o + i) = packed;
   }
 }
+// Prefill variant (bf16 GEMM output, rows updated in place): 128 threads per row, each thread keeps
+// its <= 64 elements in registers, every 16-byte load of the row is issued before the first use.
+ACP_DEVINL void unpack8(const uint4& r, float (&v)[8]) {
+  v[0] = bf16_lo(r.x); v[1] = bf16_hi(r.x); v[2] = bf16_lo(r.y); v[3] = bf16_hi(r.y);
+  v[4] = bf16_lo(r.z); v[5] = bf16_hi(r.z); v[6] = bf16_lo(r.w); v[7] = bf16_hi(r.w);
+}
+ACP_DEVINL uint4 pack8(const float (&v)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]);
+  r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
+  return r;
+}
+__global__ void __launch_bounds__(128)
+add_rmsnorm_bf16_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ add, int add_ld,
+                        const __nv_bfloat16* __restrict__ gain, __nv_bfloat16* __restrict__ xn, int hidden,
+                        float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[4];
+  const int t = blockIdx.x;
+  const int nv = hidden / 8;  // 16-byte chunks per row (<= 1024)
+  uint4* xr = reinterpret_cast<uint4*>(x + (size_t)t * hidden);
+  const uint4* ar = reinterpret_cast<const uint4*>(add + (size_t)t * add_ld);
+  uint4 xraw[8], araw[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ch = threadIdx.x + c * 128;
+    if (ch < nv) { xraw[c] = xr[ch]; araw[c] = ar[ch]; }
+  }
+  float v[8][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ch = threadIdx.x + c * 128;
+    if (ch < nv) {
+      float a[8];
+      unpack8(xraw[c], v[c]);
+      unpack8(araw[c], a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[c][j] = bf16_round(v[c][j] + a[j]); ss += v[c][j] * v[c][j]; }
+      xr[ch] = pack8(v[c]);
+    }
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  const float tot = red[0] + red[1] + red[2] + red[3];
+  const float rstd = 1.0f / sqrtf(tot / (float)hidden + eps);
+  uint4* o = reinterpret_cast<uint4*>(xn + (size_t)t * hidden);
+  const uint4* gr = reinterpret_cast<const uint4*>(gain);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ch = threadIdx.x + c * 128;
+    if (ch < nv) {
+      float g[8], y[8];
+      unpack8(gr[ch], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = g[j] * bf16_round(v[c][j] * rstd);
+      o[ch] = pack8(y);
+    }
+  }
+}
+
 int launch_add_rmsnorm(__nv_bfloat16* x, const GemmOut& add, const __nv_bfloat16* gain,
                        __nv_bfloat16* xn, const int* row_map, int T, int hidden, float eps,
                        cudaStream_t s) {
   if (T <= 0) return 0;
+  if (add.ptr != nullptr && add.splits == 0 && row_map == nullptr && hidden % 8 == 0 && hidden <= 8192) {
+    ACP_LAUNCH("add_rmsnorm_bf16", acp_launch(add_rmsnorm_bf16_kernel, dim3(T), dim3(128), 0, s, x,
+                                            (const __nv_bfloat16*)add.ptr, add.ld, gain, xn, hidden, eps));
+    return 0;
+  }
   // one thread per 4 elements (single trip through the loads => one L2 round trip per phase)
   int threads = ((hidden / 4 + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;

@@ -247,7 +247,7 @@ int Model::alloc_all() {
     ACP_TRY(dmalloc_t(allocs_, &cand_local_, (size_t)2 * Bp));
     ACP_TRY(dmalloc_t(allocs_, &cand_all_, (size_t)2 * Bp * tp_size_));
     ACP_TRY(dmalloc_t(allocs_, &amax_val_row_, (size_t)Bp));
-    ACP_TRY(dmalloc_t(allocs_, &tp_flags_, (size_t)TP_MAX, true));
+    ACP_TRY(dmalloc_t(allocs_, &tp_flags_, (size_t)TP_MAX + 8, true));  // [0..7] flags, [8] done counter
   }
   ws_bytes_ = ws;
   ACP_TRY(dmalloc(allocs_, (void**)&ws_, ws_bytes_));
@@ -404,10 +404,11 @@ int Model::rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool d
     if (rc != 0) return rc;
     ++launches_;
   }
-  rc = launch_tp_barrier(peers_, ++tp_epoch_, stream_);                     // partial sums ready everywhere
-  if (rc == 0) rc = launch_tp_reduce_norm(peers_, N, M, gain, cfg_.eps, stream_);
-  if (rc == 0) rc = launch_tp_barrier(peers_, ++tp_epoch_, stream_);        // every rank's rows landed
-  launches_ += 3;
+  const int epoch = tp_epoch_ + 1;
+  tp_epoch_ += 2;
+  rc = launch_tp_reduce_norm(peers_, N, M, gain, cfg_.eps, epoch, tp_flags_ + TP_MAX, stream_);
+  if (rc == 0) rc = launch_tp_wait(peers_, epoch + 1, stream_);  // every rank's rows have landed here
+  launches_ += 2;
   return rc;
 }
 

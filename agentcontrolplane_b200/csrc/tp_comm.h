@@ -9,8 +9,9 @@
 // all ranks straight from their HBM over NVLink (reduce-scatter by pull, fixed rank order =>
 // deterministic and bit-identical on every rank), applies residual + RMSNorm in registers, and
 // STORES the new bf16 residual and normed rows into every rank's buffers (all-gather by push).
-// The reduced fp32 activation never exists in HBM.  Two flag barriers (release/acquire at system
-// scope) bracket the exchange.  Replaces ncclAllReduce + add_rmsnorm of the NCCL baseline path.
+// The reduced fp32 activation never exists in HBM.  The flag handshakes (release/acquire at system
+// scope) live INSIDE the kernel: CTA 0 signals "partials ready", every CTA waits for all ranks, the
+// last CTA to finish signals "rows pushed"; a 1-warp wait kernel closes the exchange.  Replaces ncclAllReduce + add_rmsnorm of the NCCL baseline path.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -26,8 +27,9 @@ struct TpPeers {
   int* flags[TP_MAX];             // flags[p][r]: rank r's arrival counter as seen by rank p
 };
 
-int launch_tp_barrier(const TpPeers& p, int epoch, cudaStream_t s);
+// epoch = "partials ready", epoch + 1 = "rows pushed"; done_ctr: one zeroed int per rank
 int launch_tp_reduce_norm(const TpPeers& p, int T, int hidden, const __nv_bfloat16* gain, float eps,
-                          cudaStream_t s);
+                          int epoch, int* done_ctr, cudaStream_t s);
+int launch_tp_wait(const TpPeers& p, int epoch, cudaStream_t s);
 
 }  // namespace acp
