@@ -1,8 +1,10 @@
 // gemm.cu — host side of the tcgen05 GEMM: TMA descriptor construction and launch dispatch.
 #include "gemm.h"
 #include "gemm_tcgen05.cuh"
+#include "gemm_persistent.cuh"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace acp {
 
@@ -108,9 +110,37 @@ static int launch_bn(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t st
   return -1;
 }
 
+static bool persistent_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACP_GEMM_PERSISTENT"); v = (e && *e == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+template <int EPI>
+static int launch_persistent(const GemmLaunch& g, cudaStream_t stream) {
+  GemmArgs a;
+  a.M = g.M; a.N = g.N; a.K = g.K; a.splits = 1; a.ld = g.ld; a.n_cap = g.n_cap;
+  a.out = g.out; a.amax_val = nullptr; a.amax_idx = nullptr; a.n_dev = g.n_dev;
+  const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (g.N + PGEMM_BN - 1) / PGEMM_BN;
+  int grid = m_tiles * n_tiles;
+  if (grid > 148) grid = 148;  // one persistent CTA per SM
+  cudaError_t e = acp_launch(gemm_wx_persistent_kernel<EPI>, dim3(grid), dim3(GEMM_THREADS), PGEMM_SMEM, stream,
+                             *g.w, g.x->x[4], a, m_tiles, n_tiles);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[acp_infer] persistent gemm launch failed EPI=%d: %s\n", EPI, cudaGetErrorString(e));
+    return -5;
+  }
+  return 0;
+}
+
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   if (g.N <= 0 || g.M <= 0) return 0;
   if (g.epi != EPI_F32 && g.splits != 1) return -1;
+  // prefill-sized problems: persistent kernel with double-buffered TMEM accumulators
+  if (g.N > 256 && g.bn_override == 0 && persistent_enabled()) {
+    if (g.epi == EPI_BF16) return launch_persistent<EPI_BF16>(g, stream);
+    if (g.epi == EPI_SWIGLU) return launch_persistent<EPI_SWIGLU>(g, stream);
+  }
   const int bn = g.bn_override ? g.bn_override : gemm_pick_bn(g.N);
   switch (bn) {
     case 16: return launch_bn<16>(g, g.x->x[0], stream);
@@ -137,6 +167,9 @@ static int set_attr_bn() {
 int gemm_setup_attributes() {
   int rc = set_attr_bn<16>() | set_attr_bn<32>() | set_attr_bn<64>() | set_attr_bn<128>() |
            set_attr_bn<256>();
+  if (cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess)
+    rc = -5;
   if (rc != 0) fprintf(stderr, "[acp_infer] cudaFuncSetAttribute(max dyn smem) failed\n");
   return rc;
 }

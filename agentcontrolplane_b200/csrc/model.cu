@@ -177,6 +177,11 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int 
   if (env) lim_.splitk_target_ctas = atoi(env);
   env = getenv("ACP_FUSE_SWIGLU");
   fuse_swiglu_ = env && *env == '1';
+  // prefill (persistent GEMM: the epilogue overlaps the next tile's MMAs) fuses SwiGLU by default
+  env = getenv("ACP_FUSE_SWIGLU_PREFILL");
+  fuse_swiglu_prefill_ = !(env && *env == '0');
+  env = getenv("ACP_GEMM_PERSISTENT");
+  if (env && *env == '0') fuse_swiglu_prefill_ = false;
   ACP_CUDA_CHECK(cudaSetDevice(device));
   ACP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   ACP_TRY(tma_init());
@@ -482,7 +487,7 @@ int Model::forward(const StepInput& in) {
       PROF("add_rmsnorm_o", launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
       ++launches_;
     }
-    if (fuse_swiglu_) {
+    if (fuse_swiglu_ || (!in.decode && T > 256 && fuse_swiglu_prefill_)) {
       // optional: SwiGLU in the GEMM epilogue (measured SLOWER on B200 with this non-persistent
       // kernel: the expf/div epilogue is exposed at the end of every CTA; kept for the persistent
       // kernel of a later round, ACP_FUSE_SWIGLU=1 to try it)

@@ -45,6 +45,8 @@ def _rand_bits(rng, shape, scale):
     (512, 128, 256, 0), (256, 256, 192, 0), (256, 300, 128, 0),   # two N tiles, ragged
     (200, 20, 96, 0),                                              # ragged M, N, K
     (768, 5, 512, 0), (1024, 64, 4096, 0), (256, 7, 64, 64),
+    (2560, 2600, 192, 0),   # prefill-sized: persistent kernel, 220 tiles > 148 CTAs (several tiles per CTA, both TMEM buffers)
+    (384, 1000, 4096, 0),   # persistent kernel, long K (ring wraps many times per tile)
 ])
 def test_gemm_bf16_out(M, N, K, bn):
     rng = np.random.default_rng(M * 131 + N * 7 + K)
@@ -109,7 +111,7 @@ def test_gemm_deterministic():
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 16, 128), (2048, 64, 512), (512, 300, 256)])
+@pytest.mark.parametrize("M,N,K", [(256, 16, 128), (2048, 64, 512), (512, 300, 256), (2048, 3000, 320)])
 def test_gemm_fused_swiglu_epilogue(M, N, K):
     """epi 3: interleaved (gate_j, up_j) rows -> bf16(bf16(silu(g)) * u), the oracle's expression."""
     from oracle.bf16 import bf16_round
