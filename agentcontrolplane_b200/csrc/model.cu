@@ -177,11 +177,11 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int 
   if (env) lim_.splitk_target_ctas = atoi(env);
   env = getenv("ACP_FUSE_SWIGLU");
   fuse_swiglu_ = env && *env == '1';
-  // prefill (persistent GEMM: the epilogue overlaps the next tile's MMAs) fuses SwiGLU by default
+  // Fusing SwiGLU into the persistent prefill GEMM's epilogue measured SLOWER (1676 vs 1473 + 151 us
+  // per 8192-token layer): the expf/div epilogue outlasts the 17 us mainloop of a tile and paces the
+  // MMAs.  Off by default; ACP_FUSE_SWIGLU_PREFILL=1 to try.
   env = getenv("ACP_FUSE_SWIGLU_PREFILL");
-  fuse_swiglu_prefill_ = !(env && *env == '0');
-  env = getenv("ACP_GEMM_PERSISTENT");
-  if (env && *env == '0') fuse_swiglu_prefill_ = false;
+  fuse_swiglu_prefill_ = env && *env == '1';
   ACP_CUDA_CHECK(cudaSetDevice(device));
   ACP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   ACP_TRY(tma_init());

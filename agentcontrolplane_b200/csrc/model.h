@@ -117,7 +117,7 @@ class Model {
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   long long launches_ = 0, h2d_bytes_ = 0, d2h_bytes_ = 0;
-  bool fuse_swiglu_ = false, fuse_swiglu_prefill_ = true;
+  bool fuse_swiglu_ = false, fuse_swiglu_prefill_ = false;
   // tensor parallel
   int tp_rank_ = 0, tp_size_ = 1;
   NcclComm comm_ = nullptr;

@@ -276,7 +276,11 @@ def main():
                     "decode_tokens_per_s": total_decode_tokens / wall_max},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         # DRAM bytes of one decode step from the committed ncu --set full capture (config 1 only)
+                         "traffic": 20.08e9 if (args.config == 1 and not args.layers) else None,
+                         "traffic_source": "profiles/r1_v1_ncu_full_decode_kernels.md: 32 x (QKV 51.0 + attention 148.0 + O 34.1 "
+                                           "+ gate/up 238.6 + down 123.0 MB) + LM head 1050 MB, ctx 515",
+                         "peak_source": peak_src,
                          "kernel": "one decode step (all launches of the step, CUDA events on the engine stream)",
                          "bytes_per_decode_step": s1["decode_bytes_algorithmic"] / max(1, s1["decode_steps"]),
                          "decode_steps_timed": s1["decode_steps"]},
