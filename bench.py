@@ -181,11 +181,18 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="dev only: truncate depth (result is then NOT a bench value)")
     ap.add_argument("--config", type=int, default=1, choices=sorted(WORKLOADS),
                     help="BASELINE.json config index (1 = default; 3 = 70B TP=8: run as ONE process on an 8-GPU box, --gpus 1)")
+    ap.add_argument("--tp", type=int, default=0, help="dev only: override the tensor-parallel degree of --config 3")
     args = ap.parse_args()
     global WORKLOAD
-    WORKLOAD = WORKLOADS[args.config]
+    WORKLOAD = dict(WORKLOADS[args.config])
     if args.config != 1:
-        args.model = WORKLOAD["model"]
+        if args.model == WORKLOADS[1]["model"]:
+            args.model = WORKLOAD["model"]
+        else:
+            WORKLOAD["name"] += f" [DEV: model={args.model}]"
+        if args.tp:
+            WORKLOAD["tp"] = args.tp
+            WORKLOAD["name"] += f" [DEV: tp={args.tp}]"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -123,5 +123,10 @@ def test_gemm_fused_swiglu_epilogue(M, N, K):
     g, u = gu[:, 0::2], gu[:, 1::2]
     ref = bf16_round(bf16_round(g / (np.float32(1.0) + np.exp(-g))) * u)
     got = bits_to_f32(out)
-    tol = np.maximum(np.abs(ref) * 2.0 ** -6, 2e-3)
-    assert np.all(np.abs(got - ref) <= tol), float(np.max(np.abs(got - ref)))
+    # three bf16 roundings are chained (g, u; silu(g); product): a 1e-6 difference in the fp32
+    # accumulation can flip each of them by one ulp, so the bound is ~3 ulp (2^-7 each) ...
+    err = np.abs(got - ref)
+    tol = np.maximum(np.abs(ref) * 2.0 ** -5, 4e-3)
+    assert np.all(err <= tol), float(np.max(err / np.maximum(np.abs(ref), 1e-3)))
+    # ... but almost every element must agree to one ulp
+    assert np.mean(err <= np.maximum(np.abs(ref) * 2.0 ** -7, 1e-3)) > 0.995
