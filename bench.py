@@ -172,6 +172,7 @@ def cpu_baseline_sample() -> dict:
 
 
 def main():
+    global WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -183,7 +184,6 @@ def main():
                     help="BASELINE.json config index (1 = default; 3 = 70B TP=8: run as ONE process on an 8-GPU box, --gpus 1)")
     ap.add_argument("--tp", type=int, default=0, help="dev only: override the tensor-parallel degree of --config 3")
     args = ap.parse_args()
-    global WORKLOAD
     WORKLOAD = dict(WORKLOADS[args.config])
     if args.config != 1:
         if args.model == WORKLOADS[1]["model"]:

@@ -182,3 +182,44 @@ def test_decode_attention_modes_agree(eng, mode):
     for p, got in zip(prompts, outs):
         want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(p, 5, eos=(128001, 128008, 128009))
         assert_tokens_match(got, want, margins, where=(mode, len(p)))
+
+
+def test_decode_batch_larger_than_one_n_tile(eng):
+    """More than 256 live sequences: the decode GEMMs run two N tiles over the same split-K planes.
+    Every sequence must still produce what it produces alone (checked against the oracle on a sample)."""
+    cfg = PRESETS[eng.model_name]
+    rng = np.random.default_rng(31)
+    n = 300
+    prompts = [_prompt(rng, int(rng.integers(2, 40))) for _ in range(n)]
+    big = Engine({"model": eng.model_name, "max_batch": 320, "kv_pages": 1024, "max_tokens_per_step": 4096,
+                  "prefix_cache": False})
+    try:
+        ts = [big.submit({"model": eng.model_name, "max_tokens": 4, "acp": {"prompt_token_ids": p}}) for p in prompts]
+        outs = []
+        for t in ts:
+            assert big.wait(t, 120000)
+            st, body = big.result(t)
+            assert st == 200
+            outs.append(body["acp"]["token_ids"])
+        assert big.stats()["decode_tokens"] >= 3 * 256          # really ran wide decode steps
+    finally:
+        big.close()
+    for i in (0, 1, 128, 255, 256, 257, 299):
+        want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(prompts[i], 4, eos=(128001, 128008, 128009))
+        assert_tokens_match(outs[i], want, margins, where=i)
+
+
+def test_long_context_chunked_prefill(eng):
+    """A 2500-token window prefilled in 1024-token chunks, then decoded across page and tile
+    boundaries, against the oracle."""
+    cfg = PRESETS[eng.model_name]
+    rng = np.random.default_rng(41)
+    prompt = _prompt(rng, 2500)
+    toks, _, _ = _run(eng, prompt, 4)
+    want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(prompt, 4, eos=(128001, 128008, 128009))
+    assert_tokens_match(toks, want, margins)
+    # context limit: prompt + max_tokens beyond max_pages_per_seq * 32 is a typed 400
+    t = eng.submit({"model": eng.model_name, "max_tokens": 8000, "acp": {"prompt_token_ids": prompt}})
+    assert eng.wait(t, 10000)
+    st, body = eng.result(t)
+    assert st == 400 and body["error"]["type"] == "context_length_exceeded"
