@@ -14,10 +14,11 @@
 //   P is split into bf16 hi + lo parts (two PV MMAs) so that P keeps ~16 mantissa bits: the
 //   result matches an fp32-softmax oracle to ~1e-6 and no bf16 rounding of P needs mirroring.
 //
-// decode  : flat-scheduled persistent CTAs: the (sequence, kv head, tile) space is cut into equal
-//           contiguous chunks (one per CTA, 2 CTAs/SM); the 4 consumer warps each take a 16-token
-//           slice of every tile; per-warp partial (m, l, O) go to a workspace and
-//           attn_merge_kernel finishes every (sequence, head) in fixed order.
+// decode  : CTA = (sequence, kv head[, chunk of 1024 tokens]); the 4 consumer warps each take a
+//           16-token slice of every tile.  Short contexts: one CTA per item, warps merged in shared
+//           memory, output written directly.  Long contexts: fixed 1024-token chunks (boundaries
+//           depend only on the sequence itself => batch invariant), per-warp partial (m, l, O) to
+//           a workspace, attn_merge_kernel combines them in fixed order.
 // prefill : CTA = (16/G*4 query tokens of one sequence, kv head); every warp owns 16 rows
 //           (16/G tokens x G heads) and all warps walk the causal range of tiles together.
 //
@@ -224,11 +225,11 @@ static_assert(SCRATCH_FLOATS * 4 <= STAGES * STAGE_BYTES, "scratch must fit in t
 constexpr int ATTN_SMEM = STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + 16;
 
 // =================================================================================
-// decode (flat-scheduled persistent CTAs)
+// decode, chunked: CTA = (sequence, kv head, chunk of ATTN_CHUNK_TILES tiles).  The chunk
+// boundaries depend ONLY on the sequence's own length, so a sequence's result is bit-identical
+// whatever it is batched with (batch invariance); long contexts are cut into many CTAs, which is
+// what balances a mix of context lengths.  attn_merge_kernel combines the chunks in order.
 // =================================================================================
-ACP_DEVINL int cta_of_tile(long long f, long long total, int n_ctas) {
-  return (int)(((f + 1) * n_ctas + total - 1) / total) - 1;  // the c with c*total/n <= f < (c+1)*total/n
-}
 ACP_DEVINL int find_seq(const int* cum, int n, long long f, int kvh) {  // cum[b]*kvh <= f < cum[b+1]*kvh
   int lo = 0, hi = n - 1;
   while (lo < hi) {
@@ -245,9 +246,17 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   SmemLayout L = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = a.heads / a.kv_heads;
-  const int c = blockIdx.x;
-  const long long total = a.total_tiles;
-  const long long f0 = (long long)c * total / a.n_ctas, f1 = (long long)(c + 1) * total / a.n_ctas;
+  // flat CTA index -> (sequence b, kv head kh, chunk)
+  const long long f = blockIdx.x;
+  const int b = find_seq(a.chunk_cum, a.num_seqs, f, a.kv_heads);
+  const int nc = a.chunk_cum[b + 1] - a.chunk_cum[b];
+  const long long r = f - (long long)a.chunk_cum[b] * a.kv_heads;
+  const int kh = (int)(r / nc), chunk = (int)(r % nc);
+  const int ctx = a.ctx_len[b];
+  const int tile_begin = chunk * ATTN_CHUNK_TILES;
+  const int tok_end = min(ctx, (chunk + 1) * ATTN_CHUNK_TILES * TILE_TOK);
+  const int tile_end = (tok_end + TILE_TOK - 1) / TILE_TOK;
+  const int n_tiles = tile_end - tile_begin;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -261,126 +270,87 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   }
   __syncthreads();
   pdl_wait();  // K/V pages and q were written by the previous kernel (rope_kv)
-  if (f0 >= f1) return;
-
-  // position of flat tile f0: sequence b, kv head kh, tile index within the item
-  int b = find_seq(a.tile_cum, a.num_seqs, f0, a.kv_heads);
-  int nt = a.tile_cum[b + 1] - a.tile_cum[b];
-  long long r = f0 - (long long)a.tile_cum[b] * a.kv_heads;
-  int kh = (int)(r / nt), tile = (int)(r % nt);
 
   if (warp == CONSUMER_WARPS) {
-    // ===== producer: walk the chunk, one 64-token tile per ring slot =====
-    if (lane == 0) {
-      int it = 0;
-      int ctx = a.ctx_len[b];
-      for (long long f = f0; f < f1; ++f, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&L.empty_bar[s], ph ^ 1u);
-        const int tok0 = tile * TILE_TOK;
-        const int n_pages = (ctx - tok0 > KV_PAGE) ? 2 : 1;
-        mbar_arrive_expect_tx(&L.full_bar[s], (uint32_t)(n_pages * 4 * BLOCK_BYTES));
-        uint8_t* kdst = L.stages + s * STAGE_BYTES;
-        uint8_t* vdst = kdst + K_TILE_BYTES;
-        const int* pt_row = a.page_table + (size_t)b * a.max_pages;
-        for (int p = 0; p < n_pages; ++p) {
-          const int page = pt_row[tok0 / KV_PAGE + p];
-          const int row = (page * a.kv_heads + kh) * 2 * KV_PAGE;  // contiguous 8 KiB block
-          tma_load_2d(kdst + p * 2 * BLOCK_BYTES, &tm_k, &L.full_bar[s], 0, row, kEvictFirst);
-          tma_load_2d(vdst + p * 2 * BLOCK_BYTES, &tm_v, &L.full_bar[s], 0, row, kEvictFirst);
-        }
-        if (++tile == nt) {
-          tile = 0;
-          if (++kh == a.kv_heads) {
-            kh = 0;
-            ++b;
-            if (b < a.num_seqs) { nt = a.tile_cum[b + 1] - a.tile_cum[b]; ctx = a.ctx_len[b]; }
-          }
-        }
-      }
-    }
+    if (lane == 0)
+      produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
+                    a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, tile_begin, tile_end, tok_end);
     return;
   }
-
-  // ===== consumers: every warp waits on every tile (consecutive mbarrier phases) and owns a
-  // 16-token slice of it; per (item, piece) each warp writes its own partial (m, l, O) =====
   const float sl2e = a.scale * 1.4426950408889634f;
   const int r_lo = lane >> 2;
   const int tok_off = warp * 16;
+  const __nv_bfloat16* qbase = a.q + (size_t)b * a.heads * HEAD_DIM + (size_t)kh * G * HEAD_DIM;
+  uint32_t qf[8][4];
+  load_q_frags(qf, r_lo < G ? qbase + r_lo * HEAD_DIM : nullptr,
+               r_lo + 8 < G ? qbase + (r_lo + 8) * HEAD_DIM : nullptr, lane);
   WarpState st;
 #pragma unroll
   for (int d = 0; d < 16; ++d) st.o[d][0] = st.o[d][1] = st.o[d][2] = st.o[d][3] = 0.f;
   st.m[0] = st.m[1] = -INFINITY;
   st.l[0] = st.l[1] = 0.f;
-  uint32_t qf[8][4];
-  bool have_seg = false;
-  int seg_b = 0, seg_kh = 0;
-  long long seg_start = 0;
-  int ctx = 0;
-
-  auto flush = [&]() {
-    // quad-reduce the row sums, then rows < G of this warp go to the workspace
-    st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 1);
-    st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 2);
-    st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 1);
-    st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 2);
-    const int piece = c - cta_of_tile(seg_start, total, a.n_ctas);
-    const size_t item = (size_t)seg_b * a.kv_heads + seg_kh;
-    float* base = a.ws + (((item * ATTN_MAX_PIECES + piece) * CONSUMER_WARPS + warp) * G) * 130;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int row = r_lo + hh * 8;
-      if (row < G) {
-        float* dst = base + (size_t)row * 130;
-        if ((lane & 3) == 0) { dst[128] = st.m[hh]; dst[129] = st.l[hh]; }
-#pragma unroll
-        for (int d = 0; d < 16; ++d)
-          *reinterpret_cast<float2*>(dst + d * 8 + 2 * (lane & 3)) = make_float2(st.o[d][hh * 2], st.o[d][hh * 2 + 1]);
-      }
-    }
-  };
-
-  int it = 0;
-  for (long long f = f0; f < f1; ++f, ++it) {
-    if (!have_seg || tile == 0) {
-      if (have_seg) flush();
-      // new (sequence, kv head) segment: load its query heads, reset the running softmax state
-      have_seg = true;
-      seg_b = b; seg_kh = kh;
-      seg_start = (long long)a.tile_cum[b] * a.kv_heads + (long long)kh * nt;
-      ctx = a.ctx_len[b];
-      const __nv_bfloat16* qbase = a.q + (size_t)b * a.heads * HEAD_DIM + (size_t)kh * G * HEAD_DIM;
-      load_q_frags(qf, r_lo < G ? qbase + r_lo * HEAD_DIM : nullptr,
-                   r_lo + 8 < G ? qbase + (r_lo + 8) * HEAD_DIM : nullptr, lane);
-#pragma unroll
-      for (int d = 0; d < 16; ++d) st.o[d][0] = st.o[d][1] = st.o[d][2] = st.o[d][3] = 0.f;
-      st.m[0] = st.m[1] = -INFINITY;
-      st.l[0] = st.l[1] = 0.f;
-    }
+  for (int it = 0; it < n_tiles; ++it) {
     const int s = it % STAGES;
     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
     mbar_wait(&L.full_bar[s], ph);
     uint8_t* kt = L.stages + s * STAGE_BYTES;
     uint8_t* vt = kt + K_TILE_BYTES;
-    const int tile_tok0 = tile * TILE_TOK;
-    const int valid = ctx - tile_tok0;   // tokens of this tile that exist
+    const int tile_tok0 = (tile_begin + it) * TILE_TOK;
+    const int valid = tok_end - tile_tok0;   // tokens of this tile that exist
     if (valid > tok_off) {
       if (valid < tok_off + 16) zero_v_tail(vt, valid, tok_off + 16, lane);
-      process_tile<2>(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_off, ctx, ctx, sl2e, lane);
+      process_tile<2>(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_off, tok_end, tok_end, sl2e, lane);
     }
     __syncwarp();
     if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }
-    if (++tile == nt) {
-      tile = 0;
-      if (++kh == a.kv_heads) {
-        kh = 0;
-        ++b;
-        if (b < a.num_seqs) nt = a.tile_cum[b + 1] - a.tile_cum[b];
-      }
+  }
+  // per-warp partial (m, l, O) of this chunk -> workspace
+  st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 1);
+  st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 2);
+  st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 1);
+  st.l[1] += __shfl_xor_sync(0xffffffffu, st.l[1], 2);
+  const size_t item = (size_t)b * a.kv_heads + kh;
+  float* base = a.ws + (((item * a.max_chunks + chunk) * CONSUMER_WARPS + warp) * G) * 130;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int row = r_lo + hh * 8;
+    if (row < G) {
+      float* dst = base + (size_t)row * 130;
+      if ((lane & 3) == 0) { dst[128] = st.m[hh]; dst[129] = st.l[hh]; }
+#pragma unroll
+      for (int d = 0; d < 16; ++d)
+        *reinterpret_cast<float2*>(dst + d * 8 + 2 * (lane & 3)) = make_float2(st.o[d][hh * 2], st.o[d][hh * 2 + 1]);
     }
   }
-  if (have_seg) flush();
+}
+
+// Finishes every (sequence, head): combines chunks x 4 warp partials in fixed order.  For a
+// single-chunk item this is the same arithmetic, in the same order, as attn_decode_item_kernel.
+__global__ void __launch_bounds__(128)
+attn_merge_kernel(AttnDecodeArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
+  const int G = a.heads / a.kv_heads;
+  const int kh = head / G, g = head % G;
+  const int n_pieces = a.chunk_cum[b + 1] - a.chunk_cum[b];
+  const float sl2e = a.scale * 1.4426950408889634f;
+  const size_t item = (size_t)b * a.kv_heads + kh;
+  const float* base = a.ws + ((item * a.max_chunks) * CONSUMER_WARPS * G) * 130;
+  float M = -INFINITY;
+  for (int p = 0; p < n_pieces; ++p)
+    for (int w = 0; w < CONSUMER_WARPS; ++w)
+      M = fmaxf(M, base[(((size_t)p * CONSUMER_WARPS + w) * G + g) * 130 + 128]);
+  float num = 0.f, den = 0.f;
+  for (int p = 0; p < n_pieces; ++p)
+    for (int w = 0; w < CONSUMER_WARPS; ++w) {  // fixed order => deterministic
+      const float* src = base + (((size_t)p * CONSUMER_WARPS + w) * G + g) * 130;
+      const float mw = src[128];
+      const float wgt = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * sl2e);
+      num += wgt * src[d];
+      den += wgt * src[129];
+    }
+  a.out[(size_t)b * a.heads * HEAD_DIM + head * HEAD_DIM + d] = __float2bfloat16_rn(num / den);
 }
 
 // Per-item variant: CTA = (sequence, kv head), the whole context of the item, cross-warp merge in
@@ -477,38 +447,6 @@ attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
     }
     a.out[(size_t)b * a.heads * HEAD_DIM + (kh * G + r) * HEAD_DIM + d] = __float2bfloat16_rn(num / den);
   }
-}
-
-// Finishes every (sequence, head): combines the <= 3 pieces x 4 warp partials in fixed order.
-__global__ void __launch_bounds__(128)
-attn_merge_kernel(AttnDecodeArgs a) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int b = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
-  const int G = a.heads / a.kv_heads;
-  const int kh = head / G, g = head % G;
-  const long long total = a.total_tiles;
-  const int nt = a.tile_cum[b + 1] - a.tile_cum[b];
-  const long long fs = (long long)a.tile_cum[b] * a.kv_heads + (long long)kh * nt;
-  const int c_first = cta_of_tile(fs, total, a.n_ctas), c_last = cta_of_tile(fs + nt - 1, total, a.n_ctas);
-  const int n_pieces = c_last - c_first + 1;
-  const float sl2e = a.scale * 1.4426950408889634f;
-  const size_t item = (size_t)b * a.kv_heads + kh;
-  const float* base = a.ws + ((item * ATTN_MAX_PIECES) * CONSUMER_WARPS * G) * 130;
-  float M = -INFINITY;
-  for (int p = 0; p < n_pieces; ++p)
-    for (int w = 0; w < CONSUMER_WARPS; ++w)
-      M = fmaxf(M, base[(((size_t)p * CONSUMER_WARPS + w) * G + g) * 130 + 128]);
-  float num = 0.f, den = 0.f;
-  for (int p = 0; p < n_pieces; ++p)
-    for (int w = 0; w < CONSUMER_WARPS; ++w) {  // fixed order => deterministic
-      const float* src = base + (((size_t)p * CONSUMER_WARPS + w) * G + g) * 130;
-      const float mw = src[128];
-      const float wgt = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * sl2e);
-      num += wgt * src[d];
-      den += wgt * src[129];
-    }
-  a.out[(size_t)b * a.heads * HEAD_DIM + head * HEAD_DIM + d] = __float2bfloat16_rn(num / den);
 }
 
 // =================================================================================
@@ -625,29 +563,27 @@ int attn_make_kv_map(CUtensorMap* out, const void* base, uint64_t num_pages, int
   return tma_encode_2d_bf16(out, base, num_pages * (uint64_t)kv_heads * 2 * KV_PAGE, 64, 2 * KV_PAGE);
 }
 
-int attn_decode_plan(int total_tiles, int max_item_tiles) {
-  if (total_tiles <= 0) return 0;
-  const int min_chunk = (max_item_tiles + 1) / 2 > 0 ? (max_item_tiles + 1) / 2 : 1;
-  int n = total_tiles / min_chunk;
-  if (n > 2 * 148) n = 2 * 148;  // 2 CTAs per SM (register limited)
-  if (n < 1) n = 1;
-  return n;
+int attn_decode_chunks(int ctx_len) {
+  const int tiles = (ctx_len + TILE_TOK - 1) / TILE_TOK;
+  return (tiles + ATTN_CHUNK_TILES - 1) / ATTN_CHUNK_TILES;
 }
-size_t attn_decode_ws_floats(int max_batch, int heads, int kv_heads) {
-  return (size_t)max_batch * kv_heads * ATTN_MAX_PIECES * CONSUMER_WARPS * (heads / kv_heads) * 130;
+size_t attn_decode_ws_floats(int max_batch, int heads, int kv_heads, int max_chunks) {
+  return (size_t)max_batch * kv_heads * max_chunks * CONSUMER_WARPS * (heads / kv_heads) * 130;
 }
 
 int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnDecodeArgs& a,
                        cudaStream_t s) {
-  if (a.num_seqs <= 0 || a.total_tiles <= 0) return 0;
-  if (a.heads % a.kv_heads != 0 || a.heads / a.kv_heads > 16 || a.n_ctas < 1) return -1;
+  if (a.num_seqs <= 0) return 0;
+  if (a.heads % a.kv_heads != 0 || a.heads / a.kv_heads > 16) return -1;
   if (a.per_item) {
     cudaError_t e = acp_launch(attn_decode_item_kernel, dim3(a.num_seqs, a.kv_heads), dim3(ATTN_THREADS), ATTN_SMEM,
                                s, tm_k, tm_v, a);
     if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode_item launch: %s\n", cudaGetErrorString(e)); return -5; }
     return 0;
   }
-  cudaError_t e = acp_launch(attn_decode_kernel, dim3(a.n_ctas), dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
+  if (a.total_chunks <= 0) return -1;
+  cudaError_t e = acp_launch(attn_decode_kernel, dim3((unsigned)(a.total_chunks * a.kv_heads)), dim3(ATTN_THREADS),
+                             ATTN_SMEM, s, tm_k, tm_v, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode launch: %s\n", cudaGetErrorString(e)); return -5; }
   e = acp_launch(attn_merge_kernel, dim3(a.num_seqs, a.heads), dim3(128), 0, s, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_merge launch: %s\n", cudaGetErrorString(e)); return -5; }

@@ -7,25 +7,23 @@
 
 namespace acp {
 
-// Decode attention, flat-scheduled: the (sequence, kv head, 64-token tile) space is flattened
-// and cut into `n_ctas` equal contiguous chunks, one per persistent CTA, so every SM streams the
-// same number of K/V bytes whatever the mix of context lengths.  A (sequence, kv head) item cut
-// by a chunk boundary is finished by attn_merge_kernel (fixed piece order => deterministic).
-constexpr int ATTN_MAX_PIECES = 3;
+// Decode attention.  per_item = 1: one CTA per (sequence, kv head).  Otherwise chunked: one CTA
+// per (sequence, kv head, chunk of ATTN_CHUNK_TILES x 64 tokens) + attn_merge_kernel.
+constexpr int ATTN_CHUNK_TILES = 16;  // 1024 tokens
 struct AttnDecodeArgs {
   const __nv_bfloat16* q;   // [B][heads*128] (row b = sequence b)
   __nv_bfloat16* out;       // [B][heads*128]
   const int* ctx_len;       // [B] keys visible to the query of sequence b (incl. its own token)
-  const int* tile_cum;      // [B+1] prefix sum of ceil(ctx_len/64)
+  const int* chunk_cum;     // [B+1] prefix sum of the per-sequence chunk counts
   const int* page_table;    // [B][max_pages]
   int max_pages;
   int heads, kv_heads;
   int num_seqs;
-  int total_tiles;          // tile_cum[B] * kv_heads
-  int n_ctas;               // grid size (flat schedule)
-  int per_item;             // 1: one CTA per (sequence, kv head), no workspace / merge (short, uniform items)
+  int total_chunks;         // chunk_cum[B]
+  int max_chunks;           // workspace stride (chunks per item)
+  int per_item;             // 1: whole item per CTA, no workspace / merge
   float scale;              // 1/sqrt(128)
-  float* ws;                // partials [(item*3 + piece)*4 + warp][G rows][130] fp32
+  float* ws;                // partials [(item*max_chunks + chunk)*4 + warp][G rows][130] fp32
 };
 
 struct AttnPrefillArgs {
@@ -44,9 +42,8 @@ struct AttnPrefillArgs {
 
 int attn_setup_attributes();
 int attn_make_kv_map(CUtensorMap* out, const void* base, uint64_t num_pages, int kv_heads);
-// picks n_ctas (<= 2 per SM, chunk >= half the longest item so an item spans <= 3 CTAs)
-int attn_decode_plan(int total_tiles, int max_item_tiles);
-size_t attn_decode_ws_floats(int max_batch, int heads, int kv_heads);
+int attn_decode_chunks(int ctx_len);  // chunks of one sequence
+size_t attn_decode_ws_floats(int max_batch, int heads, int kv_heads, int max_chunks);
 int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnDecodeArgs& a,
                        cudaStream_t s);
 int attn_prefill_block_tokens(int heads, int kv_heads);

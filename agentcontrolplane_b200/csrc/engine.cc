@@ -526,7 +526,7 @@ bool Engine::step() {
     row += q;
   }
   in.tile_cum[0] = 0;
-  for (int b = 0; b < B; ++b) in.tile_cum[b + 1] = in.tile_cum[b] + (in.ctx_len[b] + 63) / 64;
+  for (int b = 0; b < B; ++b) in.tile_cum[b + 1] = in.tile_cum[b] + attn_decode_chunks(in.ctx_len[b]);
   in.n_sample = ns;
   in.all_greedy = all_greedy;
   in.want_logits = want_logits;

@@ -260,7 +260,8 @@ int Model::alloc_all() {
   ACP_TRY(dmalloc_t(allocs_, &amax_val_, (size_t)Bp * m_tiles_lm));
   ACP_TRY(dmalloc_t(allocs_, &amax_idx_, (size_t)Bp * m_tiles_lm));
   ACP_TRY(dmalloc_t(allocs_, &logits_, (size_t)lim_.max_batch * lm_rows_l_));
-  ACP_TRY(dmalloc_t(allocs_, &attn_ws_, attn_decode_ws_floats(lim_.max_batch, heads_l_, kvh_l_)));
+  attn_max_chunks_ = attn_decode_chunks(lim_.max_pages_per_seq * KV_PAGE);
+  ACP_TRY(dmalloc_t(allocs_, &attn_ws_, attn_decode_ws_floats(lim_.max_batch, heads_l_, kvh_l_, attn_max_chunks_)));
   // step staging
   ints_cap_ = (size_t)5 * lim_.max_tokens + (size_t)6 * lim_.max_batch +
               (size_t)lim_.max_batch * lim_.max_pages_per_seq + 64;
@@ -458,17 +459,17 @@ int Model::forward(const StepInput& in) {
     ++launches_;
     if (in.decode) {
       AttnDecodeArgs aa;
-      aa.q = qbuf_; aa.out = attn_; aa.ctx_len = d_ctx; aa.tile_cum = dev(in.tile_cum); aa.page_table = d_pt;
+      aa.q = qbuf_; aa.out = attn_; aa.ctx_len = d_ctx; aa.chunk_cum = dev(in.tile_cum); aa.page_table = d_pt;
       aa.max_pages = lim_.max_pages_per_seq; aa.heads = heads_l_; aa.kv_heads = kvh_l_;
       aa.num_seqs = in.B;
-      aa.total_tiles = in.tile_cum[in.B] * kvh_l_;   // host copy of the prefix sum (filled by the engine)
-      aa.n_ctas = attn_decode_plan(aa.total_tiles, (in.max_ctx + 63) / 64);
-      // enough short items to fill the machine by themselves: one CTA per item, output written
-      // directly; otherwise (few or long / uneven items) the flat schedule balances the K/V bytes
-      aa.per_item = (in.B * kvh_l_ >= 2 * 148 && in.max_ctx <= 1536) ? 1 : 0;
-      if (lim_.attn_decode_mode == 1) aa.per_item = 1;
-      if (lim_.attn_decode_mode == 2) aa.per_item = 0;
+      aa.total_chunks = in.tile_cum[in.B];   // host copy of the prefix sum (filled by the engine)
+      aa.max_chunks = attn_max_chunks_;
       aa.scale = scale; aa.ws = attn_ws_;
+      // every item fits one chunk: one CTA per item writes the output directly (identical
+      // arithmetic to chunked + merge for a single chunk, so the choice never changes results)
+      aa.per_item = (aa.total_chunks == in.B) ? 1 : 0;
+      if (lim_.attn_decode_mode == 1 && aa.total_chunks == in.B) aa.per_item = 1;
+      if (lim_.attn_decode_mode == 2) aa.per_item = 0;
       PROF("attn_decode", launch_attn_decode(L.tm_k, L.tm_v, aa, stream_));
       launches_ += aa.per_item ? 1 : 2;
     } else {

@@ -67,7 +67,7 @@ struct StepInput {
   int* blk_seq;     // [n_blocks]
   int* blk_tok0;    // [n_blocks]
   int* page_table;  // [B][max_pages_per_seq]
-  int* tile_cum;    // [B+1] prefix sum of ceil(ctx_len/64) (decode attention schedule)
+  int* tile_cum;    // [B+1] prefix sum of attn_decode_chunks(ctx_len) (decode attention schedule)
   SampleParams* sample_params;  // [n_sample] (pinned, separate upload when !all_greedy)
 };
 
@@ -153,6 +153,7 @@ class Model {
   float *amax_val_ = nullptr, *logits_ = nullptr;
   int* amax_idx_ = nullptr;
   float* attn_ws_ = nullptr;
+  int attn_max_chunks_ = 1;
   int* d_ints_ = nullptr;     // packed step ints
   size_t ints_cap_ = 0, ints_used_ = 0;
   int* h_ints_ = nullptr;     // pinned mirror

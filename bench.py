@@ -218,7 +218,10 @@ def main():
     if WORKLOAD["tool_loop"]:
         pages_per_seq += 12   # second LLM step: window + tool call + tool result
     ecfg = {"model": args.model, "device": local_rank, "max_batch": max(64, n_tasks), "max_tokens_per_step": 8192,
-            "kv_pages": n_tasks * pages_per_seq * 2 + 8, "max_pages_per_seq": max(32, pages_per_seq), "tp": WORKLOAD["tp"]}
+            "kv_pages": n_tasks * pages_per_seq * 2 + 8, "max_pages_per_seq": max(32, pages_per_seq), "tp": WORKLOAD["tp"],
+            # config 1 measures cold Task steps: KV retention stays off so that no prefill work is skipped;
+            # the tool loop of config 3 is exactly the case retention exists for (second turn of a Task)
+            "prefix_cache": bool(WORKLOAD["tool_loop"])}
     if args.layers:
         ecfg["layers"] = args.layers
     eng = Engine(ecfg)
@@ -293,7 +296,7 @@ def main():
                          "decode_steps_timed": s1["decode_steps"]},
             "clocks": clocks,
         }
-        if world == 1:
+        if world == 1 and args.config == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
     eng.close()
