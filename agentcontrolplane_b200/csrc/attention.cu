@@ -246,7 +246,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   SmemLayout L = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = a.heads / a.kv_heads;
-  // flat CTA index -> (sequence b, kv head kh, chunk)
+  // linear CTA index -> (sequence b, kv head kh, chunk)
   const long long f = blockIdx.x;
   const int b = find_seq(a.chunk_cum, a.num_seqs, f, a.kv_heads);
   const int nc = a.chunk_cum[b + 1] - a.chunk_cum[b];

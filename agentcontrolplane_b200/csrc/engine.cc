@@ -40,15 +40,13 @@ int Engine::init(const char* config_json) {
   lim.max_tokens = (int)cfg.get("max_tokens_per_step").as_int(lim.max_tokens);
   lim.num_pages = (int)cfg.get("kv_pages").as_int(lim.num_pages);
   lim.max_pages_per_seq = (int)cfg.get("max_pages_per_seq").as_int(lim.max_pages_per_seq);
-  lim.split_tokens = (int)cfg.get("attn_split_tokens").as_int(lim.split_tokens);
   {
     const std::string am = cfg.get("attn_decode_mode").as_string();
-    lim.attn_decode_mode = am == "item" ? 1 : am == "flat" ? 2 : 0;
+    lim.attn_decode_mode = am == "item" ? 1 : (am == "chunked" || am == "flat") ? 2 : 0;
   }
   if (cfg.find("prefix_cache")) prefix_cache_on_ = cfg.get("prefix_cache").as_bool(true);
   if (cfg.find("splitk_target_ctas")) lim.splitk_target_ctas = (int)cfg.get("splitk_target_ctas").as_int(lim.splitk_target_ctas);
-  if (lim.max_batch < 1 || lim.max_tokens < 16 || lim.num_pages < 2 || lim.split_tokens % 64 != 0 ||
-      lim.max_pages_per_seq < 1) {
+  if (lim.max_batch < 1 || lim.max_tokens < 16 || lim.num_pages < 2 || lim.max_pages_per_seq < 1) {
     fprintf(stderr, "[acp_infer] invalid engine limits\n");
     return -1;
   }
@@ -138,9 +136,7 @@ int Engine::init(const char* config_json) {
 void Engine::shutdown() {
   {
     std::lock_guard<std::mutex> lk(mu_);
-    if (stop_.exchange(true)) {
-      // already stopping
-    }
+    stop_ = true;  // idempotent: a second shutdown() finds nothing left to join or free
   }
   cv_work_.notify_all();
   if (thread_.joinable()) thread_.join();

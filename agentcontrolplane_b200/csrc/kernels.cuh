@@ -40,7 +40,7 @@ struct RopeKvArgs {
   const float* cos_tab;  // [max_pos][64]
   const float* sin_tab;
   __nv_bfloat16* qbuf;   // [T][q_dim]
-  __nv_bfloat16* k_cache;  // layer base: [num_pages][kv_heads][PAGE][128]
+  __nv_bfloat16* k_cache;  // layer base: [num_pages][kv_heads][2 dim-halves][KV_PAGE][64]
   __nv_bfloat16* v_cache;
   int T, heads, kv_heads;
 };

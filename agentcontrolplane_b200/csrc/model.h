@@ -41,9 +41,8 @@ struct ModelLimits {
   int max_tokens = 8192;     // token rows per step (prefill chunk budget)
   int num_pages = 2048;      // KV pages (32 tokens each) in the pool, page 0 is reserved
   int max_pages_per_seq = 256;
-  int split_tokens = 256;    // minimum KV tokens per decode-attention split (multiple of 64)
   int splitk_target_ctas = 222;
-  int attn_decode_mode = 0;  // 0 = auto, 1 = one CTA per (sequence, kv head), 2 = flat schedule
+  int attn_decode_mode = 0;  // 0 = auto, 1 = one CTA per (sequence, kv head) when possible, 2 = always chunked + merge
 };
 
 // Host-side description of one engine step (all arrays in pinned host memory, sized by limits).

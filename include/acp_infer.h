@@ -50,7 +50,8 @@ typedef struct acp_engine acp_engine;
  *   "weights": "synthetic"            (seeded generator; no checkpoint files exist in this image)
  *   "seed": 11317760                  (0xACB200)
  *   "device": 0, "max_batch": 256, "max_tokens_per_step": 8192, "kv_pages": 2048,
- *   "max_pages_per_seq": 256, "attn_split_tokens": 512                                     */
+ *   "max_pages_per_seq": 256, "prefix_cache": true, "tp": 1 (tensor-parallel GPUs of THIS process),
+ *   "tp_comm": "p2p" | "nccl", "layers": n (truncated depth, dev only)                      */
 int acp_infer_init(const char* config_json, acp_engine** out);
 
 /* Non-blocking submit of one chat-completions request (what SendRequest does at

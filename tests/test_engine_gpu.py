@@ -160,10 +160,10 @@ def test_prefix_retention_is_bit_identical_to_recompute(eng):
     assert eng.stats()["prefix_hits"] == s1["prefix_hits"]
 
 
-@pytest.mark.parametrize("mode", ["item", "flat"])
+@pytest.mark.parametrize("mode", ["item", "chunked"])
 def test_decode_attention_modes_agree(eng, mode):
-    """Both decode-attention schedules (one CTA per item / flat persistent) give the oracle's
-    tokens on mixed context lengths (the auto heuristic only picks between them)."""
+    """Both decode-attention paths (one CTA per item / chunked + merge) give the oracle's tokens on
+    mixed context lengths (auto only picks between them, and they are arithmetically identical)."""
     cfg = PRESETS[eng.model_name]
     rng = np.random.default_rng(21)
     prompts = [_prompt(rng, n) for n in (2, 31, 64, 65, 129, 300, 513)]
