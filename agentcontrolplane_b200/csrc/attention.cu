@@ -27,6 +27,7 @@
 #include "attention.h"
 #include "common.cuh"
 #include "gemm.h"
+#include "gemm_out.cuh"
 
 namespace acp {
 
@@ -210,6 +211,10 @@ struct SmemLayout {
   uint8_t* stages;
   uint64_t* full_bar;
   uint64_t* empty_bar;
+  __nv_bfloat16* nq;  // [16][128] rotated query heads of the new token (rows >= G unused)
+  float* nk;          // [128] rotated key of the new token (bf16-rounded values)
+  float* nv;          // [128]
+  float* ns;          // [16] q . k_new per head (raw score units)
 };
 ACP_DEVINL SmemLayout carve(uint8_t* raw) {
   SmemLayout L;
@@ -217,12 +222,116 @@ ACP_DEVINL SmemLayout carve(uint8_t* raw) {
   L.stages = base;
   L.full_bar = (uint64_t*)(base + STAGES * STAGE_BYTES);
   L.empty_bar = L.full_bar + STAGES;
+  uint8_t* extra = (uint8_t*)(((uintptr_t)(L.empty_bar + STAGES) + 63) & ~(uintptr_t)63);
+  L.nq = (__nv_bfloat16*)extra;
+  L.nk = (float*)(extra + 16 * HEAD_DIM * 2);
+  L.nv = L.nk + HEAD_DIM;
+  L.ns = L.nv + HEAD_DIM;
   return L;
 }
 // decode cross-warp merge scratch [4 warps][16 rows][130] aliases the (drained) stage ring
 constexpr int SCRATCH_FLOATS = CONSUMER_WARPS * 16 * 130;
 static_assert(SCRATCH_FLOATS * 4 <= STAGES * STAGE_BYTES, "scratch must fit in the ring");
-constexpr int ATTN_SMEM = STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + 16;
+// new-token scratch of the decode kernels: q[16 rows][128] bf16 (4 KiB) + k[128] + v[128] + s[16] fp32
+constexpr int NEWTOK_BYTES = 16 * HEAD_DIM * 2 + (2 * HEAD_DIM + 16) * 4;
+constexpr int ATTN_SMEM = STAGES * STAGE_BYTES + 1024 + 2 * STAGES * 8 + 16 + NEWTOK_BYTES + 64;
+
+// ---------------------------------------------------------------------------------
+// New-token prologue of the decode kernels (128 consumer threads): reduce the QKV split-K planes
+// for this (sequence, kv head), apply RoPE with the same explicit-rn arithmetic as rope_kv_kernel,
+// keep q (bf16) / k / v in shared memory, append K/V to the cache (if `write_kv`), and compute the
+// G scores q . k_new.  Ends with a consumer-only barrier.
+// ---------------------------------------------------------------------------------
+ACP_DEVINL void new_token_prologue(const AttnDecodeArgs& a, const SmemLayout& L, int b, int kh, int ctx,
+                                   bool write_kv) {
+  const int G = a.heads / a.kv_heads;
+  const int tid = threadIdx.x;  // 0..127
+  const int pos = ctx - 1;
+  const GemmOutDev qkv{a.qkv_ptr, a.qkv_splits, a.qkv_n_cap, a.qkv_ld};
+  const int q_dim = a.heads * HEAD_DIM, kv_dim = a.kv_heads * HEAD_DIM;
+  const float* ct = a.cos_tab + (size_t)pos * (HEAD_DIM / 2);
+  const float* st = a.sin_tab + (size_t)pos * (HEAD_DIM / 2);
+  const int page = a.page_table[(size_t)b * a.max_pages + pos / KV_PAGE];
+  const size_t blk = ((size_t)page * a.kv_heads + kh) * (KV_PAGE * HEAD_DIM) + (size_t)(pos % KV_PAGE) * 64;
+  // rotated vectors: G query heads then the key head; 16 work items (4 frequency pairs) per head
+  for (int w = tid; w < (G + 1) * 16; w += 128) {
+    const int hv = w >> 4, i0 = (w & 15) * 4;
+    const int col = hv < G ? (kh * G + hv) * HEAD_DIM : q_dim + kh * HEAD_DIM;
+    float x1[4], x2[4];
+    gemm_out_load4(qkv, b, col + i0, x1);
+    gemm_out_load4(qkv, b, col + 64 + i0, x2);
+    const float4 c = *reinterpret_cast<const float4*>(ct + i0);
+    const float4 s = *reinterpret_cast<const float4*>(st + i0);
+    const float cc[4] = {c.x, c.y, c.z, c.w}, sn[4] = {s.x, s.y, s.z, s.w};
+    float lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      lo[j] = bf16_round(__fsub_rn(__fmul_rn(x1[j], cc[j]), __fmul_rn(x2[j], sn[j])));
+      hi[j] = bf16_round(__fadd_rn(__fmul_rn(x2[j], cc[j]), __fmul_rn(x1[j], sn[j])));
+    }
+    if (hv < G) {
+      __nv_bfloat16* d = L.nq + hv * HEAD_DIM;
+      *reinterpret_cast<uint2*>(d + i0) = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+      *reinterpret_cast<uint2*>(d + 64 + i0) = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { L.nk[i0 + j] = lo[j]; L.nk[64 + i0 + j] = hi[j]; }
+      if (write_kv) {
+        *reinterpret_cast<uint2*>(a.k_cache + blk + i0) = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+        *reinterpret_cast<uint2*>(a.k_cache + blk + KV_PAGE * 64 + i0) =
+            make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
+      }
+    }
+  }
+  // value head: plain copy (32 work items of 4 elements), done by the upper threads
+  if (tid >= 96) {
+    const int e = (tid - 96) * 4;
+    float v[4];
+    gemm_out_load4(qkv, b, q_dim + kv_dim + kh * HEAD_DIM + e, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) L.nv[e + j] = v[j];
+    if (write_kv)
+      *reinterpret_cast<uint2*>(a.v_cache + blk + (e >> 6) * (KV_PAGE * 64) + (e & 63)) =
+          make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  // scores of the new token against itself: warp w reduces head w, w+4, ...
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int g = warp; g < G; g += CONSUMER_WARPS) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = lane * 4 + j;
+      acc += __bfloat162float(L.nq[g * HEAD_DIM + d]) * L.nk[d];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) L.ns[g] = acc;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// Warp 0 folds the new token (one extra key, kept in shared memory) into its running softmax.
+ACP_DEVINL void fold_new_token(WarpState& st, const SmemLayout& L, int G, float sl2e, int lane) {
+  const int r_lo = lane >> 2;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int row = r_lo + hh * 8;
+    if (row < G) {
+      const float s = L.ns[row];
+      const float mn = fmaxf(st.m[hh], s);
+      const float corr = (st.m[hh] == -INFINITY) ? 0.f : exp2f((st.m[hh] - mn) * sl2e);
+      const float p = exp2f((s - mn) * sl2e);
+      st.m[hh] = mn;
+      st.l[hh] = st.l[hh] * corr + (((lane & 3) == 0) ? p : 0.f);  // l is quad-reduced later
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const int dim = d * 8 + 2 * (lane & 3);
+        st.o[d][hh * 2] = st.o[d][hh * 2] * corr + p * L.nv[dim];
+        st.o[d][hh * 2 + 1] = st.o[d][hh * 2 + 1] * corr + p * L.nv[dim + 1];
+      }
+    }
+  }
+}
 
 // =================================================================================
 // decode, chunked: CTA = (sequence, kv head, chunk of ATTN_CHUNK_TILES tiles).  The chunk
@@ -253,10 +362,12 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   const long long r = f - (long long)a.chunk_cum[b] * a.kv_heads;
   const int kh = (int)(r / nc), chunk = (int)(r % nc);
   const int ctx = a.ctx_len[b];
+  // keys 0..ctx-2 are in the cache; the new token (position ctx-1) is handled from shared memory
   const int tile_begin = chunk * ATTN_CHUNK_TILES;
-  const int tok_end = min(ctx, (chunk + 1) * ATTN_CHUNK_TILES * TILE_TOK);
-  const int tile_end = (tok_end + TILE_TOK - 1) / TILE_TOK;
+  const int tok_end = min(ctx - 1, (chunk + 1) * ATTN_CHUNK_TILES * TILE_TOK);
+  const int tile_end = max(tile_begin, (tok_end + TILE_TOK - 1) / TILE_TOK);
   const int n_tiles = tile_end - tile_begin;
+  const bool last_chunk = (chunk == nc - 1);
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -280,10 +391,10 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   const float sl2e = a.scale * 1.4426950408889634f;
   const int r_lo = lane >> 2;
   const int tok_off = warp * 16;
-  const __nv_bfloat16* qbase = a.q + (size_t)b * a.heads * HEAD_DIM + (size_t)kh * G * HEAD_DIM;
+  new_token_prologue(a, L, b, kh, ctx, last_chunk);  // q/k/v of the new token; K/V appended by the last chunk
   uint32_t qf[8][4];
-  load_q_frags(qf, r_lo < G ? qbase + r_lo * HEAD_DIM : nullptr,
-               r_lo + 8 < G ? qbase + (r_lo + 8) * HEAD_DIM : nullptr, lane);
+  load_q_frags(qf, r_lo < G ? L.nq + r_lo * HEAD_DIM : nullptr,
+               r_lo + 8 < G ? L.nq + (r_lo + 8) * HEAD_DIM : nullptr, lane);
   WarpState st;
 #pragma unroll
   for (int d = 0; d < 16; ++d) st.o[d][0] = st.o[d][1] = st.o[d][2] = st.o[d][3] = 0.f;
@@ -304,6 +415,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     __syncwarp();
     if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }
   }
+  if (last_chunk && warp == 0) fold_new_token(st, L, G, sl2e, lane);
   // per-warp partial (m, l, O) of this chunk -> workspace
   st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 1);
   st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 2);
@@ -365,7 +477,8 @@ attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = a.heads / a.kv_heads;
   const int ctx = a.ctx_len[b];
-  const int n_tiles = (ctx + TILE_TOK - 1) / TILE_TOK;
+  const int cached = ctx - 1;  // the new token (position ctx-1) is handled from shared memory
+  const int n_tiles = (cached + TILE_TOK - 1) / TILE_TOK;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -383,14 +496,14 @@ attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
   if (warp == CONSUMER_WARPS) {
     if (lane == 0)
       produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
-                    a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, ctx);
+                    a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, cached);
     return;
   }
   const int r_lo = lane >> 2;
-  const __nv_bfloat16* qbase = a.q + (size_t)b * a.heads * HEAD_DIM + (size_t)kh * G * HEAD_DIM;
+  new_token_prologue(a, L, b, kh, ctx, true);
   uint32_t qf[8][4];
-  load_q_frags(qf, r_lo < G ? qbase + r_lo * HEAD_DIM : nullptr,
-               r_lo + 8 < G ? qbase + (r_lo + 8) * HEAD_DIM : nullptr, lane);
+  load_q_frags(qf, r_lo < G ? L.nq + r_lo * HEAD_DIM : nullptr,
+               r_lo + 8 < G ? L.nq + (r_lo + 8) * HEAD_DIM : nullptr, lane);
   WarpState st;
 #pragma unroll
   for (int d = 0; d < 16; ++d) st.o[d][0] = st.o[d][1] = st.o[d][2] = st.o[d][3] = 0.f;
@@ -405,14 +518,15 @@ attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
     uint8_t* kt = L.stages + s * STAGE_BYTES;
     uint8_t* vt = kt + K_TILE_BYTES;
     const int tile_tok0 = it * TILE_TOK;
-    const int valid = ctx - tile_tok0;
+    const int valid = cached - tile_tok0;
     if (valid > tok_off) {
       if (valid < tok_off + 16) zero_v_tail(vt, valid, tok_off + 16, lane);
-      process_tile<2>(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_off, ctx, ctx, sl2e, lane);
+      process_tile<2>(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_off, cached, cached, sl2e, lane);
     }
     __syncwarp();
     if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }
   }
+  if (warp == 0) fold_new_token(st, L, G, sl2e, lane);
   // ---- merge the 4 warps through the (drained) ring, rows < G only ----
   st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 1);
   st.l[0] += __shfl_xor_sync(0xffffffffu, st.l[0], 2);

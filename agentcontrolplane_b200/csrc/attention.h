@@ -24,6 +24,16 @@ struct AttnDecodeArgs {
   int per_item;             // 1: whole item per CTA, no workspace / merge
   float scale;              // 1/sqrt(128)
   float* ws;                // partials [(item*max_chunks + chunk)*4 + warp][G rows][130] fp32
+  // Fused RoPE + KV append (decode): q/k/v of the NEW token come straight from the QKV GEMM result
+  // (split-K planes reduced here), are rotated in the kernel, K/V are appended to the cache by the
+  // CTA that owns the sequence's last chunk, and the new token is folded into the softmax from
+  // registers.  Replaces the rope_kv kernel on decode steps.
+  const void* qkv_ptr;      // GemmOut of the QKV projection: row b = [q heads | k heads | v heads]
+  int qkv_splits, qkv_n_cap, qkv_ld;
+  const float* cos_tab;     // [max_pos][64]
+  const float* sin_tab;
+  __nv_bfloat16* k_cache;   // this layer's caches (written)
+  __nv_bfloat16* v_cache;
 };
 
 struct AttnPrefillArgs {

@@ -451,12 +451,14 @@ int Model::forward(const StepInput& in) {
     Layer& L = layers_[l];
     GemmOut qkv, o, dn;
     PROF("gemm_qkv", gemm(L.m_qkv, m_xn_, qkv_l_, c.hidden, T, in.decode, &qkv));
-    RopeKvArgs ra;
-    ra.qkv = qkv; ra.pos = d_pos; ra.seq_of_row = d_seq; ra.page_table = d_pt;
-    ra.max_pages = lim_.max_pages_per_seq; ra.cos_tab = cos_; ra.sin_tab = sin_; ra.qbuf = qbuf_;
-    ra.k_cache = L.k_cache; ra.v_cache = L.v_cache; ra.T = T; ra.heads = heads_l_; ra.kv_heads = kvh_l_;
-    PROF("rope_kv", launch_rope_kv(ra, stream_));
-    ++launches_;
+    if (!in.decode) {
+      RopeKvArgs ra;
+      ra.qkv = qkv; ra.pos = d_pos; ra.seq_of_row = d_seq; ra.page_table = d_pt;
+      ra.max_pages = lim_.max_pages_per_seq; ra.cos_tab = cos_; ra.sin_tab = sin_; ra.qbuf = qbuf_;
+      ra.k_cache = L.k_cache; ra.v_cache = L.v_cache; ra.T = T; ra.heads = heads_l_; ra.kv_heads = kvh_l_;
+      PROF("rope_kv", launch_rope_kv(ra, stream_));
+      ++launches_;
+    }
     if (in.decode) {
       AttnDecodeArgs aa;
       aa.q = qbuf_; aa.out = attn_; aa.ctx_len = d_ctx; aa.chunk_cum = dev(in.tile_cum); aa.page_table = d_pt;
@@ -465,6 +467,9 @@ int Model::forward(const StepInput& in) {
       aa.total_chunks = in.tile_cum[in.B];   // host copy of the prefix sum (filled by the engine)
       aa.max_chunks = attn_max_chunks_;
       aa.scale = scale; aa.ws = attn_ws_;
+      // decode: RoPE + KV append are fused into the attention kernel (no rope_kv launch)
+      aa.qkv_ptr = qkv.ptr; aa.qkv_splits = qkv.splits; aa.qkv_n_cap = qkv.n_cap; aa.qkv_ld = qkv.ld;
+      aa.cos_tab = cos_; aa.sin_tab = sin_; aa.k_cache = L.k_cache; aa.v_cache = L.v_cache;
       // every item fits one chunk: one CTA per item writes the output directly (identical
       // arithmetic to chunked + merge for a single chunk, so the choice never changes results)
       aa.per_item = (aa.total_chunks == in.B) ? 1 : 0;
