@@ -119,3 +119,9 @@ def hostsim_run(config: dict[str, Any], engine=None) -> dict:
     h = engine._h if engine is not None else None
     _check(lib().acp_hostsim_run(h, json.dumps(config).encode(), ctypes.byref(buf)), "acp_hostsim_run")
     return json.loads(_take(buf))
+
+
+def hostsim_window_tokens(prompt_tokens: int, tools: int) -> int:
+    """Length of the context window hostsim builds for this target (a dry run with zero Tasks)."""
+    r = hostsim_run({"tasks": 0, "provider": "openai", "prompt_tokens": prompt_tokens, "tools": tools})
+    return int(r["prompt_tokens"])

@@ -214,6 +214,13 @@ def main():
     from agentcontrolplane_b200.engine import Engine
 
     n_tasks, plen, max_new = WORKLOAD["tasks"], WORKLOAD["prompt_tokens"], WORKLOAD["max_tokens"]
+    if WORKLOAD["tools"]:
+        # the synthetic tokenizer is byte-level: the agent's tool schemas render to more tokens than a BPE
+        # vocabulary would need, so the window can exceed the nominal length (never less work than configured)
+        probe = host.hostsim_window_tokens(plen, WORKLOAD["tools"])
+        if probe != plen:
+            WORKLOAD["name"] += f" [windows are {probe} tokens: tool schemas under the byte-level synthetic tokenizer]"
+            plen = probe
     pages_per_seq = (plen + max_new) // 32 + 2
     if WORKLOAD["tool_loop"]:
         pages_per_seq += 12   # second LLM step: window + tool call + tool result

@@ -252,3 +252,12 @@ def test_connection_refused_is_a_retryable_error():
     out = host.task_step({"op": "sendLLMRequest", "task": _task(), "tools": [],
                           "llm": {"provider": "openai", "model": "m", "baseURL": "http://127.0.0.1:9/v1"}})
     assert out["error"].startswith("model API call failed") and out["task"]["status"]["phase"] == "ReadyForLLM"
+
+
+def test_hostsim_window_sizing_reports_real_length():
+    """The synthetic window hits its token target exactly; when the agent's tool schemas alone exceed
+    it (byte-level synthetic tokenizer) the reported length is the real one, never a failure."""
+    assert host.hostsim_window_tokens(512, 0) == 512
+    assert host.hostsim_window_tokens(1024, 2) == 1024
+    small = host.hostsim_window_tokens(64, 2)
+    assert small > 64 and small == host.hostsim_window_tokens(1, 2)
