@@ -123,17 +123,8 @@ gemm_wx_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gr
             if (n < n_valid && m < args.M)
               out[(size_t)n * args.ld + m] = __float2bfloat16_rn(__uint_as_float(r[j]));
           }
-        } else {  // EPI_SWIGLU: rows interleaved (gate_j, up_j) -> adjacent lanes
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c + j;
-            const float v = bf16_round(__uint_as_float(r[j]));
-            const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((lane & 1) == 0 && n < n_valid && m < args.M) {
-              const float act = bf16_round(v / (1.0f + expf(-v)));
-              out[(size_t)n * args.ld + (m >> 1)] = __float2bfloat16_rn(act * other);
-            }
-          }
+        } else {  // EPI_SWIGLU
+          swiglu_store16(out, r, n0 + c, n_valid, m, args.M, args.ld, lane);
         }
       }
       tcgen05_fence_before();

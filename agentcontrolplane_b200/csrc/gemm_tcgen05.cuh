@@ -63,6 +63,28 @@ struct GemmCfg {
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
+// SwiGLU epilogue of 16 accumulator columns.  W rows are interleaved (gate_j, up_j), so the pair
+// of one output sits in adjacent TMEM lanes = adjacent threads.  The two threads split the 16
+// tokens: the even lane (gate) finishes the even tokens, the odd lane (up) the odd ones, so one
+// exchange serves two outputs and no lane idles through expf.
+__device__ __forceinline__ void swiglu_store16(__nv_bfloat16* out, const uint32_t (&r)[16], int n_base, int n_valid,
+                                               int m, int M, int ld, int lane) {
+  const bool odd = lane & 1;
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const float mine0 = bf16_round(__uint_as_float(r[j]));       // the GEMM's bf16 rounding point
+    const float mine1 = bf16_round(__uint_as_float(r[j + 1]));
+    const float got = __shfl_xor_sync(0xffffffffu, odd ? mine0 : mine1, 1);
+    const float g = odd ? got : mine0;     // odd lane: partner's gate of token j+1
+    const float u = odd ? mine1 : got;     // even lane: partner's up of token j
+    const int n = n_base + j + (odd ? 1 : 0);
+    if (n < n_valid && m < M) {
+      const float act = bf16_round(g / (1.0f + expf(-g)));
+      out[(size_t)n * ld + (m >> 1)] = __float2bfloat16_rn(act * u);
+    }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
@@ -201,17 +223,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       } else if constexpr (EPI == EPI_SWIGLU) {
         // W rows are stored interleaved: even row = gate_j, odd row = up_j (j = row / 2), so the
         // pair sits in adjacent TMEM lanes = adjacent threads of this warp.
-        __nv_bfloat16* out = (__nv_bfloat16*)args.out;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c + j;
-          const float v = bf16_round(__uint_as_float(r[j]));      // the GEMM's bf16 rounding point
-          const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-          if ((lane & 1) == 0 && n < n_valid && m < args.M) {
-            const float act = bf16_round(v / (1.0f + expf(-v)));
-            out[(size_t)n * args.ld + (m >> 1)] = __float2bfloat16_rn(act * other);
-          }
-        }
+        swiglu_store16((__nv_bfloat16*)args.out, r, n0 + c, n_valid, m, args.M, args.ld, lane);
       } else {  // EPI_ARGMAX
         float* out = (float*)args.out;
         float* red_v = (float*)(smem);  // ring buffers are idle now: reuse [4][16] floats + ints

@@ -177,11 +177,11 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int 
   if (env) lim_.splitk_target_ctas = atoi(env);
   env = getenv("ACP_FUSE_SWIGLU");
   fuse_swiglu_ = env && *env == '1';
-  // Fusing SwiGLU into the persistent prefill GEMM's epilogue measured SLOWER (1676 vs 1473 + 151 us
-  // per 8192-token layer): the expf/div epilogue outlasts the 17 us mainloop of a tile and paces the
-  // MMAs.  Off by default; ACP_FUSE_SWIGLU_PREFILL=1 to try.
+  // Prefill: SwiGLU runs in the persistent gate/up GEMM's epilogue (paired-lane exchange, hidden
+  // behind the next tile's mainloop by the double-buffered TMEM accumulator): A/B on one box
+  // 471 -> 450 ms per 32768 prompt tokens.  ACP_FUSE_SWIGLU_PREFILL=0 restores the separate kernel.
   env = getenv("ACP_FUSE_SWIGLU_PREFILL");
-  fuse_swiglu_prefill_ = env && *env == '1';
+  fuse_swiglu_prefill_ = !(env && *env == '0');
   ACP_CUDA_CHECK(cudaSetDevice(device));
   ACP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   ACP_TRY(tma_init());
@@ -494,9 +494,8 @@ int Model::forward(const StepInput& in) {
       ++launches_;
     }
     if (fuse_swiglu_ || (!in.decode && T > 256 && fuse_swiglu_prefill_)) {
-      // optional: SwiGLU in the GEMM epilogue (measured SLOWER on B200 with this non-persistent
-      // kernel: the expf/div epilogue is exposed at the end of every CTA; kept for the persistent
-      // kernel of a later round, ACP_FUSE_SWIGLU=1 to try it)
+      // SwiGLU in the GEMM epilogue.  Decode (non-persistent kernel, epilogue exposed at the end of
+      // every CTA) measured no gain, so it stays a separate kernel there unless ACP_FUSE_SWIGLU=1.
       GemmLaunch g;
       g.w = &L.m_gu.w; g.x = &m_xn_; g.M = 2 * ffn_l_; g.N = T; g.K = c.hidden; g.splits = 1;
       g.epi = EPI_SWIGLU; g.out = h_; g.ld = ffn_l_; g.n_cap = T;

@@ -18,6 +18,8 @@ cfg = {"model": model, "max_batch": max(64, n_req), "kv_pages": n_req * ((plen +
        "max_tokens_per_step": 8192, "max_pages_per_seq": max(32, (plen + max_new) // 32 + 2)}
 if len(sys.argv) > 5:
     cfg["layers"] = int(sys.argv[5])
+if os.environ.get("MTPS"):
+    cfg["max_tokens_per_step"] = int(os.environ["MTPS"])
 if os.environ.get("TP"):
     cfg["tp"] = int(os.environ["TP"])
 t0 = time.time()

@@ -158,3 +158,23 @@ def test_cancel_and_sampling(eng):
     a, b, c = run(1), run(1), run(2)
     assert len(a) >= 1
     assert a == b and isinstance(c, list)
+
+
+def test_1024_concurrent_task_reconciles_queue_and_complete():
+    """North-star scale: 1024 Task reconciles blocked in SendRequest at once against an engine whose
+    batch holds 256 sequences — the rest wait in the admission queue, are admitted as sequences
+    finish (continuous batching) and every Task reaches FinalAnswer with the same result as when only
+    32 workers feed the engine (digest independent of arrival order and batching)."""
+    e = Engine({"model": "tiny", "max_batch": 256, "kv_pages": 2048, "max_tokens_per_step": 4096,
+                "max_pages_per_seq": 16, "prefix_cache": False})
+    try:
+        cfg = {"tasks": 1024, "workers": 1024, "provider": "local", "model": "tiny", "max_tokens": 6,
+               "prompt_tokens": 120, "seed": 11}
+        big = host.hostsim_run(cfg, e)
+        s = e.stats()
+        assert big["reconciles"] == 1024 and big["final_phases"] == {"FinalAnswer": 1024}
+        assert s["decode_steps"] < 1024                      # batched, not one step per Task
+        small = host.hostsim_run(dict(cfg, workers=32), e)
+        assert small["digest"] == big["digest"]
+    finally:
+        e.close()
