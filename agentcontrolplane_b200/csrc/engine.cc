@@ -123,6 +123,19 @@ int Engine::init(const char* config_json) {
       }
       cudaSetDevice(device);
     }
+    if (const char* xb = getenv("ACP_TP_EXCHANGE_BENCH")) {  // dev: time the bare exchange (no GEMM)
+      const int iters = std::max(1, atoi(xb));
+      for (int T : {64, 256, 2048}) {
+        if (T > lim.max_tokens) continue;
+        std::vector<float> us(tp_, 0.f);
+        std::vector<std::thread> th;
+        for (int i = 0; i < tp_; ++i)
+          th.emplace_back([&, i] { (i == 0 ? &model_ : extra_[i - 1].get())->bench_exchange(T, iters, &us[i]); });
+        for (auto& t : th) t.join();
+        fprintf(stderr, "[acp_infer] tp=%d bare exchange (pull fp32 partials + residual + RMSNorm + push) T=%d: %.2f us\n",
+                tp_, T, us[0]);
+      }
+    }
     for (int i = 1; i < tp_; ++i) tp_threads_.emplace_back([this, i] { tp_worker(i - 1); });
   }
   cudaSetDevice(device);

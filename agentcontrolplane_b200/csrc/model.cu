@@ -394,7 +394,8 @@ int Model::gemm_rowpar(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, 
 // Row-parallel GEMM + the fused peer-memory exchange of tp_comm.cu:
 //   GEMM (fp32 partial planes) -> local split-K reduce -> barrier -> pull/reduce/residual/RMSNorm/
 //   push -> barrier.  x_ and xn_ are updated on EVERY rank by the rank that owns the row.
-int Model::rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool decode, const __nv_bfloat16* gain) {
+int Model::rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool decode, const __nv_bfloat16* gain,
+                        bool push_x) {
   const int M = cfg_.hidden;
   GemmLaunch g;
   g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
@@ -412,9 +413,35 @@ int Model::rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool d
   }
   const int epoch = tp_epoch_ + 1;
   tp_epoch_ += 2;
-  rc = launch_tp_reduce_norm(peers_, N, M, gain, cfg_.eps, epoch, tp_flags_ + TP_MAX, stream_);
+  rc = launch_tp_reduce_norm(peers_, N, M, gain, cfg_.eps, epoch, tp_flags_ + TP_MAX, push_x, stream_);
   if (rc == 0) rc = launch_tp_wait(peers_, epoch + 1, stream_);  // every rank's rows have landed here
   launches_ += 2;
+  return rc;
+}
+
+// Micro-benchmark of the bare exchange (no GEMM): every shard must call it with the same arguments.
+int Model::bench_exchange(int T, int iters, float* avg_us) {
+  if (!have_peers_ || T > lim_.max_tokens) return -1;
+  ACP_CUDA_CHECK(cudaSetDevice(device_));
+  cudaEvent_t a, b;
+  ACP_CUDA_CHECK(cudaEventCreate(&a));
+  ACP_CUDA_CHECK(cudaEventCreate(&b));
+  ACP_CUDA_CHECK(cudaMemsetAsync(ar_buf_, 0, (size_t)T * cfg_.hidden * sizeof(float), stream_));
+  int rc = 0;
+  for (int i = 0; i < iters + 10 && rc == 0; ++i) {
+    if (i == 10) cudaEventRecord(a, stream_);
+    const int epoch = tp_epoch_ + 1;
+    tp_epoch_ += 2;
+    rc = launch_tp_reduce_norm(peers_, T, cfg_.hidden, layers_[0].ffn_norm, cfg_.eps, epoch, tp_flags_ + TP_MAX, false, stream_);
+    if (rc == 0) rc = launch_tp_wait(peers_, epoch + 1, stream_);
+  }
+  cudaEventRecord(b, stream_);
+  ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  *avg_us = 1e3f * ms / (float)iters;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
   return rc;
 }
 
@@ -486,7 +513,7 @@ int Model::forward(const StepInput& in) {
       ++launches_;
     }
     if (tp_size_ > 1 && have_peers_) {
-      PROF("gemm_o+p2p_allreduce_norm", rowpar_fused(L.m_o, m_attn_, qdim_l_, T, in.decode, L.ffn_norm));
+      PROF("gemm_o+p2p_allreduce_norm", rowpar_fused(L.m_o, m_attn_, qdim_l_, T, in.decode, L.ffn_norm, false));
     } else {
       if (tp_size_ > 1) PROF("gemm_o_allreduce", gemm_rowpar(L.m_o, m_attn_, c.hidden, qdim_l_, T, in.decode, &o));
       else PROF("gemm_o", gemm(L.m_o, m_attn_, c.hidden, qdim_l_, T, in.decode, &o));
@@ -510,7 +537,7 @@ int Model::forward(const StepInput& in) {
     if (tp_size_ > 1 && have_peers_) {
       // fused exchange writes x_ and xn_ (with the next layer's gain; the last layer's xn_ is unused)
       const __nv_bfloat16* gain = (l + 1 < c.layers) ? layers_[l + 1].attn_norm : final_norm_;
-      PROF("gemm_down+p2p_allreduce_norm", rowpar_fused(L.m_down, m_h_, ffn_l_, T, in.decode, gain));
+      PROF("gemm_down+p2p_allreduce_norm", rowpar_fused(L.m_down, m_h_, ffn_l_, T, in.decode, gain, l + 1 == c.layers));
       if (l + 1 == c.layers) {
         GemmOut nothing;
         PROF("add_rmsnorm_final", launch_add_rmsnorm(x_, nothing, final_norm_, xs_, d_srows, in.n_sample, c.hidden, c.eps, stream_));

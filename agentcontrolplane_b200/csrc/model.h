@@ -82,6 +82,7 @@ class Model {
   // Runs one step on `stream()`: tokens for the n_sample rows land in host_tokens() after sync().
   int forward(const StepInput& in);
   int sync();
+  int bench_exchange(int T, int iters, float* avg_us);  // dev: bare peer-memory exchange, all shards together
   // Carves the pinned staging buffer for a step of T rows, B sequences, n_blocks prefill query
   // blocks; the engine fills the returned arrays, then calls forward(staging()).
   StepInput& stage_begin(int T, int B, int n_blocks);
@@ -131,7 +132,8 @@ class Model {
   bool have_peers_ = false;
   int* tp_flags_ = nullptr;
   int tp_epoch_ = 0;
-  int rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool decode, const __nv_bfloat16* gain);
+  int rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool decode, const __nv_bfloat16* gain,
+                   bool push_x);
 
   struct Layer {
     __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;

@@ -53,7 +53,7 @@ ACP_DEVINL float4 ld_f4(const float* p) {
 // Epochs: `epoch` = ready, `epoch + 1` = done; flags only grow.
 __global__ void __launch_bounds__(1024)
 tp_reduce_norm_kernel(TpPeers P, int T, int hidden, const __nv_bfloat16* __restrict__ gain, float eps,
-                      int epoch, int* done_ctr) {
+                      int epoch, int* done_ctr, int push_x) {
   extern __shared__ float row[];
   __shared__ float red[32];
   pdl_launch_dependents();
@@ -84,9 +84,15 @@ tp_reduce_norm_kernel(TpPeers P, int T, int hidden, const __nv_bfloat16* __restr
       uint2 packed;
       packed.x = pack_bf16x2(v[0], v[1]);
       packed.y = pack_bf16x2(v[2], v[3]);
+      // the residual row is only ever read again by its owner (the next exchange), so it stays
+      // local; the last layer pushes it everywhere because the sampler gathers arbitrary rows
+      if (push_x) {
 #pragma unroll
-      for (int p = 0; p < TP_MAX; ++p)   // push the new residual row to every rank
-        if (p < P.size) *reinterpret_cast<uint2*>(P.x[p] + off + i) = packed;
+        for (int p = 0; p < TP_MAX; ++p)
+          if (p < P.size) *reinterpret_cast<uint2*>(P.x[p] + off + i) = packed;
+      } else {
+        *reinterpret_cast<uint2*>(P.x[P.rank] + off + i) = packed;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) { row[i + j] = v[j]; ss += v[j] * v[j]; }
     }
@@ -129,13 +135,13 @@ int launch_tp_wait(const TpPeers& p, int epoch, cudaStream_t s) {
 }
 
 int launch_tp_reduce_norm(const TpPeers& p, int T, int hidden, const __nv_bfloat16* gain, float eps,
-                          int epoch, int* done_ctr, cudaStream_t s) {
+                          int epoch, int* done_ctr, bool push_x, cudaStream_t s) {
   if (T <= 0) return 0;
   const int rows_per = (T + p.size - 1) / p.size;
   int threads = ((hidden / 4 + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   cudaError_t e = acp_launch(tp_reduce_norm_kernel, dim3(rows_per), dim3(threads), hidden * sizeof(float), s, p,
-                             T, hidden, gain, eps, epoch, done_ctr);
+                             T, hidden, gain, eps, epoch, done_ctr, push_x ? 1 : 0);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] tp_reduce_norm launch: %s\n", cudaGetErrorString(e)); return -5; }
   return 0;
 }

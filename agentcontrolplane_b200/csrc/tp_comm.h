@@ -8,7 +8,8 @@
 // Rank r owns a contiguous block of token rows.  For its rows it LOADS the fp32 partial sums of
 // all ranks straight from their HBM over NVLink (reduce-scatter by pull, fixed rank order =>
 // deterministic and bit-identical on every rank), applies residual + RMSNorm in registers, and
-// STORES the new bf16 residual and normed rows into every rank's buffers (all-gather by push).
+// STORES the normed rows into every rank's buffers (all-gather by push); the new bf16 residual
+// stays with its owner except after the last layer (push_x), when the sampler needs any row.
 // The reduced fp32 activation never exists in HBM.  The flag handshakes (release/acquire at system
 // scope) live INSIDE the kernel: CTA 0 signals "partials ready", every CTA waits for all ranks, the
 // last CTA to finish signals "rows pushed"; a 1-warp wait kernel closes the exchange.  Replaces ncclAllReduce + add_rmsnorm of the NCCL baseline path.
@@ -29,7 +30,7 @@ struct TpPeers {
 
 // epoch = "partials ready", epoch + 1 = "rows pushed"; done_ctr: one zeroed int per rank
 int launch_tp_reduce_norm(const TpPeers& p, int T, int hidden, const __nv_bfloat16* gain, float eps,
-                          int epoch, int* done_ctr, cudaStream_t s);
+                          int epoch, int* done_ctr, bool push_x, cudaStream_t s);
 int launch_tp_wait(const TpPeers& p, int epoch, cudaStream_t s);
 
 }  // namespace acp

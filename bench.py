@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="dev only: truncate depth (result is then NOT a bench value)")
     ap.add_argument("--config", type=int, default=1, choices=sorted(WORKLOADS),
                     help="BASELINE.json config index (1 = default; 3 = 70B TP=8: run as ONE process on an 8-GPU box, --gpus 1)")
+    ap.add_argument("--max-tokens-per-step", type=int, default=8192, help="engine knob: token rows per prefill step")
     ap.add_argument("--tp", type=int, default=0, help="dev only: override the tensor-parallel degree of --config 3")
     args = ap.parse_args()
     WORKLOAD = dict(WORKLOADS[args.config])
@@ -224,7 +225,7 @@ def main():
     pages_per_seq = (plen + max_new) // 32 + 2
     if WORKLOAD["tool_loop"]:
         pages_per_seq += 12   # second LLM step: window + tool call + tool result
-    ecfg = {"model": args.model, "device": local_rank, "max_batch": max(64, n_tasks), "max_tokens_per_step": 8192,
+    ecfg = {"model": args.model, "device": local_rank, "max_batch": max(64, n_tasks), "max_tokens_per_step": args.max_tokens_per_step,
             "kv_pages": n_tasks * pages_per_seq * 2 + 8, "max_pages_per_seq": max(32, pages_per_seq), "tp": WORKLOAD["tp"],
             # config 1 measures cold Task steps: KV retention stays off so that no prefill work is skipped;
             # the tool loop of config 3 is exactly the case retention exists for (second turn of a Task)
