@@ -93,7 +93,7 @@ int Engine::init(const char* config_json) {
     // peer-memory exchange (default): every shard may load/store every other shard's buffers
     const std::string comm = cfg.get("tp_comm").as_string();
     if (comm != "nccl") {
-      bool ok = true;
+      bool ok = (tp_ == 2 || tp_ == 4 || tp_ == 8);  // the exchange kernel is instantiated for these
       for (int i = 0; i < tp_ && ok; ++i) {
         cudaSetDevice(devs[i]);
         for (int j = 0; j < tp_; ++j) {
@@ -125,16 +125,18 @@ int Engine::init(const char* config_json) {
     }
     if (const char* xb = getenv("ACP_TP_EXCHANGE_BENCH")) {  // dev: time the bare exchange (no GEMM)
       const int iters = std::max(1, atoi(xb));
-      for (int T : {64, 256, 2048}) {
-        if (T > lim.max_tokens) continue;
-        std::vector<float> us(tp_, 0.f);
-        std::vector<std::thread> th;
-        for (int i = 0; i < tp_; ++i)
-          th.emplace_back([&, i] { (i == 0 ? &model_ : extra_[i - 1].get())->bench_exchange(T, iters, &us[i]); });
-        for (auto& t : th) t.join();
-        fprintf(stderr, "[acp_infer] tp=%d bare exchange (pull fp32 partials + residual + RMSNorm + push) T=%d: %.2f us\n",
-                tp_, T, us[0]);
-      }
+      // diag bits (wrong results, timing only): 1 = volatile instead of .nc loads, 2 = no remote pushes,
+      // 4 = no remote pulls
+      for (int diag : {0, 1, 2, 4, 6})
+        for (int T : {64, 256, 2048}) {
+          if (T > lim.max_tokens) continue;
+          std::vector<float> us(tp_, 0.f);
+          std::vector<std::thread> th;
+          for (int i = 0; i < tp_; ++i)
+            th.emplace_back([&, i] { (i == 0 ? &model_ : extra_[i - 1].get())->bench_exchange(T, iters, &us[i], diag); });
+          for (auto& t : th) t.join();
+          fprintf(stderr, "[acp_infer] tp=%d bare exchange diag=%d T=%d: %.2f us\n", tp_, diag, T, us[0]);
+        }
     }
     for (int i = 1; i < tp_; ++i) tp_threads_.emplace_back([this, i] { tp_worker(i - 1); });
   }

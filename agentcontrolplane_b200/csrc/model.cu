@@ -414,13 +414,12 @@ int Model::rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool d
   const int epoch = tp_epoch_ + 1;
   tp_epoch_ += 2;
   rc = launch_tp_reduce_norm(peers_, N, M, gain, cfg_.eps, epoch, tp_flags_ + TP_MAX, push_x, stream_);
-  if (rc == 0) rc = launch_tp_wait(peers_, epoch + 1, stream_);  // every rank's rows have landed here
-  launches_ += 2;
+  ++launches_;  // the kernel itself waits until every rank's rows have landed here
   return rc;
 }
 
 // Micro-benchmark of the bare exchange (no GEMM): every shard must call it with the same arguments.
-int Model::bench_exchange(int T, int iters, float* avg_us) {
+int Model::bench_exchange(int T, int iters, float* avg_us, int diag) {
   if (!have_peers_ || T > lim_.max_tokens) return -1;
   ACP_CUDA_CHECK(cudaSetDevice(device_));
   cudaEvent_t a, b;
@@ -432,8 +431,7 @@ int Model::bench_exchange(int T, int iters, float* avg_us) {
     if (i == 10) cudaEventRecord(a, stream_);
     const int epoch = tp_epoch_ + 1;
     tp_epoch_ += 2;
-    rc = launch_tp_reduce_norm(peers_, T, cfg_.hidden, layers_[0].ffn_norm, cfg_.eps, epoch, tp_flags_ + TP_MAX, false, stream_);
-    if (rc == 0) rc = launch_tp_wait(peers_, epoch + 1, stream_);
+    rc = launch_tp_reduce_norm(peers_, T, cfg_.hidden, layers_[0].ffn_norm, cfg_.eps, epoch, tp_flags_ + TP_MAX, false, stream_, diag);
   }
   cudaEventRecord(b, stream_);
   ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));

@@ -82,7 +82,7 @@ class Model {
   // Runs one step on `stream()`: tokens for the n_sample rows land in host_tokens() after sync().
   int forward(const StepInput& in);
   int sync();
-  int bench_exchange(int T, int iters, float* avg_us);  // dev: bare peer-memory exchange, all shards together
+  int bench_exchange(int T, int iters, float* avg_us, int diag = 0);  // dev: bare peer-memory exchange, all shards together
   // Carves the pinned staging buffer for a step of T rows, B sequences, n_blocks prefill query
   // blocks; the engine fills the returned arrays, then calls forward(staging()).
   StepInput& stage_begin(int T, int B, int n_blocks);

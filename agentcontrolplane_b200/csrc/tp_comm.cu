@@ -16,10 +16,8 @@ ACP_DEVINL int ld_acquire_sys(const int* p) {
 }
 
 ACP_DEVINL void tp_signal(const TpPeers& P, int lane, int epoch) {  // lanes 0..size-1 of one warp
-  if (lane < P.size) {
-    __threadfence_system();
-    st_release_sys(P.flags[lane] + P.rank, epoch);
-  }
+  // st.release.sys is itself a system-scope fence followed by the store (one MEMBAR.SYS, not two)
+  if (lane < P.size) st_release_sys(P.flags[lane] + P.rank, epoch);
 }
 ACP_DEVINL void tp_wait_all(const TpPeers& P, int lane, int epoch) {  // lanes 0..size-1 of one warp
   if (lane < P.size) {
@@ -33,14 +31,12 @@ ACP_DEVINL void tp_wait_all(const TpPeers& P, int lane, int epoch) {  // lanes 0
   }
 }
 
-// wait-only kernel: every rank's rows have landed in this rank's x / xn
-__global__ void __launch_bounds__(32)
-tp_wait_kernel(TpPeers P, int epoch) {
-  pdl_launch_dependents();
-  pdl_wait();
-  tp_wait_all(P, threadIdx.x, epoch);
+ACP_DEVINL float4 ld_f4_volatile(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
 }
-
 ACP_DEVINL float4 ld_f4(const float* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -49,11 +45,14 @@ ACP_DEVINL float4 ld_f4(const float* p) {
 }
 
 // One kernel: [signal "my partial sums are complete"] -> [wait for every rank] -> pull + reduce +
-// residual + RMSNorm + push for the rows this rank owns -> [last CTA signals "my rows are pushed"].
+// residual + RMSNorm + push for the rows this rank owns -> [last CTA signals "my rows are pushed"]
+// -> [CTA 0 waits for every rank's "pushed"], so grid completion == exchange complete.
 // Epochs: `epoch` = ready, `epoch + 1` = done; flags only grow.
+// NP = number of ranks (compile time: no redundant pulls, every loop fully unrolled)
+template <int NP>
 __global__ void __launch_bounds__(1024)
 tp_reduce_norm_kernel(TpPeers P, int T, int hidden, const __nv_bfloat16* __restrict__ gain, float eps,
-                      int epoch, int* done_ctr, int push_x) {
+                      int epoch, int* done_ctr, int push_x, int diag) {
   extern __shared__ float row[];
   __shared__ float red[32];
   pdl_launch_dependents();
@@ -68,13 +67,15 @@ tp_reduce_norm_kernel(TpPeers P, int T, int hidden, const __nv_bfloat16* __restr
     float ss = 0.f;
     for (int i = threadIdx.x * 4; i < hidden; i += blockDim.x * 4) {
       // pull the partial sums of every rank (all loads in flight together), add in rank order
-      float4 q[TP_MAX];
+      float4 q[NP];
 #pragma unroll
-      for (int p = 0; p < TP_MAX; ++p) q[p] = ld_f4(P.ar[p < P.size ? p : P.size - 1] + off + i);
+      for (int p = 0; p < NP; ++p) {
+        const int src = (diag & 4) ? P.rank : p;   // diag 4: no remote pulls
+        q[p] = (diag & 1) ? ld_f4_volatile(P.ar[src] + off + i) : ld_f4(P.ar[src] + off + i);
+      }
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int p = 0; p < TP_MAX; ++p)
-        if (p < P.size) { acc.x += q[p].x; acc.y += q[p].y; acc.z += q[p].z; acc.w += q[p].w; }
+      for (int p = 0; p < NP; ++p) { acc.x += q[p].x; acc.y += q[p].y; acc.z += q[p].z; acc.w += q[p].w; }
       const uint2 raw = *reinterpret_cast<const uint2*>(P.x[P.rank] + off + i);
       float v[4] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y)};
       v[0] = bf16_round(v[0] + bf16_round(acc.x));
@@ -88,8 +89,7 @@ tp_reduce_norm_kernel(TpPeers P, int T, int hidden, const __nv_bfloat16* __restr
       // local; the last layer pushes it everywhere because the sampler gathers arbitrary rows
       if (push_x) {
 #pragma unroll
-        for (int p = 0; p < TP_MAX; ++p)
-          if (p < P.size) *reinterpret_cast<uint2*>(P.x[p] + off + i) = packed;
+        for (int p = 0; p < NP; ++p) *reinterpret_cast<uint2*>(P.x[p] + off + i) = packed;
       } else {
         *reinterpret_cast<uint2*>(P.x[P.rank] + off + i) = packed;
       }
@@ -109,39 +109,47 @@ tp_reduce_norm_kernel(TpPeers P, int T, int hidden, const __nv_bfloat16* __restr
       packed.x = pack_bf16x2(g[0] * bf16_round(row[i] * rstd), g[1] * bf16_round(row[i + 1] * rstd));
       packed.y = pack_bf16x2(g[2] * bf16_round(row[i + 2] * rstd), g[3] * bf16_round(row[i + 3] * rstd));
 #pragma unroll
-      for (int p = 0; p < TP_MAX; ++p)
-        if (p < P.size) *reinterpret_cast<uint2*>(P.xn[p] + off + i) = packed;
+      for (int p = 0; p < NP; ++p)
+        if (!(diag & 2) || p == P.rank) *reinterpret_cast<uint2*>(P.xn[p] + off + i) = packed;  // diag 2: no remote pushes
     }
   }
-  // the last CTA of this rank to finish its pushes tells every rank "my rows have landed"
+  // The last CTA of this rank to finish its pushes tells every rank "my rows have landed".  Each
+  // CTA publishes its stores at DEVICE scope (fence + counter atomic); only the last one pays for
+  // the system-scope release — a MEMBAR.SYS per CTA serialises in L2 and made the exchange cost
+  // 0.1 us per row.  Causality: pushes -> fence.gpu/atomic -> last CTA's atomic -> st.release.sys
+  // -> peer's ld.acquire.sys, every link morally strong.
   __syncthreads();
   __shared__ int is_last;
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence();
     const int old = atomicAdd(done_ctr, 1);
     is_last = (old == (int)gridDim.x - 1);
-    if (is_last) *done_ctr = 0;
+    if (is_last) { __threadfence(); *done_ctr = 0; }
   }
   __syncthreads();
   if (is_last && threadIdx.x < 32) tp_signal(P, threadIdx.x, epoch + 1);
+  // CTA 0 closes the exchange: the grid (and with it the dependent GEMM's griddepcontrol.wait)
+  // completes only when every rank's rows have landed in this rank's buffers.
+  if (blockIdx.x == 0 && threadIdx.x < 32) tp_wait_all(P, threadIdx.x, epoch + 1);
 }
 
 }  // namespace
 
-int launch_tp_wait(const TpPeers& p, int epoch, cudaStream_t s) {
-  cudaError_t e = acp_launch(tp_wait_kernel, dim3(1), dim3(32), 0, s, p, epoch);
-  if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] tp_wait launch: %s\n", cudaGetErrorString(e)); return -5; }
-  return 0;
-}
-
 int launch_tp_reduce_norm(const TpPeers& p, int T, int hidden, const __nv_bfloat16* gain, float eps,
-                          int epoch, int* done_ctr, bool push_x, cudaStream_t s) {
+                          int epoch, int* done_ctr, bool push_x, cudaStream_t s, int diag) {
   if (T <= 0) return 0;
   const int rows_per = (T + p.size - 1) / p.size;
   int threads = ((hidden / 4 + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
-  cudaError_t e = acp_launch(tp_reduce_norm_kernel, dim3(rows_per), dim3(threads), hidden * sizeof(float), s, p,
-                             T, hidden, gain, eps, epoch, done_ctr, push_x ? 1 : 0);
+  cudaError_t e;
+  const size_t smem = hidden * sizeof(float);
+  const int px = push_x ? 1 : 0;
+  switch (p.size) {
+    case 2: e = acp_launch(tp_reduce_norm_kernel<2>, dim3(rows_per), dim3(threads), smem, s, p, T, hidden, gain, eps, epoch, done_ctr, px, diag); break;
+    case 4: e = acp_launch(tp_reduce_norm_kernel<4>, dim3(rows_per), dim3(threads), smem, s, p, T, hidden, gain, eps, epoch, done_ctr, px, diag); break;
+    case 8: e = acp_launch(tp_reduce_norm_kernel<8>, dim3(rows_per), dim3(threads), smem, s, p, T, hidden, gain, eps, epoch, done_ctr, px, diag); break;
+    default: fprintf(stderr, "[acp_infer] tp exchange supports 2, 4 or 8 ranks (got %d)\n", p.size); return -1;
+  }
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] tp_reduce_norm launch: %s\n", cudaGetErrorString(e)); return -5; }
   return 0;
 }

@@ -12,7 +12,7 @@
 // stays with its owner except after the last layer (push_x), when the sampler needs any row.
 // The reduced fp32 activation never exists in HBM.  The flag handshakes (release/acquire at system
 // scope) live INSIDE the kernel: CTA 0 signals "partials ready", every CTA waits for all ranks, the
-// last CTA to finish signals "rows pushed"; a 1-warp wait kernel closes the exchange.  Replaces ncclAllReduce + add_rmsnorm of the NCCL baseline path.
+// last CTA to finish signals "rows pushed" and CTA 0 waits for every rank's "rows pushed" before the grid completes.  Replaces ncclAllReduce + add_rmsnorm of the NCCL baseline path.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -30,7 +30,6 @@ struct TpPeers {
 
 // epoch = "partials ready", epoch + 1 = "rows pushed"; done_ctr: one zeroed int per rank
 int launch_tp_reduce_norm(const TpPeers& p, int T, int hidden, const __nv_bfloat16* gain, float eps,
-                          int epoch, int* done_ctr, bool push_x, cudaStream_t s);
-int launch_tp_wait(const TpPeers& p, int epoch, cudaStream_t s);
+                          int epoch, int* done_ctr, bool push_x, cudaStream_t s, int diag = 0);  // diag: bench only
 
 }  // namespace acp
