@@ -22,16 +22,29 @@ int Engine::init(const char* config_json) {
   }
   ModelConfig mc;
   std::string name = cfg.get("model").as_string();
-  if (name.empty()) name = "tiny";
-  if (!model_preset(name, &mc)) {
-    fprintf(stderr, "[acp_infer] unknown model preset '%s'\n", name.c_str());
-    return -1;
-  }
   const std::string weights = cfg.get("weights").as_string();
   if (!weights.empty() && weights != "synthetic") {
-    fprintf(stderr, "[acp_infer] weights='%s' not supported: only 'synthetic' (no checkpoints in this image)\n",
-            weights.c_str());
-    return -1;
+    // a HuggingFace Llama checkpoint directory (config.json + safetensors); "model" is then only
+    // the name requests must carry (LLM.spec.parameters.model), default = the directory name
+    std::string err;
+    ckpt_.reset(new Checkpoint());
+    if (!ckpt_->open(weights, &err)) { fprintf(stderr, "[acp_infer] weights: %s\n", err.c_str()); return -1; }
+    if (!ckpt_->has_config()) { fprintf(stderr, "[acp_infer] weights: no config.json in %s\n", ckpt_->dir().c_str()); return -1; }
+    if (!model_config_from_hf(ckpt_->config(), &mc, &err)) { fprintf(stderr, "[acp_infer] weights: %s\n", err.c_str()); return -1; }
+    if (name.empty()) {
+      const std::string& d = ckpt_->dir();
+      const size_t e = d.find_last_not_of('/');
+      const size_t b = d.find_last_of('/', e);
+      name = d.substr(b == std::string::npos ? 0 : b + 1, e == std::string::npos ? std::string::npos : e - (b == std::string::npos ? 0 : b + 1) + 1);
+      if (name.empty()) name = "checkpoint";
+    }
+    mc.name = name;
+  } else {
+    if (name.empty()) name = "tiny";
+    if (!model_preset(name, &mc)) {
+      fprintf(stderr, "[acp_infer] unknown model preset '%s'\n", name.c_str());
+      return -1;
+    }
   }
   if (cfg.find("seed")) mc.seed = (uint64_t)cfg.get("seed").as_int((long long)mc.seed);
   if (cfg.find("layers")) mc.layers = (int)cfg.get("layers").as_int(mc.layers);  // truncated-depth runs
@@ -68,7 +81,7 @@ int Engine::init(const char* config_json) {
   }
   int rc = 0;
   if (tp_ == 1) {
-    rc = model_.init(mc, lim, device);
+    rc = model_.init(mc, lim, device, 0, 1, nullptr, nullptr, ckpt_.get());
     if (rc != 0) return rc;
   } else {
     // tensor parallel inside ONE process: a communicator and a host thread per GPU
@@ -86,7 +99,7 @@ int Engine::init(const char* config_json) {
     for (int i = 0; i < tp_; ++i)
       inits.emplace_back([&, i] {
         Model* m = i == 0 ? &model_ : extra_[i - 1].get();
-        rcs[i] = m->init(mc, lim, devs[i], i, tp_, comms_[i], i == 0 ? nullptr : &model_);
+        rcs[i] = m->init(mc, lim, devs[i], i, tp_, comms_[i], i == 0 ? nullptr : &model_, ckpt_.get());
       });
     for (auto& t : inits) t.join();
     for (int r : rcs) if (r != 0) return r;
@@ -144,6 +157,7 @@ int Engine::init(const char* config_json) {
   if (cudaEventCreate(&ev0_) != cudaSuccess || cudaEventCreate(&ev1_) != cudaSuccess) return -5;
   max_ctx_tokens_ = std::min(lim.max_pages_per_seq * KV_PAGE, mc.max_pos);
   for (int p = lim.num_pages - 1; p >= 1; --p) free_pages_.push_back(p);  // page 0 reserved
+  ckpt_.reset();  // weights are in HBM: drop the file mappings
   thread_ = std::thread([this] { run(); });
   return 0;
 }

@@ -16,6 +16,7 @@
 #include <vector>
 #include "chat.h"
 #include "model.h"
+#include "safetensors.h"
 
 namespace acp {
 
@@ -85,6 +86,7 @@ class Engine {
   int run_forward(const StepInput& in);
   void tp_worker(int idx);
 
+  std::unique_ptr<Checkpoint> ckpt_;             // "weights": <dir> — mmap'ed until the shards are loaded
   Model model_;                                  // shard 0 (the only one when tp == 1)
   std::vector<std::unique_ptr<Model>> extra_;    // tensor-parallel shards 1..tp-1, one GPU each
   std::vector<NcclComm> comms_;

@@ -12,6 +12,8 @@
 #include <chrono>
 #include <thread>
 #include "../chat.h"
+#include "../model.h"
+#include "../safetensors.h"
 #include "task.h"
 
 using namespace acp;
@@ -354,6 +356,37 @@ static std::string synth_text(uint64_t seed, int task, int n) {
   for (int i = 0; i < n; ++i)
     s.push_back(alphabet[mix64(seed * 1000003ull + (uint64_t)task * 7919ull + (uint64_t)i) % 30]);
   return s;
+}
+
+extern "C" int acp_host_checkpoint_index(const char* path, char** out_json) {
+  if (!path || !out_json) return ACP_ERR_INVALID;
+  acp::Checkpoint ck;
+  std::string err;
+  auto fail = [&](const std::string& e) {
+    Json j = Json::object();
+    j.set("error", Json(e));
+    ret_json(j, out_json);
+    return ACP_ERR_INVALID;
+  };
+  if (!ck.open(path, &err)) return fail(err);
+  Json out;
+  std::string perr;
+  if (!Json::parse(ck.index_json(), &out, &perr)) return fail(perr);
+  if (!ck.has_config()) return fail("no config.json in " + ck.dir());
+  acp::ModelConfig mc;
+  if (!acp::model_config_from_hf(ck.config(), &mc, &err)) return fail(err);
+  Json m = Json::object();
+  m.set("hidden", Json(mc.hidden)); m.set("layers", Json(mc.layers)); m.set("heads", Json(mc.heads));
+  m.set("kv_heads", Json(mc.kv_heads)); m.set("ffn", Json(mc.ffn)); m.set("vocab", Json(mc.vocab));
+  m.set("rope_theta", Json(mc.rope_theta)); m.set("eps", Json((double)mc.eps));
+  m.set("tied_embeddings", Json(mc.tied_embeddings)); m.set("max_pos", Json(mc.max_pos));
+  float inv[64];
+  acp::rope_inv_freq(mc, inv);
+  Json fr = Json::array();
+  for (float f : inv) fr.push(Json((double)f));
+  m.set("rope_inv_freq", fr);
+  out.set("model", m);
+  return ret_json(out, out_json);
 }
 
 extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char** result_json_out) {

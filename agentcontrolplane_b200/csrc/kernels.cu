@@ -464,28 +464,30 @@ int launch_sample(const float* logits, int V, int N, const SampleParams* params_
 // ---------------------------------------------------------------------------------
 // Local element i of a (possibly tiled / interleaved / sharded) tensor -> index in the logical
 // row-major tensor whose values oracle/synth.py defines.
+__device__ __forceinline__ size_t synth_logical_index(size_t i, const SynthMap& mp) {
+  if (mp.local_cols <= 1) return i;
+  // storage is tiled: [m_tile][kb][128 rows][64 cols]  ->  local (row, col) of element i
+  const size_t nkb = (size_t)mp.local_cols / 64;
+  const size_t tile = i / 8192, in_tile = i % 8192;
+  const size_t r = (tile / nkb) * 128 + in_tile / 64, c = (tile % nkb) * 64 + in_tile % 64;
+  size_t lr;
+  if (mp.interleave_half > 0) {
+    lr = (size_t)mp.seg_global[r & 1] + (r >> 1);
+  } else {
+    size_t rr = r;
+    int sg = 0;
+    while (sg + 1 < mp.nseg && rr >= (size_t)mp.seg_rows[sg]) { rr -= (size_t)mp.seg_rows[sg]; ++sg; }
+    lr = (size_t)mp.seg_global[sg] + rr;
+  }
+  return lr * (size_t)mp.logical_cols + (size_t)mp.col0 + c;
+}
+
 __global__ void synth_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n, uint64_t base,
                                     float scale, int plus_one, SynthMap mp) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    size_t li = i;
-    if (mp.local_cols > 1) {
-      // storage is tiled: [m_tile][kb][128 rows][64 cols]  ->  local (row, col) of element i
-      const size_t nkb = (size_t)mp.local_cols / 64;
-      const size_t tile = i / 8192, in_tile = i % 8192;
-      const size_t r = (tile / nkb) * 128 + in_tile / 64, c = (tile % nkb) * 64 + in_tile % 64;
-      size_t lr;
-      if (mp.interleave_half > 0) {
-        lr = (size_t)mp.seg_global[r & 1] + (r >> 1);
-      } else {
-        size_t rr = r;
-        int sg = 0;
-        while (sg + 1 < mp.nseg && rr >= (size_t)mp.seg_rows[sg]) { rr -= (size_t)mp.seg_rows[sg]; ++sg; }
-        lr = (size_t)mp.seg_global[sg] + rr;
-      }
-      li = lr * (size_t)mp.logical_cols + (size_t)mp.col0 + c;
-    }
+    const size_t li = synth_logical_index(i, mp);
     const uint64_t z = splitmix64(base + (uint64_t)li * 0xD1B54A32D192ED03ull);
     const int s = (int)(z & 0xffff) + (int)((z >> 16) & 0xffff) + (int)((z >> 32) & 0xffff) +
                   (int)(z >> 48) - 131070;
@@ -494,6 +496,24 @@ __global__ void synth_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n, u
     out[i] = __float2bfloat16_rn(w);
   }
 }
+
+// Checkpoint weights: `src` holds the logical row-major tensor (or the part of it that starts at
+// logical element `src_elem0`); every local element fetches its value through the same map the
+// synthetic generator uses, so tiling / interleaving / sharding are defined in ONE place.
+__global__ void gather_weight_kernel(__nv_bfloat16* __restrict__ out, size_t n,
+                                     const __nv_bfloat16* __restrict__ src, size_t src_elem0, SynthMap mp) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = src[synth_logical_index(i, mp) - src_elem0];
+}
+int launch_gather_weight(__nv_bfloat16* out, size_t n, const __nv_bfloat16* src, size_t src_elem0,
+                         cudaStream_t s, const SynthMap& map) {
+  if (n == 0) return 0;
+  gather_weight_kernel<<<148 * 8, 256, 0, s>>>(out, n, src, src_elem0, map);
+  ACP_LAUNCH_CHECK("gather_weight");
+  return 0;
+}
+
 int launch_synth(__nv_bfloat16* out, size_t n, uint64_t seed, uint32_t tid, double std,
                  int plus_one, cudaStream_t s, const SynthMap& map) {
   if (n == 0) return 0;

@@ -79,6 +79,11 @@ struct SynthMap {
 int launch_synth(__nv_bfloat16* out, size_t n, uint64_t seed, uint32_t tid, double std,
                  int plus_one, cudaStream_t s, const SynthMap& map = SynthMap());
 
+// out[i] = src[logical_index(i) - src_elem0]: places a row-major checkpoint tensor (staged on the
+// device) into the tiled / interleaved / sharded weight layout described by `map`
+int launch_gather_weight(__nv_bfloat16* out, size_t n, const __nv_bfloat16* src, size_t src_elem0,
+                         cudaStream_t s, const SynthMap& map);
+
 // out[i] = sum_s planes[s][i] (index order), fp32 -> fp32: local split-K reduction in front of a
 // tensor-parallel all-reduce
 int launch_reduce_planes(const float* planes, int splits, size_t plane_elems, float* out, cudaStream_t s);

@@ -8,6 +8,7 @@
 // the consumer kernels; prefill steps write bf16 directly.  bf16 rounding points are exactly the
 // ones listed in oracle/llama_oracle.py.
 #include "model.h"
+#include "safetensors.h"
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
 #include <math.h>
@@ -148,7 +149,7 @@ int Model::choose_splits(int M, int K, int N) const {
 }
 
 int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int tp_rank, int tp_size,
-                NcclComm comm, Model* lead) {
+                NcclComm comm, Model* lead, const Checkpoint* ckpt) {
   cfg_ = cfg;
   lim_ = lim;
   device_ = device;
@@ -188,7 +189,9 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int 
   ACP_TRY(gemm_setup_attributes());
   ACP_TRY(attn_setup_attributes());
   ACP_TRY(alloc_all());
-  ACP_TRY(gen_weights());
+  if (ckpt) ACP_TRY(load_weights(*ckpt));
+  else ACP_TRY(gen_weights());
+  ACP_TRY(build_rope_tables());
   ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
   return 0;
 }
@@ -315,10 +318,34 @@ int Model::gen_weights() {
     ACP_TRY(launch_synth(L.attn_norm, H, c.seed, base + 4, 0.1, 1, stream_));
     ACP_TRY(launch_synth(L.ffn_norm, H, c.seed, base + 5, 0.1, 1, stream_));
   }
-  // RoPE tables: same recipe as oracle/llama_oracle.py rope_tables()
+  return 0;
+}
+
+void rope_inv_freq(const ModelConfig& c, float* inv64) {
+  const double kTwoPi = 6.283185307179586476925286766559;
+  for (int i = 0; i < 64; ++i) {
+    double f = pow(c.rope_theta, -(2.0 * i) / (double)HEAD_DIM);
+    if (c.rope_factor > 0.0) {  // Llama-3.1 "llama3" scaling: long wavelengths slowed by `factor`
+      const double wavelen = kTwoPi / f;
+      const double low_wl = (double)c.rope_orig_max_pos / c.rope_low_freq;
+      const double high_wl = (double)c.rope_orig_max_pos / c.rope_high_freq;
+      if (wavelen > low_wl) {
+        f = f / c.rope_factor;
+      } else if (!(wavelen < high_wl)) {
+        const double smooth = ((double)c.rope_orig_max_pos / wavelen - c.rope_low_freq) / (c.rope_high_freq - c.rope_low_freq);
+        f = (1.0 - smooth) * f / c.rope_factor + smooth * f;
+      }
+    }
+    inv64[i] = (float)f;
+  }
+}
+
+// RoPE tables: same recipe as oracle/llama_oracle.py rope_tables()
+int Model::build_rope_tables() {
+  const ModelConfig& c = cfg_;
   std::vector<float> hc((size_t)c.max_pos * 64), hs((size_t)c.max_pos * 64);
   float inv[64];
-  for (int i = 0; i < 64; ++i) inv[i] = (float)pow(c.rope_theta, -(2.0 * i) / (double)HEAD_DIM);
+  rope_inv_freq(c, inv);
   for (int p = 0; p < c.max_pos; ++p)
     for (int i = 0; i < 64; ++i) {
       const float ang = (float)p * inv[i];
@@ -329,6 +356,152 @@ int Model::gen_weights() {
   ACP_CUDA_CHECK(cudaMemcpyAsync(sin_, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, stream_));
   ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
   return 0;
+}
+
+bool model_config_from_hf(const Json& hf, ModelConfig* out, std::string* err) {
+  ModelConfig m;
+  auto need = [&](const char* key, int* v) {
+    const Json* j = hf.find(key);
+    if (!j || !j->is_number()) { *err = std::string("config.json: missing ") + key; return false; }
+    *v = (int)j->as_int();
+    return true;
+  };
+  const std::string mt = hf.get("model_type").as_string();
+  if (!mt.empty() && mt != "llama") { *err = "config.json: model_type \"" + mt + "\" is not supported (llama only)"; return false; }
+  if (!need("hidden_size", &m.hidden) || !need("num_hidden_layers", &m.layers) ||
+      !need("num_attention_heads", &m.heads) || !need("intermediate_size", &m.ffn) || !need("vocab_size", &m.vocab))
+    return false;
+  m.kv_heads = (int)hf.get("num_key_value_heads").as_int(m.heads);
+  const int head_dim = (int)hf.get("head_dim").as_int(m.heads > 0 ? m.hidden / m.heads : 0);
+  if (head_dim != HEAD_DIM) { *err = "config.json: head_dim " + std::to_string(head_dim) + " (this engine is built for 128)"; return false; }
+  if (m.kv_heads <= 0 || m.heads % m.kv_heads || m.heads / m.kv_heads > 16 || 16 % (m.heads / m.kv_heads)) {
+    *err = "config.json: unsupported attention head grouping";
+    return false;
+  }
+  if (m.hidden % 128 || m.ffn % 64 || m.vocab % 128) { *err = "config.json: hidden/ffn/vocab must be multiples of 128/64/128"; return false; }
+  if (hf.get("attention_bias").as_bool(false) || hf.get("mlp_bias").as_bool(false)) { *err = "config.json: biased projections are not supported"; return false; }
+  const std::string act = hf.get("hidden_act").as_string();
+  if (!act.empty() && act != "silu") { *err = "config.json: hidden_act must be silu"; return false; }
+  m.rope_theta = hf.get("rope_theta").as_double(10000.0);
+  m.eps = (float)hf.get("rms_norm_eps").as_double(1e-5);
+  m.tied_embeddings = hf.get("tie_word_embeddings").as_bool(false);
+  const int mp = (int)hf.get("max_position_embeddings").as_int(8192);
+  m.max_pos = mp < 8192 ? mp : 8192;   // table size; contexts are bounded by the KV page budget anyway
+  const Json& rs = hf.get("rope_scaling");
+  if (rs.is_object()) {
+    std::string type = rs.get("rope_type").as_string();
+    if (type.empty()) type = rs.get("type").as_string();
+    if (type == "llama3") {
+      m.rope_factor = rs.get("factor").as_double(8.0);
+      m.rope_low_freq = rs.get("low_freq_factor").as_double(1.0);
+      m.rope_high_freq = rs.get("high_freq_factor").as_double(4.0);
+      m.rope_orig_max_pos = (int)rs.get("original_max_position_embeddings").as_int(8192);
+    } else if (!type.empty() && type != "default") {
+      *err = "config.json: rope_scaling type \"" + type + "\" is not supported";
+      return false;
+    }
+  }
+  m.name = "checkpoint";
+  *out = m;
+  return true;
+}
+
+// HuggingFace Llama checkpoint -> this shard's tiled weights.  Every logical tensor ([q;k;v],
+// o_proj, [gate;up], down_proj, lm_head rows of this shard) is staged row-major on the device and
+// placed by gather_weight_kernel through the SAME SynthMap the synthetic generator uses.
+int Model::load_weights(const Checkpoint& ck) {
+  const ModelConfig& c = cfg_;
+  const size_t H = c.hidden;
+  const int r = tp_rank_;
+  size_t stage_elems = (size_t)c.qkv_dim() * H;
+  if ((size_t)2 * c.ffn * H > stage_elems) stage_elems = (size_t)2 * c.ffn * H;
+  if ((size_t)lm_rows_l_ * H > stage_elems) stage_elems = (size_t)lm_rows_l_ * H;
+  __nv_bfloat16* stage = nullptr;
+  ACP_CUDA_CHECK(cudaMalloc((void**)&stage, stage_elems * sizeof(__nv_bfloat16)));
+  std::vector<uint16_t> conv;  // host conversion buffer for F16/F32 checkpoints
+  struct Part { std::string name; int64_t rows, cols; int64_t row0, nrows; };
+  int rc = 0;
+  // copies rows [row0, row0+nrows) of a [rows][cols] tensor to dst (device, bf16)
+  auto upload = [&](const Part& p, __nv_bfloat16* dst) -> int {
+    const StTensor* t = ck.find(p.name);
+    if (!t) { fprintf(stderr, "[acp_infer] checkpoint is missing %s\n", p.name.c_str()); return -1; }
+    const bool shape_ok = p.cols == 1 ? (t->shape.size() == 1 && t->shape[0] == p.rows)
+                                      : (t->shape.size() == 2 && t->shape[0] == p.rows && t->shape[1] == p.cols);
+    if (!shape_ok) { fprintf(stderr, "[acp_infer] %s has an unexpected shape\n", p.name.c_str()); return -1; }
+    const size_t e0 = (size_t)p.row0 * (size_t)p.cols, n = (size_t)p.nrows * (size_t)p.cols;
+    if (t->dtype == "BF16") {
+      ACP_CUDA_CHECK(cudaMemcpyAsync(dst, t->data + e0 * 2, n * 2, cudaMemcpyHostToDevice, stream_));
+      ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      return 0;
+    }
+    const size_t chunk = (size_t)16 << 20;
+    conv.resize(n < chunk ? n : chunk);
+    for (size_t o = 0; o < n; o += chunk) {
+      const size_t m = n - o < chunk ? n - o : chunk;
+      if (!st_to_bf16(*t, e0 + o, m, conv.data())) {
+        fprintf(stderr, "[acp_infer] %s: dtype %s is not supported (BF16, F16, F32)\n", p.name.c_str(), t->dtype.c_str());
+        return -1;
+      }
+      ACP_CUDA_CHECK(cudaMemcpyAsync(dst + o, conv.data(), m * 2, cudaMemcpyHostToDevice, stream_));
+      ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+    return 0;
+  };
+  auto tiled = [&](int local_cols, int logical_cols, int col0) {
+    SynthMap m;
+    m.local_cols = local_cols; m.logical_cols = logical_cols; m.col0 = col0;
+    return m;
+  };
+  auto whole = [&](const std::string& name, int64_t rows, int64_t cols) { return Part{name, rows, cols, 0, rows}; };
+  do {
+    if ((rc = upload(whole("model.embed_tokens.weight", c.vocab, H), embed_)) != 0) break;
+    {  // LM head: this shard's rows only (contiguous in the logical tensor)
+      const bool tied = c.tied_embeddings || !ck.find("lm_head.weight");
+      Part p{tied ? "model.embed_tokens.weight" : "lm_head.weight", c.vocab, (int64_t)H, lm_row0_, lm_rows_l_};
+      if ((rc = upload(p, stage)) != 0) break;
+      SynthMap m = tiled((int)H, (int)H, 0);
+      m.nseg = 1; m.seg_rows[0] = lm_rows_l_; m.seg_global[0] = lm_row0_;
+      if ((rc = launch_gather_weight(lm_head_, (size_t)lm_rows_l_ * H, stage, (size_t)lm_row0_ * H, stream_, m)) != 0) break;
+      ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+    if ((rc = upload(whole("model.norm.weight", H, 1), final_norm_)) != 0) break;
+    for (int l = 0; l < c.layers && rc == 0; ++l) {
+      Layer& L = layers_[l];
+      const std::string pre = "model.layers." + std::to_string(l) + ".";
+      {  // logical [q; k; v]
+        if ((rc = upload(whole(pre + "self_attn.q_proj.weight", c.q_dim(), H), stage)) != 0) break;
+        if ((rc = upload(whole(pre + "self_attn.k_proj.weight", c.kv_dim(), H), stage + (size_t)c.q_dim() * H)) != 0) break;
+        if ((rc = upload(whole(pre + "self_attn.v_proj.weight", c.kv_dim(), H), stage + (size_t)(c.q_dim() + c.kv_dim()) * H)) != 0) break;
+        SynthMap m = tiled((int)H, (int)H, 0);
+        m.nseg = 3;
+        m.seg_rows[0] = qdim_l_; m.seg_global[0] = r * qdim_l_;
+        m.seg_rows[1] = kvdim_l_; m.seg_global[1] = c.q_dim() + r * kvdim_l_;
+        m.seg_rows[2] = kvdim_l_; m.seg_global[2] = c.q_dim() + c.kv_dim() + r * kvdim_l_;
+        if ((rc = launch_gather_weight(L.wqkv, (size_t)qkv_l_ * H, stage, 0, stream_, m)) != 0) break;
+        ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      }
+      if ((rc = upload(whole(pre + "self_attn.o_proj.weight", H, c.q_dim()), stage)) != 0) break;
+      if ((rc = launch_gather_weight(L.wo, H * qdim_l_, stage, 0, stream_, tiled(qdim_l_, c.q_dim(), r * qdim_l_))) != 0) break;
+      ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      {  // logical [gate; up], stored interleaved (2j = gate_j, 2j+1 = up_j)
+        if ((rc = upload(whole(pre + "mlp.gate_proj.weight", c.ffn, H), stage)) != 0) break;
+        if ((rc = upload(whole(pre + "mlp.up_proj.weight", c.ffn, H), stage + (size_t)c.ffn * H)) != 0) break;
+        SynthMap m = tiled((int)H, (int)H, 0);
+        m.interleave_half = ffn_l_;
+        m.seg_global[0] = r * ffn_l_;
+        m.seg_global[1] = c.ffn + r * ffn_l_;
+        if ((rc = launch_gather_weight(L.wgu, (size_t)2 * ffn_l_ * H, stage, 0, stream_, m)) != 0) break;
+        ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      }
+      if ((rc = upload(whole(pre + "mlp.down_proj.weight", H, c.ffn), stage)) != 0) break;
+      if ((rc = launch_gather_weight(L.wdown, H * ffn_l_, stage, 0, stream_, tiled(ffn_l_, c.ffn, r * ffn_l_))) != 0) break;
+      ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      if ((rc = upload(whole(pre + "input_layernorm.weight", H, 1), L.attn_norm)) != 0) break;
+      if ((rc = upload(whole(pre + "post_attention_layernorm.weight", H, 1), L.ffn_norm)) != 0) break;
+    }
+  } while (false);
+  cudaFree(stage);
+  return rc;
 }
 
 static inline size_t align4(size_t v) { return (v + 3) & ~(size_t)3; }

@@ -9,6 +9,7 @@
 #include <vector>
 #include "attention.h"
 #include "gemm.h"
+#include "json.h"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
 #include "tp_comm.h"
@@ -23,6 +24,10 @@ struct ModelConfig {
   double w_std = 0.02;
   int max_pos = 8192;
   uint64_t seed = 0xACB200ull;
+  bool tied_embeddings = false;   // checkpoint without lm_head.weight: LM head = embedding matrix
+  // Llama-3.1 "llama3" RoPE frequency scaling (config.json rope_scaling); factor 0 = none
+  double rope_factor = 0.0, rope_low_freq = 1.0, rope_high_freq = 4.0;
+  int rope_orig_max_pos = 8192;
   int q_dim() const { return heads * HEAD_DIM; }
   int kv_dim() const { return kv_heads * HEAD_DIM; }
   int qkv_dim() const { return q_dim() + 2 * kv_dim(); }
@@ -35,6 +40,12 @@ struct ModelConfig {
   double kv_bytes_per_token() const { return 2.0 * kv_dim() * 2.0 * layers; }
 };
 bool model_preset(const std::string& name, ModelConfig* out);
+class Checkpoint;
+// ModelConfig from a HuggingFace Llama config.json; false + *err when the architecture is not one
+// this engine runs (head_dim must be 128, vocab a multiple of 128, ...).
+bool model_config_from_hf(const Json& hf, ModelConfig* out, std::string* err);
+// inverse RoPE frequencies [64] as the engine and oracle/llama_oracle.py rope_tables() build them
+void rope_inv_freq(const ModelConfig& c, float* inv64);
 
 struct ModelLimits {
   int max_batch = 256;       // sequences per decode step / sampled rows per step
@@ -78,7 +89,7 @@ class Model {
   // gate/up column-parallel, O and down row-parallel + NCCL all-reduce, LM head vocab-parallel);
   // `lead` is shard 0, whose pinned step staging every shard uploads from.
   int init(const ModelConfig& cfg, const ModelLimits& lim, int device, int tp_rank = 0, int tp_size = 1,
-           NcclComm comm = nullptr, Model* lead = nullptr);
+           NcclComm comm = nullptr, Model* lead = nullptr, const Checkpoint* ckpt = nullptr);
   // Runs one step on `stream()`: tokens for the n_sample rows land in host_tokens() after sync().
   int forward(const StepInput& in);
   int sync();
@@ -108,6 +119,8 @@ class Model {
  private:
   int alloc_all();
   int gen_weights();
+  int load_weights(const Checkpoint& ck);   // HuggingFace Llama safetensors -> tiled/sharded HBM layout
+  int build_rope_tables();
   int gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool decode, GemmOut* out);
   int choose_splits(int M, int K, int N) const;
   int gemm_rowpar(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool decode, GemmOut* out);

@@ -28,6 +28,7 @@ def lib():
         l.acp_host_stub_server_stop.argtypes = [ctypes.c_int]
         l.acp_host_stub_server_stop.restype = None
         l.acp_hostsim_run.argtypes = [vp, cp, out]
+        l.acp_host_checkpoint_index.argtypes = [cp, out]
         l.acp_infer_free.argtypes = [vp]
         l.acp_infer_free.restype = None
         _bound = l
@@ -125,3 +126,14 @@ def hostsim_window_tokens(prompt_tokens: int, tools: int) -> int:
     """Length of the context window hostsim builds for this target (a dry run with zero Tasks)."""
     r = hostsim_run({"tasks": 0, "provider": "openai", "prompt_tokens": prompt_tokens, "tools": tools})
     return int(r["prompt_tokens"])
+
+
+def checkpoint_index(path: str) -> dict:
+    """What acp_infer_init {"weights": path} would see: tensor table, config.json, derived model
+    config (raises ValueError with the loader's message when the checkpoint is not usable)."""
+    buf = ctypes.c_void_p()
+    rc = lib().acp_host_checkpoint_index(path.encode(), ctypes.byref(buf))
+    out = json.loads(_take(buf)) if buf.value else {}
+    if rc != 0:
+        raise ValueError(out.get("error", f"acp_host_checkpoint_index failed with {rc}"))
+    return out

@@ -67,6 +67,14 @@ void acp_host_stub_server_stop(int handle);
  *               "step_ms_p99": …, "store_writes": n, "final_phases": {...}, "digest": "…"} */
 int acp_hostsim_run(acp_engine* engine_or_null, const char* config_json, char** result_json);
 
+/* Checkpoint inspection (no GPU): opens a HuggingFace Llama checkpoint directory the way
+ * acp_infer_init {"weights": dir} does and reports
+ *   {"dir":…, "config":{…config.json…}, "tensors":{"name":{"dtype","shape","nbytes"}},
+ *    "model":{"hidden":…, "layers":…, "heads":…, "kv_heads":…, "ffn":…, "vocab":…, "rope_theta":…,
+ *             "eps":…, "tied_embeddings":…, "rope_inv_freq":[64 floats]}}
+ * or {"error": "..."} with return code ACP_ERR_INVALID. */
+int acp_host_checkpoint_index(const char* path, char** out_json);
+
 #ifdef __cplusplus
 }
 #endif

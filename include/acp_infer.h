@@ -47,7 +47,9 @@ typedef struct acp_engine acp_engine;
  * llmclient.NewLangchainClient (langchaingo_client.go:27-80): the Go `local` client is a
  * zero-cost handle onto this singleton.  config_json keys (all optional):
  *   "model": "llama-3-8b" | "llama-3-8b-l2" | "llama-3-70b" | "tiny" | "tiny-g2"
- *   "weights": "synthetic"            (seeded generator; no checkpoint files exist in this image)
+ *   "weights": "synthetic" (seeded generator, default) | "<dir>" = HuggingFace Llama checkpoint
+ *              (config.json + model.safetensors or model.safetensors.index.json + shards; BF16/F16/F32;
+ *              "model" is then just the name requests must carry, default = the directory name)
  *   "seed": 11317760                  (0xACB200)
  *   "device": 0, "max_batch": 256, "max_tokens_per_step": 8192, "kv_pages": 2048,
  *   "max_pages_per_seq": 256, "prefix_cache": true, "tp": 1 (tensor-parallel GPUs of THIS process),

@@ -1,0 +1,79 @@
+"""acp_infer_init {"weights": <dir>}: a HuggingFace-format checkpoint (written with the real
+`safetensors` library from the oracle's seeded weights) must produce EXACTLY the tokens and logits
+of the engine's synthetic-weight path — the loader's tiling / gate-up interleaving / q-k-v fusion /
+dtype conversion is then proven against the layout every other parity test already pins."""
+import numpy as np
+import pytest
+import torch
+
+from agentcontrolplane_b200 import _lib
+from agentcontrolplane_b200.engine import Engine
+from ckpt_util import write_checkpoint
+from oracle.llama_oracle import PRESETS
+
+pytestmark = pytest.mark.gpu
+SEED = 0xACB200
+BASE = {"max_batch": 8, "kv_pages": 128, "max_tokens_per_step": 1024, "max_pages_per_seq": 16}
+
+
+def _gen(e, model, prompts, n_new):
+    ts = [e.submit({"model": model, "max_tokens": n_new, "acp": {"prompt_token_ids": p, "return_logits": 2}}) for p in prompts]
+    out = []
+    for t in ts:
+        assert e.wait(t, 120000)
+        lg = e.logits(t, 2, 128256)
+        st, body = e.result(t)
+        assert st == 200, body
+        out.append((body["acp"]["token_ids"], lg))
+    return out
+
+
+@pytest.fixture(scope="module")
+def prompts():
+    rng = np.random.default_rng(21)
+    return [[128000] + [int(t) for t in rng.integers(0, 256, size=n - 1)] for n in (7, 64, 300)]
+
+
+@pytest.fixture(scope="module")
+def synthetic(prompts):
+    with Engine(dict(BASE, model="tiny-g2")) as e:
+        return _gen(e, "tiny-g2", prompts, 6)
+
+
+@pytest.mark.parametrize("variant", ["bf16", "sharded", "f32"])
+def test_checkpoint_equals_synthetic_weights(tmp_path, prompts, synthetic, variant):
+    d = str(tmp_path / "tiny-g2-ckpt")
+    write_checkpoint(d, PRESETS["tiny-g2"], SEED, shards=3 if variant == "sharded" else 1,
+                     dtype=torch.float32 if variant == "f32" else torch.bfloat16)
+    with Engine(dict(BASE, weights=d)) as e:
+        assert e.stats()["model"] == "tiny-g2-ckpt"          # default served name = directory name
+        got = _gen(e, "tiny-g2-ckpt", prompts, 6)
+        st, body = e.complete({"model": "something-else", "max_tokens": 2, "acp": {"prompt_token_ids": prompts[0]}})
+        assert st == 404
+    for (a, la), (b, lb) in zip(got, synthetic):
+        assert a == b and np.array_equal(la, lb)
+
+
+def test_checkpoint_tensor_parallel(tmp_path, prompts, synthetic):
+    if _lib.load().acp_kernel_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = str(tmp_path / "ckpt-tp")
+    write_checkpoint(d, PRESETS["tiny-g2"], SEED)
+    with Engine(dict(BASE, weights=d, model="m", tp=2)) as e:
+        got = [e.complete({"model": "m", "max_tokens": 6, "acp": {"prompt_token_ids": p}})[1]["acp"]["token_ids"] for p in prompts]
+    with Engine(dict(BASE, model="tiny-g2", tp=2)) as e:
+        want = [e.complete({"model": "tiny-g2", "max_tokens": 6, "acp": {"prompt_token_ids": p}})[1]["acp"]["token_ids"] for p in prompts]
+    assert got == want
+
+
+def test_missing_tensor_fails_init(tmp_path):
+    import os
+    from safetensors.torch import load_file, save_file
+    d = str(tmp_path / "broken")
+    write_checkpoint(d, PRESETS["tiny"], SEED)
+    f = os.path.join(d, "model.safetensors")
+    t = load_file(f)
+    del t["model.layers.1.mlp.down_proj.weight"]
+    save_file(t, f)
+    with pytest.raises(RuntimeError):
+        Engine(dict(BASE, weights=d))
