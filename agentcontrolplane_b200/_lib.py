@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libacp_infer.so")
+# ACP_INFER_LIB: load a library built elsewhere (e.g. a scratch build while the in-tree one is in use)
+LIB_PATH = os.environ.get("ACP_INFER_LIB") or os.path.join(_HERE, "lib", "libacp_infer.so")
 _lib = None
 
 

@@ -100,25 +100,8 @@ int parse_chat_request(const char* json, size_t len, ChatRequest* out, std::stri
 // ---------------------------------------------------------------------------------
 // tokenizer
 // ---------------------------------------------------------------------------------
-void encode_text(const std::string& text, std::vector<int>* ids) {
-  for (unsigned char c : text) ids->push_back((int)c);
-}
-
-std::string decode_tokens(const std::vector<int>& ids) {
-  std::string out;
-  for (int id : ids) {
-    if (id < 0) continue;
-    if (id < 256) out.push_back((char)(unsigned char)id);
-    else if (id < TOK_BEGIN_OF_TEXT) {
-      // synthetic "word" tokens: a space followed by the id in base-26 letters (LSB first)
-      out.push_back(' ');
-      unsigned n = (unsigned)(id - 256);
-      do { out.push_back((char)('a' + n % 26)); n /= 26; } while (n > 0);
-    }
-    // special tokens (>= 128000) decode to nothing
-  }
-  return out;
-}
+void encode_text(const std::string& text, std::vector<int>* ids) { synthetic_tokenizer().encode(text, ids); }
+std::string decode_tokens(const std::vector<int>& ids) { return synthetic_tokenizer().decode(ids); }
 
 // ---------------------------------------------------------------------------------
 // chat template
@@ -127,21 +110,29 @@ namespace {
 struct Emitter {
   std::vector<int>* ids;   // either token ids ...
   std::string* text;       // ... or the spelled-out string
+  const Tokenizer* tok;
+  std::string pending;     // ordinary text since the last special token: encoded as ONE string, as a
+                           // tokenizer that splits the rendered prompt at special tokens would
+  void flush() {
+    if (ids && !pending.empty()) tok->encode(pending, ids);
+    pending.clear();
+  }
   void special(int id, const char* spelled) {
+    flush();
     if (ids) ids->push_back(id);
     if (text) *text += spelled;
   }
   void bytes(const std::string& s) {
-    if (ids) encode_text(s, ids);
+    if (ids) pending += s;
     if (text) *text += s;
   }
   void header(const char* role) {
-    special(TOK_START_HEADER, "<|start_header_id|>");
+    special(tok->special().start_header, "<|start_header_id|>");
     bytes(role);
-    special(TOK_END_HEADER, "<|end_header_id|>");
+    special(tok->special().end_header, "<|end_header_id|>");
     bytes("\n\n");
   }
-  void eot() { special(TOK_EOT, "<|eot_id|>"); }
+  void eot() { special(tok->special().eot, "<|eot_id|>"); }
 };
 
 std::string tool_json(const ToolDef& t) {
@@ -156,7 +147,7 @@ std::string tool_json(const ToolDef& t) {
 }
 
 void render(const ChatRequest& req, Emitter& e) {
-  e.special(TOK_BEGIN_OF_TEXT, "<|begin_of_text|>");
+  e.special(e.tok->special().begin_of_text, "<|begin_of_text|>");
   size_t idx = 0;
   std::string sys;
   if (!req.messages.empty() && req.messages[0].role == "system") { sys = req.messages[0].content; idx = 1; }
@@ -208,16 +199,17 @@ void render(const ChatRequest& req, Emitter& e) {
     }
   }
   e.header("assistant");
+  e.flush();
 }
 }  // namespace
 
-void render_prompt(const ChatRequest& req, std::vector<int>* ids) {
-  Emitter e{ids, nullptr};
+void render_prompt(const ChatRequest& req, std::vector<int>* ids, const Tokenizer& tok) {
+  Emitter e{ids, nullptr, &tok, std::string()};
   render(req, e);
 }
 std::string render_prompt_text(const ChatRequest& req) {
   std::string s;
-  Emitter e{nullptr, &s};
+  Emitter e{nullptr, &s, &synthetic_tokenizer(), std::string()};
   render(req, e);
   return s;
 }

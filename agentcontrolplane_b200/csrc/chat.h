@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include "json.h"
+#include "tokenizer.h"
 
 namespace acp {
 
@@ -55,12 +56,12 @@ struct ChatRequest {
 // Parses an OpenAI chat-completions body.  Returns 0 or an HTTP-like 4xx status with *err set.
 int parse_chat_request(const char* json, size_t len, ChatRequest* out, std::string* err);
 
-// ---- tokenizer (synthetic byte-level vocabulary) ----
+// ---- tokenizer: see tokenizer.h; these two are the synthetic byte-level vocabulary ----
 void encode_text(const std::string& text, std::vector<int>* ids);  // one id per UTF-8 byte
 std::string decode_tokens(const std::vector<int>& ids);            // total over [0, vocab)
 
 // ---- chat template (Llama-3 headers; Llama-3.1 JSON tool calling) ----
-void render_prompt(const ChatRequest& req, std::vector<int>* ids);
+void render_prompt(const ChatRequest& req, std::vector<int>* ids, const Tokenizer& tok = synthetic_tokenizer());
 std::string render_prompt_text(const ChatRequest& req);  // specials spelled out, for tests
 
 // ---- completion text -> assistant message ----

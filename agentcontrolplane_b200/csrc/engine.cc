@@ -46,6 +46,27 @@ int Engine::init(const char* config_json) {
       return -1;
     }
   }
+  {  // vocabulary: explicit "tokenizer", else the checkpoint's tokenizer.json, else the synthetic one
+    std::string tpath = cfg.get("tokenizer").as_string();
+    if (tpath.empty() && ckpt_) {
+      const std::string cand = ckpt_->dir() + "/tokenizer.json";
+      if (FILE* f = fopen(cand.c_str(), "rb")) { fclose(f); tpath = cand; }
+    }
+    if (!tpath.empty() && tpath != "synthetic") {
+      std::string err;
+      tok_owned_ = load_tokenizer_json(tpath, &err);
+      if (!tok_owned_) { fprintf(stderr, "[acp_infer] tokenizer: %s\n", err.c_str()); return -1; }
+      tok_ = tok_owned_.get();
+      if (tok_->vocab_size() > mc.vocab) {
+        fprintf(stderr, "[acp_infer] tokenizer has %d ids but the model's vocabulary is %d\n", tok_->vocab_size(), mc.vocab);
+        return -1;
+      }
+    } else if (mc.vocab < synthetic_tokenizer().vocab_size()) {
+      fprintf(stderr, "[acp_infer] the synthetic tokenizer needs a model vocabulary of %d (got %d): pass \"tokenizer\"\n",
+              synthetic_tokenizer().vocab_size(), mc.vocab);
+      return -1;
+    }
+  }
   if (cfg.find("seed")) mc.seed = (uint64_t)cfg.get("seed").as_int((long long)mc.seed);
   if (cfg.find("layers")) mc.layers = (int)cfg.get("layers").as_int(mc.layers);  // truncated-depth runs
   ModelLimits lim;
@@ -212,7 +233,7 @@ int Engine::submit(const char* json, size_t len, uint64_t* ticket) {
   }
   if (status == 0) {
     if (req.has_prompt_ids) s->tokens = req.prompt_token_ids;
-    else render_prompt(req, &s->tokens);
+    else render_prompt(req, &s->tokens, *tok_);
     const int vocab = model_.config().vocab;
     for (int t : s->tokens)
       if (t < 0 || t >= vocab) { status = 400; err = "prompt token id out of range"; break; }
@@ -321,7 +342,7 @@ int Engine::result(uint64_t ticket, std::string* body, int* status) {
   std::vector<int> gen(s->tokens.begin() + s->prompt_len, s->tokens.end());
   std::vector<int> text_ids = gen;
   if (s->finish_reason == "stop" && !text_ids.empty()) text_ids.pop_back();  // drop the stop token
-  const std::string text = decode_tokens(text_ids);
+  const std::string text = tok_->decode(text_ids);
   ParsedCompletion pc = parse_completion(text, s->tools, "call_" + std::to_string(ticket) + "_");
   if (pc.tool_calls.empty() && pc.content.empty()) {
     // The Task controller loops forever on an empty assistant message
@@ -603,7 +624,7 @@ bool Engine::step() {
     if (gen_idx < (int)s.force_tokens.size()) tok = s.force_tokens[gen_idx];
     if (gen_idx == 0) s.t_first = now;
     s.tokens.push_back(tok);
-    const bool stop_tok = (tok == TOK_EOT || tok == TOK_END_OF_TEXT || tok == TOK_EOM);
+    const bool stop_tok = tok_->is_stop(tok);
     const bool at_cap = (gen_idx + 1 >= s.sampling.max_tokens);
     if (stop_tok || at_cap) {
       for (auto it = running_.begin(); it != running_.end(); ++it)
@@ -671,6 +692,7 @@ std::string Engine::stats_json() {
   const ModelConfig& c = model_.config();
   Json j = Json::object();
   j.set("model", Json(model_name_));
+  j.set("tokenizer", Json(tok_->kind()));
   j.set("layers", Json(c.layers));
   j.set("decode_steps", Json(stats_.decode_steps));
   j.set("decode_tokens", Json(stats_.decode_tokens));

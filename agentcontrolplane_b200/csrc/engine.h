@@ -86,6 +86,8 @@ class Engine {
   int run_forward(const StepInput& in);
   void tp_worker(int idx);
 
+  std::unique_ptr<Tokenizer> tok_owned_;         // "tokenizer": tokenizer.json (byte-level BPE)
+  const Tokenizer* tok_ = &synthetic_tokenizer();
   std::unique_ptr<Checkpoint> ckpt_;             // "weights": <dir> — mmap'ed until the shards are loaded
   Model model_;                                  // shard 0 (the only one when tp == 1)
   std::vector<std::unique_ptr<Model>> extra_;    // tensor-parallel shards 1..tp-1, one GPU each

@@ -9,6 +9,8 @@
 #include <unistd.h>
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <chrono>
 #include <thread>
 #include "../chat.h"
@@ -182,6 +184,86 @@ extern "C" void acp_host_stub_server_stop(int handle) {
 // ---------------------------------------------------------------------------------
 // chat-side hooks
 // ---------------------------------------------------------------------------------
+namespace {
+// tokenizer.json files loaded for the test hooks, by path (nullptr / "" / "synthetic" = built in)
+const Tokenizer* hook_tokenizer(const char* path, std::string* err) {
+  if (!path || !*path || std::string(path) == "synthetic") return &synthetic_tokenizer();
+  static std::mutex mu;
+  static std::map<std::string, std::unique_ptr<Tokenizer>> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(path);
+  if (it != cache.end()) return it->second.get();
+  std::unique_ptr<Tokenizer> t = load_tokenizer_json(path, err);
+  if (!t) return nullptr;
+  return (cache[path] = std::move(t)).get();
+}
+int tokenizer_error(const std::string& err, char** out_json) {
+  Json j = Json::object();
+  j.set("error", Json(err));
+  ret_json(j, out_json);
+  return ACP_ERR_INVALID;
+}
+}  // namespace
+
+extern "C" int acp_host_tokenizer_encode(const char* tokenizer_path, const char* text, size_t len, char** out_json) {
+  if (!text || !out_json) return ACP_ERR_INVALID;
+  std::string err;
+  const Tokenizer* tok = hook_tokenizer(tokenizer_path, &err);
+  if (!tok) return tokenizer_error(err, out_json);
+  const std::string s(text, len);
+  std::vector<int> ids;
+  tok->encode(s, &ids);
+  std::vector<std::string> pieces;
+  llama3_pretokenize(s, &pieces);
+  Json out = Json::object(), a = Json::array(), p = Json::array();
+  for (int t : ids) a.push(Json(t));
+  for (const std::string& x : pieces) p.push(Json(x));
+  out.set("ids", a);
+  out.set("pieces", p);
+  out.set("kind", Json(tok->kind()));
+  out.set("vocab_size", Json(tok->vocab_size()));
+  Json sp = Json::object();
+  sp.set("begin_of_text", Json(tok->special().begin_of_text)); sp.set("end_of_text", Json(tok->special().end_of_text));
+  sp.set("start_header", Json(tok->special().start_header)); sp.set("end_header", Json(tok->special().end_header));
+  sp.set("eom", Json(tok->special().eom)); sp.set("eot", Json(tok->special().eot));
+  sp.set("python_tag", Json(tok->special().python_tag));
+  out.set("special", sp);
+  return ret_json(out, out_json);
+}
+
+extern "C" int acp_host_tokenizer_decode(const char* tokenizer_path, const int* ids, int n, char** out_text, size_t* out_len) {
+  if ((!ids && n > 0) || !out_text) return ACP_ERR_INVALID;
+  std::string err;
+  const Tokenizer* tok = hook_tokenizer(tokenizer_path, &err);
+  if (!tok) return ACP_ERR_INVALID;
+  std::vector<int> v(ids, ids + n);
+  *out_text = dup_out(tok->decode(v), out_len);
+  return *out_text ? ACP_OK : ACP_ERR_NOMEM;
+}
+
+extern "C" int acp_host_render_prompt_with(const char* tokenizer_path, const char* chat_request_json, size_t len,
+                                           char** out_json) {
+  if (!chat_request_json || !out_json) return ACP_ERR_INVALID;
+  std::string err;
+  const Tokenizer* tok = hook_tokenizer(tokenizer_path, &err);
+  if (!tok) return tokenizer_error(err, out_json);
+  ChatRequest req;
+  Json out = Json::object();
+  int status = parse_chat_request(chat_request_json, len, &req, &err);
+  if (status != 0) {
+    out.set("status", Json(status));
+    out.set("error", Json(err));
+    return ret_json(out, out_json);
+  }
+  std::vector<int> ids;
+  render_prompt(req, &ids, *tok);
+  Json arr = Json::array();
+  for (int t : ids) arr.push(Json(t));
+  out.set("text", Json(render_prompt_text(req)));
+  out.set("token_ids", arr);
+  return ret_json(out, out_json);
+}
+
 extern "C" int acp_host_render_prompt(const char* chat_request_json, size_t len, char** out_json) {
   if (!chat_request_json || !out_json) return ACP_ERR_INVALID;
   ChatRequest req;

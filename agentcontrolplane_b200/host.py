@@ -137,3 +137,39 @@ def checkpoint_index(path: str) -> dict:
     if rc != 0:
         raise ValueError(out.get("error", f"acp_host_checkpoint_index failed with {rc}"))
     return out
+
+
+def tokenizer_encode(text: str | bytes, tokenizer_path: str | None = None) -> dict:
+    """ids / pre-tokenizer pieces of `text` under a tokenizer.json (None = synthetic vocabulary)."""
+    raw = text.encode() if isinstance(text, str) else text
+    buf = ctypes.c_void_p()
+    l = lib()
+    l.acp_host_tokenizer_encode.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+    rc = l.acp_host_tokenizer_encode(tokenizer_path.encode() if tokenizer_path else None, raw, len(raw), ctypes.byref(buf))
+    out = json.loads(_take(buf)) if buf.value else {}
+    if rc != 0:
+        raise ValueError(out.get("error", f"acp_host_tokenizer_encode failed with {rc}"))
+    return out
+
+
+def tokenizer_decode(ids: list[int], tokenizer_path: str | None = None) -> bytes:
+    arr = (ctypes.c_int * len(ids))(*ids)
+    buf, n = ctypes.c_void_p(), ctypes.c_size_t()
+    l = lib()
+    l.acp_host_tokenizer_decode.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                            ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
+    _check(l.acp_host_tokenizer_decode(tokenizer_path.encode() if tokenizer_path else None, arr, len(ids),
+                                       ctypes.byref(buf), ctypes.byref(n)), "acp_host_tokenizer_decode")
+    return _take(buf, n.value)
+
+
+def render_prompt_with(request: dict, tokenizer_path: str | None) -> dict:
+    raw = json.dumps(request).encode()
+    buf = ctypes.c_void_p()
+    l = lib()
+    l.acp_host_render_prompt_with.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+    rc = l.acp_host_render_prompt_with(tokenizer_path.encode() if tokenizer_path else None, raw, len(raw), ctypes.byref(buf))
+    out = json.loads(_take(buf)) if buf.value else {}
+    if rc != 0:
+        raise ValueError(out.get("error", f"acp_host_render_prompt_with failed with {rc}"))
+    return out

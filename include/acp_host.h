@@ -67,6 +67,16 @@ void acp_host_stub_server_stop(int handle);
  *               "step_ms_p99": …, "store_writes": n, "final_phases": {...}, "digest": "…"} */
 int acp_hostsim_run(acp_engine* engine_or_null, const char* config_json, char** result_json);
 
+/* Tokenizer hooks (no GPU).  tokenizer_path = a HuggingFace tokenizer.json (or its directory);
+ * NULL / "" / "synthetic" = the built-in synthetic byte-level vocabulary.
+ *   encode: {"ids":[…], "pieces":[Llama-3 pre-tokenizer split of the text], "kind":…, "vocab_size":n,
+ *            "special":{"begin_of_text":id, …}}   or {"error":…} with ACP_ERR_INVALID
+ *   decode: raw bytes of the ids (special / unknown ids decode to nothing)
+ *   render_prompt_with: acp_host_render_prompt through that tokenizer. */
+int acp_host_tokenizer_encode(const char* tokenizer_path, const char* text, size_t len, char** out_json);
+int acp_host_tokenizer_decode(const char* tokenizer_path, const int* ids, int n, char** out_text, size_t* out_len);
+int acp_host_render_prompt_with(const char* tokenizer_path, const char* chat_request_json, size_t len, char** out_json);
+
 /* Checkpoint inspection (no GPU): opens a HuggingFace Llama checkpoint directory the way
  * acp_infer_init {"weights": dir} does and reports
  *   {"dir":…, "config":{…config.json…}, "tensors":{"name":{"dtype","shape","nbytes"}},

@@ -77,3 +77,49 @@ def test_missing_tensor_fails_init(tmp_path):
     save_file(t, f)
     with pytest.raises(RuntimeError):
         Engine(dict(BASE, weights=d))
+
+
+def test_checkpoint_with_its_own_tokenizer_json(tmp_path):
+    """A checkpoint directory that ships tokenizer.json is served with THAT vocabulary: the chat
+    template is tokenised by the byte-level BPE (tests/test_tokenizer_cpu.py pins it to HuggingFace
+    `tokenizers`), stop tokens are the tokenizer's own ids, and the text is detokenised with it."""
+    import json
+    import os
+    import shutil
+
+    from agentcontrolplane_b200 import host
+    from oracle.llama_oracle import LlamaOracle
+    here = os.path.dirname(os.path.abspath(__file__))
+    tok_file = os.path.join(here, "golden", "llama3_style_tokenizer.json")
+    gold = json.load(open(os.path.join(here, "golden", "tokenizer_golden.json")))
+    d = str(tmp_path / "served-model")
+    write_checkpoint(d, PRESETS["tiny"], SEED)
+    shutil.copy(tok_file, os.path.join(d, "tokenizer.json"))
+    req = {"model": "served-model", "max_tokens": 12, "messages": [
+        {"role": "system", "content": "You are a helpful assistant."},
+        {"role": "user", "content": "What is the capital of France?"}]}
+    want_prompt = host.render_prompt_with(req, tok_file)["token_ids"]
+    stops = tuple(gold["special"][k] for k in ("<|eot_id|>", "<|eom_id|>", "<|end_of_text|>"))
+    with Engine(dict(BASE, weights=d)) as e:
+        assert e.stats()["tokenizer"] == "byte-level-bpe"
+        st, body = e.complete(req)
+        assert st in (200, 422), body          # 422 = the random-weight model stopped immediately
+        if st == 200:
+            ids = body["acp"]["token_ids"]
+            assert body["usage"]["prompt_tokens"] == len(want_prompt)
+            want, margins = LlamaOracle(PRESETS["tiny"], SEED, mode="bf16").greedy(want_prompt, 12, eos=stops)
+            for i, (g, w) in enumerate(zip(ids, want)):
+                if g != w:
+                    assert margins[i] < 0.06, (ids, want, margins)
+                    break
+            text_ids = ids[:-1] if ids and ids[-1] in stops else ids
+            import re
+            squash = lambda t: re.sub("\ufffd+", "\ufffd", t)      # replacement granularity for invalid UTF-8 may differ
+            assert squash(body["choices"][0]["message"]["content"]) == squash(host.tokenizer_decode(text_ids, tok_file).decode(errors="replace"))
+    # a tokenizer whose ids exceed the model's vocabulary is refused at init
+    small = str(tmp_path / "small-vocab")
+    from oracle.llama_oracle import LlamaConfig
+    write_checkpoint(small, LlamaConfig("small", hidden=256, layers=1, heads=2, kv_heads=1, ffn=512, vocab=1024), SEED)
+    shutil.copy(tok_file, os.path.join(small, "tokenizer.json"))
+    with pytest.raises(RuntimeError):
+        Engine(dict(BASE, weights=small))
