@@ -277,11 +277,13 @@ def main():
             "n_gpus": world * WORKLOAD["tp"], "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"] + (f" [DEV: layers={args.layers}]" if args.layers else ""),
-                       "weights": "seeded synthetic bf16 at Llama-3-8B shapes (seed 0xACB200)",
+                       "weights": f"seeded synthetic bf16 at {args.model} shapes (seed 0xACB200)",
                        "parallelism": (f"dp{world} (one engine replica per GPU, no collective)" if WORKLOAD["tp"] == 1 else
-                                       f"tp{WORKLOAD['tp']} (one process, NCCL all-reduce x2 per layer over NVLink)"),
+                                       f"tp{WORKLOAD['tp']} (one process; fused peer-memory all-reduce + residual + RMSNorm "
+                                       "x2 per layer over NVLink, tp_comm.cu)"),
                        "prefix_hits": s1.get("prefix_hits", 0), "prefix_tokens_reused": s1.get("prefix_tokens_reused", 0),
-                       "l2": "inputs larger than L2: every decode step streams 15.0 GB of weights + 4.3 GB of KV through a 126 MB L2",
+                       "l2": (f"inputs larger than L2: every decode step streams {s1['decode_bytes_algorithmic'] / max(1, s1['decode_steps']) / 1e9:.1f} GB "
+                              "of weights + KV (all GPUs) through a 126 MB L2 per GPU"),
                        "final_phases": phases},
             "decode_tokens_per_s": total_decode_tokens / dec_max if dec_max > 0 else 0.0,  # all ranks / max decode time
             "decode_tokens_per_s_rank0": s1["decode_tokens"] / dec_s if dec_s > 0 else 0.0,
