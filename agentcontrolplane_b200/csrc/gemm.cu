@@ -83,14 +83,27 @@ int gemm_pick_bn(int N) {
   return 256;
 }
 
+// ACP_GEMM_SHALLOW=0: wide tiles keep the deep ring / one CTA per SM (A/B switch)
+static bool shallow_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACP_GEMM_SHALLOW"); v = (e && *e == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 template <int BN, int EPI>
 static int launch_one(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t stream) {
   GemmArgs a;
   a.M = g.M; a.N = g.N; a.K = g.K; a.splits = g.splits; a.ld = g.ld; a.n_cap = g.n_cap;
   a.out = g.out; a.amax_val = g.amax_val; a.amax_idx = g.amax_idx; a.n_dev = g.n_dev;
   dim3 grid((g.N + BN - 1) / BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.splits);
-  cudaError_t e = acp_launch(gemm_wx_kernel<BN, EPI>, grid, dim3(GEMM_THREADS), GemmCfg<BN>::kSmemBytes,
-                             stream, *g.w, tx, a);
+  cudaError_t e;
+  constexpr int kShallow = GemmCfg<BN>::kShallowStages;
+  if (kShallow != GemmCfg<BN>::kStages && shallow_enabled())
+    e = acp_launch(gemm_wx_kernel<BN, EPI, kShallow>, grid, dim3(GEMM_THREADS), GemmCfg<BN>::smem_bytes(kShallow),
+                   stream, *g.w, tx, a);
+  else
+    e = acp_launch(gemm_wx_kernel<BN, EPI>, grid, dim3(GEMM_THREADS), GemmCfg<BN>::kSmemBytes,
+                   stream, *g.w, tx, a);
   if (e != cudaSuccess) {
     fprintf(stderr, "[acp_infer] gemm launch failed BN=%d EPI=%d: %s\n", BN, EPI,
             cudaGetErrorString(e));
@@ -157,6 +170,10 @@ static int set_attr() {
   cudaError_t e = cudaFuncSetAttribute(gemm_wx_kernel<BN, EPI>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        GemmCfg<BN>::kSmemBytes);
+  constexpr int kShallow = GemmCfg<BN>::kShallowStages;
+  if (e == cudaSuccess && kShallow != GemmCfg<BN>::kStages)
+    e = cudaFuncSetAttribute(gemm_wx_kernel<BN, EPI, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             GemmCfg<BN>::smem_bytes(kShallow));
   return e == cudaSuccess ? 0 : -5;
 }
 template <int BN>

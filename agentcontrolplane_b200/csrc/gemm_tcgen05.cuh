@@ -60,6 +60,8 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kShallowStages = BN == 256 ? 2 : (BN == 128 ? 3 : kStages);   // two CTAs per SM
+  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 + 256; }
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
@@ -85,12 +87,15 @@ __device__ __forceinline__ void swiglu_store16(__nv_bfloat16* out, const uint32_
   }
 }
 
-template <int BN, int EPI>
+// STAGES: depth of the TMA ring.  The wide tiles (BN 128 / 256) come in two flavours: a deep ring
+// with one CTA per SM, or a shallow ring (3 / 2 stages, 96 KiB) with TWO CTAs per SM — the same
+// bytes in flight per SM, but 296 CTA slots, so a split-K grid of 150-296 CTAs runs as ONE wave.
+template <int BN, int EPI, int STAGES_ = GemmCfg<BN>::kStages>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                GemmArgs args) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
+  constexpr int STAGES = STAGES_;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atom (8 rows x 128 B).
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
