@@ -365,36 +365,110 @@ void Engine::cancel(uint64_t ticket) {
   cv_work_.notify_one();
 }
 
+// caller holds mu_.  Pages mapped from the prefix cache go back to it (one user fewer), the
+// sequence's own pages to the free list.
 void Engine::release_pages(Sequence& s) {
-  for (int p : s.pages) free_pages_.push_back(p);
+  for (size_t i = 0; i < s.pages.size(); ++i) {
+    if (i < s.shared.size()) --pcache_[(size_t)s.shared[i]].active;
+    else free_pages_.push_back(s.pages[i]);
+  }
   s.pages.clear();
+  s.shared.clear();
 }
 
-// caller holds mu_
-bool Engine::evict_one_locked() {
-  if (prefix_cache_.empty()) return false;
-  size_t lru = 0;
-  for (size_t i = 1; i < prefix_cache_.size(); ++i)
-    if (prefix_cache_[i].last_use < prefix_cache_[lru].last_use) lru = i;
-  for (int p : prefix_cache_[lru].pages) free_pages_.push_back(p);
-  prefix_cache_[lru] = std::move(prefix_cache_.back());
-  prefix_cache_.pop_back();
-  return true;
+static uint64_t chain_key(uint64_t parent_key, const int* tokens) {
+  uint64_t h = parent_key * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+  for (int i = 0; i < KV_PAGE; ++i) {
+    h ^= (uint64_t)(uint32_t)tokens[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+  }
+  return h;
 }
 
-// caller holds mu_.  Keeps the pages that hold the PROMPT's K/V; everything else goes back.
+// entry holding the page (parent, tokens[0..32)) or -1; caller holds mu_
+int Engine::pcache_find_locked(int parent, const int* tokens) const {
+  const uint64_t key = chain_key(parent < 0 ? 0 : pcache_[(size_t)parent].key, tokens);
+  auto range = pcache_index_.equal_range(key);
+  for (auto it = range.first; it != range.second; ++it) {
+    const CachedPage& e = pcache_[(size_t)it->second];
+    if (e.parent == parent && memcmp(e.tokens, tokens, sizeof e.tokens) == 0) return it->second;
+  }
+  return -1;
+}
+
+// caller holds mu_.  Frees cached pages that nobody maps and nothing chains from (leaves first, so
+// a chain shrinks from its tail), least recently used first, until `want` pages are free or
+// nothing is evictable.
+bool Engine::evict_locked(int want) {
+  bool any = false;
+  while ((int)free_pages_.size() < want) {
+    std::vector<std::pair<uint64_t, int>> cand;
+    for (size_t i = 0; i < pcache_.size(); ++i) {
+      const CachedPage& e = pcache_[i];
+      if (e.page >= 0 && e.active == 0 && e.children == 0) cand.emplace_back(e.last_use, (int)i);
+    }
+    if (cand.empty()) break;
+    std::sort(cand.begin(), cand.end());
+    for (const auto& c : cand) {
+      if ((int)free_pages_.size() >= want) break;
+      CachedPage& e = pcache_[(size_t)c.second];
+      auto range = pcache_index_.equal_range(e.key);
+      for (auto it = range.first; it != range.second; ++it)
+        if (it->second == c.second) { pcache_index_.erase(it); break; }
+      if (e.parent >= 0) --pcache_[(size_t)e.parent].children;
+      free_pages_.push_back(e.page);
+      e.page = -1;
+      free_entries_.push_back(c.second);
+      --pcache_pages_;
+      any = true;
+    }
+  }
+  return any;
+}
+
+// caller holds mu_.  Donates the whole pages that hold the PROMPT's K/V to the prefix cache (pages
+// whose content is already cached are simply freed); everything else goes back to the free list.
 void Engine::retain_prefix_locked(Sequence& s) {
   const int keep_tokens = std::min(s.prompt_len, s.n_cached);
   const int keep_pages = keep_tokens / KV_PAGE;  // whole pages only
   if (!prefix_cache_on_ || keep_pages < 1 || (int)s.pages.size() < keep_pages) { release_pages(s); return; }
-  CachedPrefix e;
-  e.tokens.assign(s.tokens.begin(), s.tokens.begin() + keep_pages * KV_PAGE);
-  e.pages.assign(s.pages.begin(), s.pages.begin() + keep_pages);
-  e.last_use = ++use_clock_;
-  for (size_t i = keep_pages; i < s.pages.size(); ++i) free_pages_.push_back(s.pages[i]);
+  ++use_clock_;
+  int parent = -1;
+  for (int i = 0; i < (int)s.pages.size(); ++i) {
+    if (i < (int)s.shared.size()) {          // mapped from the cache: hand it back, keep walking the chain
+      parent = s.shared[(size_t)i];
+      --pcache_[(size_t)parent].active;
+      pcache_[(size_t)parent].last_use = use_clock_;
+      continue;
+    }
+    if (i >= keep_pages) { free_pages_.push_back(s.pages[(size_t)i]); continue; }
+    const int* toks = s.tokens.data() + (size_t)i * KV_PAGE;
+    const int have = pcache_find_locked(parent, toks);
+    if (have >= 0) {                          // same content cached meanwhile by another sequence
+      free_pages_.push_back(s.pages[(size_t)i]);
+      pcache_[(size_t)have].last_use = use_clock_;
+      parent = have;
+      continue;
+    }
+    int idx;
+    if (!free_entries_.empty()) { idx = free_entries_.back(); free_entries_.pop_back(); }
+    else { idx = (int)pcache_.size(); pcache_.emplace_back(); }
+    CachedPage& e = pcache_[(size_t)idx];
+    e.page = s.pages[(size_t)i];
+    e.parent = parent;
+    e.children = 0;
+    e.active = 0;
+    e.key = chain_key(parent < 0 ? 0 : pcache_[(size_t)parent].key, toks);
+    e.last_use = use_clock_;
+    memcpy(e.tokens, toks, sizeof e.tokens);
+    if (parent >= 0) ++pcache_[(size_t)parent].children;
+    pcache_index_.emplace(e.key, idx);
+    ++pcache_pages_;
+    parent = idx;
+  }
   s.pages.clear();
-  if (prefix_cache_.size() >= prefix_cache_max_) evict_one_locked();
-  prefix_cache_.push_back(std::move(e));
+  s.shared.clear();
 }
 
 void Engine::finish(const std::shared_ptr<Sequence>& s, int status, const std::string& type,
@@ -430,42 +504,38 @@ void Engine::admit_locked() {
   while (!waiting_.empty() && (int)running_.size() < max_batch) {
     auto& s = waiting_.front();
     const int need = (s->prompt_len + s->sampling.max_tokens + KV_PAGE - 1) / KV_PAGE;
-    // longest retained prefix (page granular; at least one prompt token is always recomputed so
-    // that there are logits to sample from)
-    int best = -1, best_pages = 0;
+    // longest cached chain of whole prompt pages (at least one prompt token is always recomputed
+    // so that there are logits to sample from); the pages are MAPPED, not moved: any number of
+    // running sequences read the same physical pages
+    std::vector<int> chain;
     if (prefix_cache_on_) {
-      for (size_t i = 0; i < prefix_cache_.size(); ++i) {
-        const CachedPrefix& e = prefix_cache_[i];
-        if (e.tokens[0] != s->tokens[0] || (int)e.tokens.size() <= best_pages * KV_PAGE) continue;
-        const int lim = std::min((int)e.tokens.size(), s->prompt_len - 1);
-        int common = 0;
-        while (common < lim && e.tokens[common] == s->tokens[common]) ++common;
-        const int pg = common / KV_PAGE;
-        if (pg > best_pages) { best_pages = pg; best = (int)i; }
+      const int max_pages = (s->prompt_len - 1) / KV_PAGE;
+      int parent = -1;
+      for (int i = 0; i < max_pages; ++i) {
+        const int e = pcache_find_locked(parent, s->tokens.data() + (size_t)i * KV_PAGE);
+        if (e < 0) break;
+        chain.push_back(e);
+        parent = e;
       }
     }
-    const int fresh = need - best_pages;
-    while (fresh > (int)free_pages_.size() && !prefix_cache_.empty()) {
-      // evict retained prefixes (never the one about to be reused) to make room
-      size_t lru = prefix_cache_.size();
-      for (size_t i = 0; i < prefix_cache_.size(); ++i)
-        if ((int)i != best && (lru == prefix_cache_.size() || prefix_cache_[i].last_use < prefix_cache_[lru].last_use)) lru = i;
-      if (lru == prefix_cache_.size()) break;
-      for (int p : prefix_cache_[lru].pages) free_pages_.push_back(p);
-      if (best == (int)prefix_cache_.size() - 1) best = (int)lru;  // the reused entry moves into the hole
-      prefix_cache_[lru] = std::move(prefix_cache_.back());
-      prefix_cache_.pop_back();
+    const int fresh = need - (int)chain.size();
+    // pin the chain while evicting to make room (an entry with users is never evicted)
+    for (int e : chain) ++pcache_[(size_t)e].active;
+    if (fresh > (int)free_pages_.size()) evict_locked(fresh);
+    if (fresh > (int)free_pages_.size()) {    // FIFO: wait for pages to come back
+      for (int e : chain) --pcache_[(size_t)e].active;
+      break;
     }
-    if (fresh > (int)free_pages_.size()) break;  // FIFO: wait for pages to come back
-    if (best >= 0) {
-      CachedPrefix& e = prefix_cache_[best];
-      for (int i = 0; i < best_pages; ++i) s->pages.push_back(e.pages[i]);
-      for (size_t i = best_pages; i < e.pages.size(); ++i) free_pages_.push_back(e.pages[i]);
-      s->n_cached = best_pages * KV_PAGE;
+    if (!chain.empty()) {
+      ++use_clock_;
+      for (int e : chain) {
+        s->pages.push_back(pcache_[(size_t)e].page);
+        pcache_[(size_t)e].last_use = use_clock_;
+      }
+      s->shared = chain;
+      s->n_cached = (int)chain.size() * KV_PAGE;
       ++stats_.prefix_hits;
       stats_.prefix_tokens_reused += s->n_cached;
-      prefix_cache_[best] = std::move(prefix_cache_.back());
-      prefix_cache_.pop_back();
     }
     for (int i = 0; i < fresh; ++i) { s->pages.push_back(free_pages_.back()); free_pages_.pop_back(); }
     s->t_admit = clk::now();
@@ -724,7 +794,7 @@ std::string Engine::stats_json() {
   }
   j.set("prefix_hits", Json(stats_.prefix_hits));
   j.set("prefix_tokens_reused", Json(stats_.prefix_tokens_reused));
-  j.set("prefix_cache_entries", Json((int)prefix_cache_.size()));
+  j.set("prefix_cache_pages", Json(pcache_pages_));
   j.set("kv_pages_free", Json((int)free_pages_.size()));
   j.set("kv_pages_total", Json(model_.limits().num_pages - 1));
   {

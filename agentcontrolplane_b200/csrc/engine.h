@@ -30,6 +30,7 @@ struct Sequence {
   int prompt_len = 0;
   int n_cached = 0;          // tokens whose K/V are in the cache
   std::vector<int> pages;
+  std::vector<int> shared;   // prefix-cache entries behind pages[0 .. shared.size()): not ours to free
   std::atomic<bool> cancelled{false};
   bool done = false, reported = false;
   int status = 0;            // HTTP-like, valid when done
@@ -39,15 +40,21 @@ struct Sequence {
   std::chrono::steady_clock::time_point t_submit, t_admit, t_first, t_done;
 };
 
-// KV retained after a sequence finishes: the context window of a Task is
-// append-only, so the next LLM step of the same Task (after its tool calls) starts with the same
-// tokens.  Only the PROMPT part is kept (those K/V came from the prefill arithmetic path, so a
-// cache hit is bit-identical to recomputing).  Move semantics: a hit hands the pages to the new
-// sequence; nothing is shared, nothing needs copy-on-write.
-struct CachedPrefix {
-  std::vector<int> tokens;  // tokens whose K/V the pages hold (positions 0..size-1)
-  std::vector<int> pages;
+// KV retained after a sequence finishes and SHARED between sequences: the
+// context window of a Task is append-only, so its next LLM step starts with the same tokens; and
+// every Task of an Agent starts with the same system prompt + tool schemas.  The cache is a chain
+// of whole PROMPT pages keyed by (parent page, the page's 32 tokens): a new sequence walks the
+// chain from its first token and maps every page it finds into its own page table — read-only,
+// reference-counted, any number of sequences at once.  Only prompt-path K/V is cached (prefill
+// arithmetic, batch invariant), so a hit is bit-identical to recomputing.
+struct CachedPage {
+  int page = -1;        // physical KV page (owned by the cache)
+  int parent = -1;      // entry index of the previous page of the chain, -1 for position 0
+  int children = 0;     // cached pages whose parent is this one
+  int active = 0;       // running sequences that map this page
+  uint64_t key = 0;
   uint64_t last_use = 0;
+  int tokens[32];       // KV_PAGE tokens (exact match on lookup: the hash only routes)
 };
 
 struct EngineStats {
@@ -109,11 +116,14 @@ class Engine {
   std::unordered_map<uint64_t, std::shared_ptr<Sequence>> all_;
   std::deque<uint64_t> finished_unreported_;
   std::vector<int> free_pages_;
-  std::vector<CachedPrefix> prefix_cache_;
+  std::vector<CachedPage> pcache_;               // entries; holes are chained through free_entries_
+  std::vector<int> free_entries_;
+  std::unordered_multimap<uint64_t, int> pcache_index_;   // chain key -> entry
+  int pcache_pages_ = 0;
   uint64_t use_clock_ = 0;
   bool prefix_cache_on_ = true;
-  size_t prefix_cache_max_ = 4096;
-  bool evict_one_locked();
+  int pcache_find_locked(int parent, const int* tokens) const;
+  bool evict_locked(int want);
   void retain_prefix_locked(Sequence& s);
   std::atomic<bool> stop_{false};
   bool broken_ = false;

@@ -45,4 +45,12 @@ for rep in range(int(os.environ.get("REPS", "2"))):
                       "decode_step_ms_p50": s.get("decode_step_ms_p50"), "decode_steps": s["decode_steps"],
                       "prefill_ms": round(s["prefill_ms"], 1), "prefill_tok_per_s": round(s["prefill_tokens"] / (s["prefill_ms"] / 1e3), 1),
                       "decode_ms": round(s["decode_ms"], 1)}), flush=True)
+if os.environ.get("ACP_PROFILE"):
+    prof = eng.stats().get("profile", {})
+    for phase in ("decode", "prefill"):
+        items = sorted(prof.get(phase, {}).items(), key=lambda kv: -kv[1]["ms"])
+        tot = sum(v["ms"] for _, v in items) or 1.0
+        print(f"--- {phase} profile (CUDA events per launch, warm cache, PDL overlap broken) total {tot:.2f} ms")
+        for k, v in items:
+            print(f"{k:24s} n={v['n']:6d} total={v['ms']:9.2f} ms  avg={1e3 * v['ms'] / v['n']:8.2f} us  {100 * v['ms'] / tot:5.1f}%")
 eng.close()

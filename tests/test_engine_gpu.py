@@ -160,6 +160,52 @@ def test_prefix_retention_is_bit_identical_to_recompute(eng):
     assert eng.stats()["prefix_hits"] == s1["prefix_hits"]
 
 
+def test_shared_prefix_pages_serve_many_sequences_at_once():
+    """§8(f) rank 1, second half: every Task of an Agent starts with the same system prompt + tool
+    schemas.  Once that prefix is cached, ANY number of concurrent sequences map the same physical
+    pages read-only (reference counted, page-chained by content); each result is bit-identical to a
+    cold engine's, only the tails are prefilled, and no page leaks."""
+    rng = np.random.default_rng(23)
+    base = _prompt(rng, 170)                                        # 5 whole pages + 10 tokens
+    tails = [[int(t) for t in rng.integers(0, 256, size=n)] for n in (3, 40, 22, 61, 9, 35, 50, 17, 28, 44, 5, 31)]
+    prompts = [base + t for t in tails]
+    cfg = {"model": "tiny-g2", "max_batch": 16, "kv_pages": 160, "max_tokens_per_step": 512, "max_pages_per_seq": 16}
+
+    def run_all(e, ps):
+        ts = [e.submit({"model": "tiny-g2", "max_tokens": 5, "acp": {"prompt_token_ids": p, "return_logits": 1}}) for p in ps]
+        out = []
+        for t in ts:
+            assert e.wait(t, 120000)
+            lg = e.logits(t, 1, 128256)
+            st, body = e.result(t)
+            assert st == 200, body
+            out.append((body["acp"]["token_ids"], lg))
+        return out
+
+    with Engine(dict(cfg, prefix_cache=False)) as cold:
+        want = run_all(cold, prompts)
+    with Engine(cfg) as e:
+        run_all(e, [base])                                          # seeds the cache: 5 pages
+        s0 = e.stats()
+        assert s0["prefix_cache_pages"] == 5
+        got = run_all(e, prompts)                                   # 12 sequences share them concurrently
+        s1 = e.stats()
+        assert s1["prefix_hits"] - s0["prefix_hits"] == 12
+        assert s1["prefix_tokens_reused"] - s0["prefix_tokens_reused"] == 12 * 160
+        assert s1["prefill_tokens"] - s0["prefill_tokens"] == sum(len(p) for p in prompts) - 12 * 160
+        for (a, la), (b, lb) in zip(got, want):
+            assert a == b and np.array_equal(la, lb)
+        # conservation: every page is either free or held by the cache, and the shared chain was
+        # extended by the tails' own whole pages (no duplicates of the 5 common pages)
+        assert s1["kv_pages_free"] + s1["prefix_cache_pages"] == s1["kv_pages_total"] and s1["running"] == 0
+        assert 5 < s1["prefix_cache_pages"] <= 5 + sum((170 + len(t)) // 32 - 5 for t in tails)
+        # a pool too small for everything evicts cached leaves instead of failing
+        big = [_prompt(rng, 400) for _ in range(12)]
+        run_all(e, big)
+        s2 = e.stats()
+        assert s2["kv_pages_free"] + s2["prefix_cache_pages"] == s2["kv_pages_total"]
+
+
 @pytest.mark.parametrize("mode", ["item", "chunked"])
 def test_decode_attention_modes_agree(eng, mode):
     """Both decode-attention paths (one CTA per item / chunked + merge) give the oracle's tokens on
