@@ -569,11 +569,17 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
         if (t.Status.Phase == "ReadyForLLM") {
           const auto s0 = std::chrono::steady_clock::now();
           task::ClientFactory factory = [&](std::string* cerr) -> std::unique_ptr<llmclient::LLMClient> {
-            auto c = llmclient::NewLLMClient(provider, "test-key", bc, engine, cerr);
-            if (c && provider == "local" && tool_loop && steps == 0 && !tools.empty()) {
-              // scripted step 1: force the model's output to be a tool call (BASELINE config 3)
-              const std::string call = "{\"name\": \"" + tools[0].Function.Name +
-                                       "\", \"parameters\": {\"url\": \"https://api.example.com/data\"}}";
+            const bool scripted = provider == "local" && tool_loop && steps == 0 && !tools.empty();
+            // scripted step 1: force the model's output to be a tool call (BASELINE config 3)
+            const std::string call = scripted ? "{\"name\": \"" + tools[0].Function.Name +
+                                                    "\", \"parameters\": {\"url\": \"https://api.example.com/data\"}}"
+                                              : std::string();
+            llmclient::BaseConfig step_bc = bc;
+            // the call must fit the completion budget or it is cut mid-JSON and parsed as plain content
+            // (one token per byte under the synthetic vocabulary): never fewer decode steps than configured
+            if (scripted && step_bc.MaxTokens < (int)call.size() + 1) step_bc.MaxTokens = (int)call.size() + 1;
+            auto c = llmclient::NewLLMClient(provider, "test-key", step_bc, engine, cerr);
+            if (c && scripted) {
               Json ext = Json::object();
               Json forced = Json::array();
               for (unsigned char ch : call) forced.push(Json((int)ch));

@@ -284,6 +284,7 @@ def main():
                        "prefix_hits": s1.get("prefix_hits", 0), "prefix_tokens_reused": s1.get("prefix_tokens_reused", 0),
                        "l2": (f"inputs larger than L2: every decode step streams {s1['decode_bytes_algorithmic'] / max(1, s1['decode_steps']) / 1e9:.1f} GB "
                               "of weights + KV (all GPUs) through a 126 MB L2 per GPU"),
+                       "llm_steps_per_task": total_reconciles / (world * n_tasks * args.steps),
                        "final_phases": phases},
             "decode_tokens_per_s": total_decode_tokens / dec_max if dec_max > 0 else 0.0,  # all ranks / max decode time
             "decode_tokens_per_s_rank0": s1["decode_tokens"] / dec_s if dec_s > 0 else 0.0,

@@ -141,6 +141,21 @@ def test_tool_loop_two_llm_steps(eng):
     r = host.hostsim_run({"tasks": 16, "workers": 16, "provider": "local", "model": "tiny", "max_tokens": 96,
                           "prompt_tokens": 0, "tools": 2, "tool_loop": True, "seed": 5}, eng)
     assert r["reconciles"] == 32 and r["final_phases"] == {"FinalAnswer": 16}
+    # BASELINE config 3's shape: max_tokens 64 is SHORTER than the scripted tool call under the byte-level
+    # vocabulary; the scripted step must still end in ToolCallsPending (2 LLM steps per Task), the second
+    # turn re-uses the first turn's window from the shared prefix cache, later Tasks the agent's preamble
+    eng.stats_reset()
+    cfg = {"tasks": 8, "workers": 8, "provider": "local", "model": "tiny", "max_tokens": 64, "prompt_tokens": 512,
+           "tools": 2, "tool_loop": True, "seed": 6}
+    r = host.hostsim_run(cfg, eng)
+    assert r["reconciles"] == 16 and r["final_phases"] == {"FinalAnswer": 8}
+    s0 = eng.stats()
+    r = host.hostsim_run(dict(cfg, seed=7), eng)
+    s1 = eng.stats()
+    assert r["reconciles"] == 16
+    assert s1["prefix_hits"] - s0["prefix_hits"] == 16              # both turns of every Task hit
+    window = r["prompt_tokens"]
+    assert s1["prefix_tokens_reused"] - s0["prefix_tokens_reused"] >= 8 * (640 + (window // 32) * 32)
 
 
 def test_cancel_and_sampling(eng):
