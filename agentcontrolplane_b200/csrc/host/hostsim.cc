@@ -471,6 +471,20 @@ extern "C" int acp_host_checkpoint_index(const char* path, char** out_json) {
   return ret_json(out, out_json);
 }
 
+extern "C" int acp_host_checkpoint_tensor_bf16(const char* path, const char* name, uint16_t* out, size_t max_elems,
+                                               size_t* n_elems) {
+  if (!path || !name || !n_elems) return ACP_ERR_INVALID;
+  acp::Checkpoint ck;
+  std::string err;
+  if (!ck.open(path, &err)) return ACP_ERR_INVALID;
+  const acp::StTensor* t = ck.find(name);
+  if (!t) return ACP_ERR_NOT_FOUND;
+  *n_elems = (size_t)t->numel();
+  if (!out) return ACP_OK;
+  if (max_elems < *n_elems) return ACP_ERR_INVALID;
+  return acp::st_to_bf16(*t, 0, *n_elems, out) ? ACP_OK : ACP_ERR_INVALID;
+}
+
 extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char** result_json_out) {
   if (!config_json || !result_json_out) return ACP_ERR_INVALID;
   Json cfg;

@@ -173,3 +173,17 @@ def render_prompt_with(request: dict, tokenizer_path: str | None) -> dict:
     if rc != 0:
         raise ValueError(out.get("error", f"acp_host_render_prompt_with failed with {rc}"))
     return out
+
+
+def checkpoint_tensor_bf16(path: str, name: str):
+    """bf16 bit patterns (numpy uint16) of one checkpoint tensor as the loader would upload it."""
+    import numpy as np
+    l = lib()
+    l.acp_host_checkpoint_tensor_bf16.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                  ctypes.POINTER(ctypes.c_size_t)]
+    n = ctypes.c_size_t()
+    _check(l.acp_host_checkpoint_tensor_bf16(path.encode(), name.encode(), None, 0, ctypes.byref(n)), "acp_host_checkpoint_tensor_bf16")
+    out = np.empty(n.value, dtype=np.uint16)
+    _check(l.acp_host_checkpoint_tensor_bf16(path.encode(), name.encode(), out.ctypes.data_as(ctypes.c_void_p), n.value,
+                                             ctypes.byref(n)), "acp_host_checkpoint_tensor_bf16")
+    return out

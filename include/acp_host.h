@@ -84,6 +84,10 @@ int acp_host_render_prompt_with(const char* tokenizer_path, const char* chat_req
  *             "eps":…, "tied_embeddings":…, "rope_inv_freq":[64 floats]}}
  * or {"error": "..."} with return code ACP_ERR_INVALID. */
 int acp_host_checkpoint_index(const char* path, char** out_json);
+/* One tensor of the checkpoint as the bf16 bits the loader uploads (BF16 verbatim; F16 / F32 rounded
+ * to nearest even).  out == NULL: only *n_elems is set.  ACP_ERR_NOT_FOUND: no such tensor. */
+int acp_host_checkpoint_tensor_bf16(const char* path, const char* name, uint16_t* out, size_t max_elems,
+                                    size_t* n_elems);
 
 #ifdef __cplusplus
 }

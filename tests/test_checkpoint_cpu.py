@@ -80,3 +80,23 @@ def test_unusable_checkpoints_are_rejected_with_a_reason(tmp_path, breakage, nee
             f.truncate(64)
     with pytest.raises(ValueError, match=needle):
         host.checkpoint_index(d)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_dtype_conversion_is_round_to_nearest_even(tmp_path, dtype):
+    """F32 / F16 checkpoints are converted on the host exactly as torch converts to bfloat16
+    (round to nearest even; subnormals, infinities and NaN included); BF16 passes through."""
+    from safetensors.torch import save_file
+    rng = np.random.default_rng(3)
+    vals = np.concatenate([rng.standard_normal(4096).astype(np.float32) * np.float32(0.02),
+                           np.array([0.0, -0.0, 1.0, -1.0, 1.00390625, 1.0078125, 1.01171875, 3.3895314e38, 65504.0, 6.1e-5, 5.96e-8,
+                                     1e-40, -1e-40, np.inf, -np.inf, np.nan, 2.0 ** -126, 2.0 ** -133], dtype=np.float32)])
+    with np.errstate(over="ignore"):
+        t = torch.from_numpy(vals).to(dtype)
+    f = str(tmp_path / "t.safetensors")
+    save_file({"x": t}, f)
+    got = host.checkpoint_tensor_bf16(f, "x")
+    want = t.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    nan = np.isnan(t.float().numpy())
+    assert np.array_equal(got[~nan], want[~nan])
+    assert ((got[nan] & 0x7F80) == 0x7F80).all() and ((got[nan] & 0x007F) != 0).all()      # NaN stays NaN
