@@ -48,6 +48,9 @@ class LlamaConfig:
     eps: float = 1e-5
     w_std: float = 0.02
     max_pos: int = 8192
+    # Llama-3.1 "llama3" RoPE frequency scaling: (factor, low_freq_factor, high_freq_factor,
+    # original_max_position_embeddings) or None; same formula as csrc/model.cu rope_inv_freq()
+    rope_scaling: tuple | None = None
 
     @property
     def q_dim(self):
@@ -69,13 +72,28 @@ PRESETS = {
 }
 
 
+def rope_inv_freq(cfg: LlamaConfig) -> np.ndarray:
+    """fp32 inverse frequencies, computed in double like csrc/model.cu rope_inv_freq(): plain
+    theta^(-2i/d), then (rope_scaling) wavelengths above orig_max/low are slowed by `factor`, those
+    between orig_max/high and orig_max/low are interpolated (transformers' "llama3" rope type)."""
+    half = cfg.head_dim // 2
+    f = cfg.rope_theta ** (-(np.arange(half, dtype=np.float64) * 2.0) / cfg.head_dim)
+    if cfg.rope_scaling is not None:
+        factor, low, high, orig = (float(v) for v in cfg.rope_scaling)
+        wavelen = 2.0 * np.pi / f
+        low_wl, high_wl = orig / low, orig / high
+        smooth = (orig / wavelen - low) / (high - low)
+        mid = (1.0 - smooth) * f / factor + smooth * f
+        f = np.where(wavelen > low_wl, f / factor, np.where(wavelen < high_wl, f, mid))
+    return f.astype(np.float32)
+
+
 def rope_tables(cfg: LlamaConfig, max_pos: int):
     """cos/sin [max_pos][head_dim/2] fp32 — the same recipe as csrc/model.cu build_rope_table():
     inv_freq = fp32(theta^(-2i/d)) from double; angle = fp32(pos) * inv_freq (fp32 multiply);
     cos/sin evaluated in double on that fp32 angle, rounded to fp32."""
     half = cfg.head_dim // 2
-    inv = (cfg.rope_theta ** (-(np.arange(half, dtype=np.float64) * 2.0) / cfg.head_dim)).astype(
-        np.float32)
+    inv = rope_inv_freq(cfg)
     ang = (np.arange(max_pos, dtype=np.float32)[:, None] * inv[None, :]).astype(np.float32)
     return np.cos(ang.astype(np.float64)).astype(np.float32), np.sin(ang.astype(np.float64)).astype(
         np.float32)

@@ -60,6 +60,12 @@ def test_rope_frequencies_match_oracle_and_hf(tmp_path):
     want, _ = ROPE_INIT_FUNCTIONS["llama3"](hf, "cpu")
     np.testing.assert_allclose(inv31, want.double().numpy(), rtol=3e-7)
     assert inv31[-1] < inv[-1] / 7.9          # the lowest frequency really is slowed 8x
+    # engine (C++) and oracle (numpy) build the SAME fp32 table, bit for bit, scaled or not
+    import dataclasses
+    from oracle.llama_oracle import rope_inv_freq
+    got31 = np.array(host.checkpoint_index(d2)["model"]["rope_inv_freq"], dtype=np.float32)
+    assert np.array_equal(got31, rope_inv_freq(dataclasses.replace(CFG, rope_scaling=(8.0, 1.0, 4.0, 8192))))
+    assert np.array_equal(inv, rope_inv_freq(CFG))
 
 
 @pytest.mark.parametrize("breakage,needle", [

@@ -33,6 +33,22 @@ def test_fp32_oracle_matches_huggingface_fixture(name):
     assert toks == [int(t) for t in GOLD[f"{name}.greedy"]]
 
 
+def test_llama31_rope_scaling_matches_huggingface_fixture():
+    """Llama-3.1 checkpoints carry rope_scaling {"rope_type": "llama3"}: the oracle's scaled
+    frequencies and forward pass against transformers (fixture: make_rope_scaling_golden.py)."""
+    import dataclasses
+    from oracle.llama_oracle import rope_inv_freq
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "llama_rope31_golden.npz"))
+    cfg = dataclasses.replace(PRESETS["tiny"], name="tiny-rope31", rope_scaling=tuple(g["scaling"]))
+    np.testing.assert_allclose(rope_inv_freq(cfg).astype(np.float64), g["inv_freq"], rtol=3e-7)
+    logits = LlamaOracle(cfg, SEED, mode="fp32").forward(g["prompt"], all_logits=True)
+    assert np.max(np.abs(logits[:, COLS] - g["prompt_logits"])) < 2e-4
+    assert np.array_equal(np.argmax(logits, axis=-1), g["greedy_next"])
+    # and the scaling is not a no-op at these positions
+    plain = LlamaOracle(PRESETS["tiny"], SEED, mode="fp32").forward(g["prompt"], all_logits=True)
+    assert np.max(np.abs(plain[:, COLS] - g["prompt_logits"])) > 0.05
+
+
 def test_bf16_mode_stays_close_to_fp32_mode():
     cfg = PRESETS["tiny"]
     prompt = GOLD["tiny.prompt"]
