@@ -11,6 +11,8 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <set>
+#include <condition_variable>
 #include <chrono>
 #include <thread>
 #include "../chat.h"
@@ -88,11 +90,25 @@ struct StubServer {
   std::atomic<bool> stop{false};
   std::thread thread;
   std::atomic<long long> served{0};
+  // connection handlers are detached threads: stop() shuts their sockets down and waits for the
+  // last one to leave before the server object is freed (found by the ThreadSanitizer build)
+  std::mutex conn_mu;
+  std::condition_variable conn_cv;
+  std::set<int> conn_fds;
 };
 StubServer* g_stubs[16] = {nullptr};
 std::mutex g_stub_mu;
 
+void serve_conn_loop(StubServer* s, int fd);
 void serve_conn(StubServer* s, int fd) {
+  serve_conn_loop(s, fd);
+  std::lock_guard<std::mutex> lk(s->conn_mu);
+  s->conn_fds.erase(fd);
+  close(fd);
+  s->conn_cv.notify_all();
+}
+
+void serve_conn_loop(StubServer* s, int fd) {
   // HTTP/1.1 keep-alive: serve requests on this connection until the peer closes it
   std::string buf_acc;
   char buf[16384];
@@ -100,7 +116,7 @@ void serve_conn(StubServer* s, int fd) {
     size_t he;
     while ((he = buf_acc.find("\r\n\r\n")) == std::string::npos) {
       ssize_t n = recv(fd, buf, sizeof buf, 0);
-      if (n <= 0) { close(fd); return; }
+      if (n <= 0) return;
       buf_acc.append(buf, (size_t)n);
     }
     size_t cl = buf_acc.find("Content-Length:");
@@ -108,7 +124,7 @@ void serve_conn(StubServer* s, int fd) {
     const size_t need = he + 4 + len;
     while (buf_acc.size() < need) {
       ssize_t n = recv(fd, buf, sizeof buf, 0);
-      if (n <= 0) { close(fd); return; }
+      if (n <= 0) return;
       buf_acc.append(buf, (size_t)n);
     }
     buf_acc.erase(0, need);
@@ -117,7 +133,7 @@ void serve_conn(StubServer* s, int fd) {
     size_t off = 0;
     while (off < resp.size()) {
       ssize_t n = send(fd, resp.data() + off, resp.size() - off, MSG_NOSIGNAL);
-      if (n <= 0) { close(fd); return; }
+      if (n <= 0) return;
       off += (size_t)n;
     }
     ++s->served;
@@ -132,6 +148,10 @@ void stub_loop(StubServer* s) {
     if (fd < 0) { if (s->stop) break; continue; }
     int one = 1;
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+    {
+      std::lock_guard<std::mutex> lk(s->conn_mu);
+      s->conn_fds.insert(fd);
+    }
     std::thread(serve_conn, s, fd).detach();  // one goroutine per connection, like net/http
   }
 }
@@ -177,7 +197,11 @@ extern "C" void acp_host_stub_server_stop(int handle) {
   shutdown(s->listen_fd, SHUT_RDWR);
   close(s->listen_fd);
   if (s->thread.joinable()) s->thread.join();
-  std::this_thread::sleep_for(std::chrono::milliseconds(20));  // let detached handlers drain
+  {
+    std::unique_lock<std::mutex> lk(s->conn_mu);
+    for (int fd : s->conn_fds) shutdown(fd, SHUT_RDWR);   // wakes handlers blocked in recv on keep-alive sockets
+    s->conn_cv.wait(lk, [&] { return s->conn_fds.empty(); });
+  }
   delete s;
 }
 
