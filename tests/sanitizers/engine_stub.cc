@@ -1,5 +1,5 @@
 // Host-only stand-in for the CUDA engine behind include/acp_infer.h, for the ThreadSanitizer build
-// of the host side (tests/test_tsan_cpu.py).  It answers every submitted request from a worker
+// of the host side (tests/test_sanitizers_cpu.py).  It answers every submitted request from a worker
 // thread after a short delay, so LocalClient's submit / wait / result hand-off, the Task state
 // machine, the object store and the HTTP client/server are exercised under real concurrency with
 // no GPU.  TEST INFRASTRUCTURE: never linked into libacp_infer.so.
