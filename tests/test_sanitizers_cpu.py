@@ -33,6 +33,31 @@ def test_host_side_is_race_free_under_tsan(tmp_path):
         assert leg in run.stdout
 
 
+def test_real_scheduler_over_a_fake_model_under_tsan(tmp_path):
+    """csrc/engine.cc (scheduler, paged-KV allocator, shared prefix cache, cancellation, wait/poll)
+    and c_api.cc are compiled UNCHANGED against tests/sanitizers/fake_model.cc — a stand-in Model
+    whose emitted tokens are a hash chain over the K/V slots reached THROUGH the page tables the
+    scheduler builds — and driven by 24 producer threads with shared prefixes, a KV pool that forces
+    queueing and eviction, and cancellations.  Every response must equal the cache-free reference,
+    no page may leak, and ThreadSanitizer must stay silent."""
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    san = os.path.join(ROOT, "tests", "sanitizers")
+    exe = str(tmp_path / "acp_engine_sim")
+    srcs = [os.path.join(san, "engine_sim_main.cc"), os.path.join(san, "fake_model.cc")] + [
+        os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc")]
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-I" + san, "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
+           "-I/usr/local/cuda/include", *srcs, "-o", exe, "-lpthread"]
+    build = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if build.returncode != 0 and ("tsan" in build.stderr.lower() or "sanitize" in build.stderr.lower()):
+        pytest.skip("ThreadSanitizer runtime not available: " + build.stderr[-300:])
+    assert build.returncode == 0, build.stderr[-3000:]
+    for _ in range(2):
+        run = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, TSAN_OPTIONS="exitcode=66"))
+        assert "ThreadSanitizer" not in run.stderr, run.stderr[-6000:]
+        assert run.returncode == 0 and "bad=0" in run.stdout, (run.returncode, run.stdout[-1500:], run.stderr[-3000:])
+
+
 def test_untrusted_input_parsers_under_asan_ubsan(tmp_path):
     """Request bodies, completion text, tokenizer input and checkpoint / tokenizer.json files are
     untrusted bytes: a deterministic mutation fuzzer (tests/sanitizers/fuzz_main.cc) runs them through the
