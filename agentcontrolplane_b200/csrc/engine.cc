@@ -427,6 +427,51 @@ bool Engine::evict_locked(int want) {
   return any;
 }
 
+// caller holds mu_.  New cache entry for `page` holding `toks` behind `parent` (-1: position 0).
+int Engine::pcache_insert_locked(int parent, const int* toks, int page) {
+  int idx;
+  if (!free_entries_.empty()) { idx = free_entries_.back(); free_entries_.pop_back(); }
+  else { idx = (int)pcache_.size(); pcache_.emplace_back(); }
+  CachedPage& e = pcache_[(size_t)idx];
+  e.page = page;
+  e.parent = parent;
+  e.children = 0;
+  e.active = 0;
+  e.key = chain_key(parent < 0 ? 0 : pcache_[(size_t)parent].key, toks);
+  e.last_use = use_clock_;
+  memcpy(e.tokens, toks, sizeof e.tokens);
+  if (parent >= 0) ++pcache_[(size_t)parent].children;
+  pcache_index_.emplace(e.key, idx);
+  ++pcache_pages_;
+  return idx;
+}
+
+// caller holds mu_.  Publishes the whole PROMPT pages of a running sequence whose K/V the last
+// prefill step completed: from now on any admitted request maps them (the owner keeps using them
+// through its page table like any other shared page).  If an identical page was published by a
+// twin in the meantime, the sequence switches to the cached page and frees its own — both hold the
+// same bits (prompt K/V is batch invariant).
+void Engine::publish_prefix_locked(Sequence& s) {
+  if (!prefix_cache_on_) return;
+  const int whole = std::min(s.prompt_len, s.n_cached) / KV_PAGE;
+  if ((int)s.shared.size() >= whole) return;
+  ++use_clock_;
+  for (int i = (int)s.shared.size(); i < whole && i < (int)s.pages.size(); ++i) {
+    const int parent = i == 0 ? -1 : s.shared[(size_t)i - 1];
+    const int* toks = s.tokens.data() + (size_t)i * KV_PAGE;
+    int e = pcache_find_locked(parent, toks);
+    if (e >= 0) {
+      free_pages_.push_back(s.pages[(size_t)i]);
+      s.pages[(size_t)i] = pcache_[(size_t)e].page;
+    } else {
+      e = pcache_insert_locked(parent, toks, s.pages[(size_t)i]);
+    }
+    ++pcache_[(size_t)e].active;
+    pcache_[(size_t)e].last_use = use_clock_;
+    s.shared.push_back(e);
+  }
+}
+
 // caller holds mu_.  Donates the whole pages that hold the PROMPT's K/V to the prefix cache (pages
 // whose content is already cached are simply freed); everything else goes back to the free list.
 void Engine::retain_prefix_locked(Sequence& s) {
@@ -451,20 +496,7 @@ void Engine::retain_prefix_locked(Sequence& s) {
       parent = have;
       continue;
     }
-    int idx;
-    if (!free_entries_.empty()) { idx = free_entries_.back(); free_entries_.pop_back(); }
-    else { idx = (int)pcache_.size(); pcache_.emplace_back(); }
-    CachedPage& e = pcache_[(size_t)idx];
-    e.page = s.pages[(size_t)i];
-    e.parent = parent;
-    e.children = 0;
-    e.active = 0;
-    e.key = chain_key(parent < 0 ? 0 : pcache_[(size_t)parent].key, toks);
-    e.last_use = use_clock_;
-    memcpy(e.tokens, toks, sizeof e.tokens);
-    if (parent >= 0) ++pcache_[(size_t)parent].children;
-    pcache_index_.emplace(e.key, idx);
-    ++pcache_pages_;
+    const int idx = pcache_insert_locked(parent, toks, s.pages[(size_t)i]);
     parent = idx;
   }
   s.pages.clear();
@@ -517,6 +549,22 @@ void Engine::admit_locked() {
         chain.push_back(e);
         parent = e;
       }
+    }
+    // in-flight dedup: if a RUNNING sequence is about to publish the very next page of this prompt
+    // (same tokens up to and including it, not yet published), wait for it instead of prefilling a
+    // copy — a burst of Tasks of one Agent then computes the shared system prompt + tool schemas
+    // once.  FIFO is kept (everything behind waits too); the owner publishes after its next prefill
+    // step, or leaves running_ (finished / cancelled), so the condition clears by itself.
+    if (prefix_cache_on_) {
+      const int c = (int)chain.size();
+      const int next_end = (c + 1) * KV_PAGE;
+      bool in_flight = false;
+      if (next_end <= s->prompt_len - 1)
+        for (const auto& r : running_) {
+          if (r->prompt_len < next_end || (int)r->shared.size() > c || r->n_cached >= r->prompt_len) continue;
+          if (memcmp(r->tokens.data(), s->tokens.data(), (size_t)next_end * sizeof(int)) == 0) { in_flight = true; break; }
+        }
+      if (in_flight) { ++stats_.prefix_deferrals; break; }
     }
     const int fresh = need - (int)chain.size();
     // pin the chain while evicting to make room (an entry with users is never evicted)
@@ -680,6 +728,8 @@ bool Engine::step() {
     if (stats_.decode_step_ms.size() < 65536) stats_.decode_step_ms.push_back(step_ms);
   }
   for (int b = 0; b < B; ++b) part[b]->n_cached += take[b];
+  if (prefill)
+    for (int b = 0; b < B; ++b) publish_prefix_locked(*part[b]);
   bool any_done = false;
   for (int i = 0; i < ns; ++i) {
     Sequence& s = *part[sample_seq[i]];
@@ -795,6 +845,7 @@ std::string Engine::stats_json() {
   j.set("prefix_hits", Json(stats_.prefix_hits));
   j.set("prefix_tokens_reused", Json(stats_.prefix_tokens_reused));
   j.set("prefix_cache_pages", Json(pcache_pages_));
+  j.set("prefix_deferrals", Json(stats_.prefix_deferrals));
   j.set("kv_pages_free", Json((int)free_pages_.size()));
   j.set("kv_pages_total", Json(model_.limits().num_pages - 1));
   {

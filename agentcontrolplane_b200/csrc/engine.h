@@ -58,7 +58,7 @@ struct CachedPage {
 };
 
 struct EngineStats {
-  long long prefix_hits = 0, prefix_tokens_reused = 0;
+  long long prefix_hits = 0, prefix_tokens_reused = 0, prefix_deferrals = 0;
   long long decode_steps = 0, decode_tokens = 0, decode_ctx_tokens = 0;
   long long prefill_steps = 0, prefill_tokens = 0;
   double decode_ms = 0, prefill_ms = 0;
@@ -123,6 +123,8 @@ class Engine {
   uint64_t use_clock_ = 0;
   bool prefix_cache_on_ = true;
   int pcache_find_locked(int parent, const int* tokens) const;
+  int pcache_insert_locked(int parent, const int* tokens, int page);
+  void publish_prefix_locked(Sequence& s);
   bool evict_locked(int want);
   void retain_prefix_locked(Sequence& s);
   std::atomic<bool> stop_{false};

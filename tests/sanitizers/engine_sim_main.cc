@@ -39,7 +39,9 @@ int main() {
   std::atomic<int> bad{0}, ok{0}, cancelled{0};
   auto worker = [&](int tid) {
     for (int i = 0; i < kPerThread; ++i) {
-      const std::vector<int> prompt = make_prompt(17, (tid + i) % 5, tid * 1000 + i);
+      // every 7th request repeats a prompt other threads send too (twins: the publish-time switch to
+      // an already cached page), the rest share only their agent's preamble
+      const std::vector<int> prompt = (i % 7 == 3) ? make_prompt(17, i % 5, 424242 + i % 3) : make_prompt(17, (tid + i) % 5, tid * 1000 + i);
       Json ids = Json::array();
       for (int t : prompt) ids.push(Json(t));
       Json acp = Json::object();
@@ -85,6 +87,74 @@ int main() {
       }
     }
   };
+  // phase 0: a cold burst — 48 Tasks of ONE agent (same 288-token preamble, different tails) submitted
+  // back to back before anything is cached: the first computes the preamble, the rest must wait for its
+  // pages (in-flight dedup) instead of prefilling 47 copies
+  {
+    std::vector<std::string> bodies;
+    std::vector<std::vector<int>> prompts;
+    for (int i = 0; i < 48; ++i) {
+      std::vector<int> p = {128000};
+      uint64_t h = 99;
+      for (int k = 0; k < 287; ++k) { h = fakemodel::mix(h); p.push_back(32 + (int)(h % 90)); }
+      h = fakemodel::mix(5000 + (uint64_t)i);
+      for (int k = 0; k < 20 + i % 30; ++k) { h = fakemodel::mix(h); p.push_back(32 + (int)(h % 90)); }
+      Json ids = Json::array();
+      for (int t : p) ids.push(Json(t));
+      Json acp = Json::object();
+      acp.set("prompt_token_ids", ids);
+      Json req = Json::object();
+      req.set("model", Json("sim"));
+      req.set("max_tokens", Json(kMaxTokens));
+      req.set("acp", acp);
+      bodies.push_back(req.dump());
+      prompts.push_back(p);
+    }
+    {  // the blocker: an unrelated 420-token prompt whose prefill step keeps the scheduler busy (fake_model.cc)
+      std::vector<int> p = {128000};
+      uint64_t h = 7;
+      for (int k = 0; k < 419; ++k) { h = fakemodel::mix(h); p.push_back(32 + (int)(h % 90)); }
+      Json ids = Json::array();
+      for (int t : p) ids.push(Json(t));
+      Json acp = Json::object();
+      acp.set("prompt_token_ids", ids);
+      Json req = Json::object();
+      req.set("model", Json("sim"));
+      req.set("max_tokens", Json(4));
+      req.set("acp", acp);
+      bodies.push_back(req.dump());
+      prompts.push_back(p);
+      std::swap(bodies.front(), bodies.back());
+      std::swap(prompts.front(), prompts.back());
+    }
+    std::vector<uint64_t> tickets(bodies.size());
+    acp_infer_submit(e, bodies[0].c_str(), bodies[0].size(), &tickets[0]);
+    std::this_thread::sleep_for(std::chrono::milliseconds(5));      // the blocker's prefill step is now running
+    for (size_t i = 1; i < bodies.size(); ++i) acp_infer_submit(e, bodies[i].c_str(), bodies[i].size(), &tickets[i]);
+    for (size_t i = 0; i < bodies.size(); ++i) {
+      acp_infer_wait(e, tickets[i], -1);
+      char* out = nullptr; size_t len = 0; int status = 0;
+      acp_infer_result(e, tickets[i], &out, &len, &status);
+      const std::string resp(out ? out : "", len);
+      acp_infer_free(out);
+      const std::vector<int> want = fakemodel::generate(prompts[i], i == 0 ? 4 : kMaxTokens);
+      std::vector<int> got;
+      Json j; std::string err;
+      if (status == 200 && Json::parse(resp, &j, &err))
+        for (const Json& t : j.get("acp").get("token_ids").items()) got.push_back((int)t.as_int());
+      const bool empty_ok = status == 422 && want.size() == 1 && want[0] == 128009;
+      if (!(empty_ok || (status == 200 && got == want))) { fprintf(stderr, "cold burst: request %zu wrong (status %d)\n", i, status); ++bad; }
+    }
+    char* sj0 = nullptr;
+    acp_infer_stats(e, &sj0);
+    Json s0; std::string err0;
+    Json::parse(std::string(sj0), &s0, &err0);
+    acp_infer_free(sj0);
+    const long long pf = s0.get("prefill_tokens").as_int(), df = s0.get("prefix_deferrals").as_int();
+    printf("cold burst: prefill_tokens=%lld (48 cold copies would be %d) deferrals=%lld hits=%lld\n", pf, 48 * 288, df,
+           (long long)s0.get("prefix_hits").as_int());
+    if (df < 1 || pf > 420 + 48 * 288 / 3) { fprintf(stderr, "in-flight dedup did not engage\n"); ++bad; }
+  }
   std::vector<std::thread> th;
   for (int t = 0; t < kThreads; ++t) th.emplace_back(worker, t);
   for (auto& t : th) t.join();
@@ -96,8 +166,9 @@ int main() {
   acp_infer_free(sj);
   const long long free_pages = s.get("kv_pages_free").as_int(), cached = s.get("prefix_cache_pages").as_int(),
                   total = s.get("kv_pages_total").as_int(), hits = s.get("prefix_hits").as_int();
-  printf("engine-sim: ok=%d cancelled=%d bad=%d prefix_hits=%lld reused=%lld pages free=%lld cached=%lld total=%lld running=%lld\n",
-         ok.load(), cancelled.load(), bad.load(), hits, (long long)s.get("prefix_tokens_reused").as_int(), free_pages, cached, total,
+  printf("engine-sim: ok=%d cancelled=%d bad=%d prefix_hits=%lld reused=%lld deferrals=%lld prefill_tokens=%lld pages free=%lld cached=%lld total=%lld running=%lld\n",
+         ok.load(), cancelled.load(), bad.load(), hits, (long long)s.get("prefix_tokens_reused").as_int(),
+         (long long)s.get("prefix_deferrals").as_int(), (long long)s.get("prefill_tokens").as_int(), free_pages, cached, total,
          (long long)s.get("running").as_int());
   int rc = 0;
   if (bad != 0) rc = 1;

@@ -117,7 +117,9 @@ int Model::forward(const StepInput& in) {
     h_tokens_[s] = fakemodel::next_token(ctx.data(), n);
   }
   launches_ += 8;
-  std::this_thread::sleep_for(std::chrono::microseconds(in.decode ? 150 : 400));   // leave room for producers to race the step
+  // leave room for producers to race the step; a step of >= 400 rows is the checker's "blocker": it
+  // holds the scheduler long enough for a whole burst to queue up behind it
+  std::this_thread::sleep_for(std::chrono::microseconds(in.decode ? 150 : (in.T >= 400 ? 40000 : 400)));
   return 0;
 }
 
