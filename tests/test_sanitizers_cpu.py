@@ -69,8 +69,9 @@ def test_real_scheduler_over_a_fake_model_under_tsan(binaries):
     queueing and eviction, and cancellations.  Every response must equal the cache-free reference,
     no page may leak, and ThreadSanitizer must stay silent."""
     exe = _exe(binaries, "engine_sim")
-    for _ in range(2):
-        run = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, TSAN_OPTIONS="exitcode=66"))
+    for extra in ({}, {"ACP_SIM_NO_CACHE": "1"}):
+        run = subprocess.run([exe], capture_output=True, text=True, timeout=300,
+                             env=dict(os.environ, TSAN_OPTIONS="exitcode=66", **extra))
         assert "ThreadSanitizer" not in run.stderr, run.stderr[-6000:]
         assert run.returncode == 0 and "bad=0" in run.stdout, (run.returncode, run.stdout[-1500:], run.stderr[-3000:])
 
