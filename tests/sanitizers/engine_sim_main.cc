@@ -38,13 +38,14 @@ int main() {
                              : "{\"model\": \"sim\", \"max_batch\": 24, \"kv_pages\": 300, \"max_tokens_per_step\": 512, "
                                "\"max_pages_per_seq\": 16, \"prefix_cache\": true}";
   if (acp_infer_init(cfg, &e) != 0) { fprintf(stderr, "init failed\n"); return 1; }
+  const uint64_t sim_seed = getenv("ACP_SIM_SEED") ? strtoull(getenv("ACP_SIM_SEED"), nullptr, 10) : 17;
   const int kThreads = 24, kPerThread = 60, kMaxTokens = 24;
   std::atomic<int> bad{0}, ok{0}, cancelled{0};
   auto worker = [&](int tid) {
     for (int i = 0; i < kPerThread; ++i) {
       // every 7th request repeats a prompt other threads send too (twins: the publish-time switch to
       // an already cached page), the rest share only their agent's preamble
-      const std::vector<int> prompt = (i % 7 == 3) ? make_prompt(17, i % 5, 424242 + i % 3) : make_prompt(17, (tid + i) % 5, tid * 1000 + i);
+      const std::vector<int> prompt = (i % 7 == 3) ? make_prompt(sim_seed, i % 5, 424242 + i % 3) : make_prompt(sim_seed, (tid + i) % 5, tid * 1000 + i);
       Json ids = Json::array();
       for (int t : prompt) ids.push(Json(t));
       Json acp = Json::object();
