@@ -35,6 +35,26 @@ int parse_chat_request(const char* json, size_t len, ChatRequest* out, std::stri
   r.model = root.get("model").as_string();
   if (root.get("stream").as_bool(false)) { *err = "stream=true is not supported by provider local"; return 400; }
   if (root.find("n") && root.get("n").as_int(1) != 1) { *err = "n must be 1"; return 400; }
+  // Parameters that would change the completion but are not implemented are refused, never silently
+  // ignored (the reference's SendRequest sets none of them: langchaingo_client.go:83-102).
+  {
+    const Json& stop = root.get("stop");
+    if ((stop.is_string() && !stop.as_string().empty()) || (stop.is_array() && stop.size() > 0)) {
+      *err = "stop sequences are not supported by provider local";
+      return 400;
+    }
+    const Json& tc = root.get("tool_choice");
+    if (!tc.is_null() && !(tc.is_string() && tc.as_string() == "auto")) {
+      *err = "tool_choice other than \"auto\" is not supported by provider local";
+      return 400;
+    }
+    if (root.get("logprobs").as_bool(false)) { *err = "logprobs are not supported by provider local"; return 400; }
+    const Json& rf = root.get("response_format");
+    if (rf.is_object() && !rf.get("type").as_string().empty() && rf.get("type").as_string() != "text") {
+      *err = "response_format other than text is not supported by provider local";
+      return 400;
+    }
+  }
 
   const Json& acp = root.get("acp");
   if (acp.is_object()) {

@@ -261,3 +261,17 @@ def test_hostsim_window_sizing_reports_real_length():
     assert host.hostsim_window_tokens(1024, 2) == 1024
     small = host.hostsim_window_tokens(64, 2)
     assert small > 64 and small == host.hostsim_window_tokens(1, 2)
+
+
+def test_unimplemented_completion_parameters_are_refused_not_ignored():
+    """stop / tool_choice / logprobs / response_format would change the completion: a request that sets
+    them gets a 400 (terminal LLMRequestError upstream) instead of a silently different answer; their
+    neutral spellings pass."""
+    base = {"model": "m", "messages": [{"role": "user", "content": "hi"}]}
+    for extra in ({}, {"stop": []}, {"stop": None}, {"tool_choice": "auto"}, {"logprobs": False}, {"response_format": {"type": "text"}}):
+        assert "status" not in host.render_prompt(dict(base, **extra)), extra
+    for extra, needle in (({"stop": ["\n"]}, "stop"), ({"stop": "x"}, "stop"), ({"tool_choice": "required"}, "tool_choice"),
+                          ({"tool_choice": {"type": "function", "function": {"name": "f"}}}, "tool_choice"),
+                          ({"logprobs": True}, "logprobs"), ({"response_format": {"type": "json_object"}}, "response_format")):
+        r = host.render_prompt(dict(base, **extra))
+        assert r.get("status") == 400 and needle in r["error"], (extra, r)
