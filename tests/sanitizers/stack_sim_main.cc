@@ -1,0 +1,58 @@
+// The whole host stack in one ThreadSanitizer binary: reconcile workers (csrc/host/hostsim.cc, task.cc)
+// -> LocalClient (llmclient.cc) -> C ABI (c_api.cc) -> the REAL scheduler (engine.cc) -> the fake
+// Model (fake_model.cc).  Runs BASELINE config 3's shape on a CPU: Tasks with two tool schemas, a
+// scripted tool call on the first LLM step (force_tokens through the real engine), ToolCall CRs,
+// fold-back, second LLM step served from the shared prefix cache.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <string>
+
+#include "acp_host.h"
+#include "acp_infer.h"
+#include "json.h"
+
+using acp::Json;
+
+static Json stats(acp_engine* e) {
+  char* sj = nullptr;
+  acp_infer_stats(e, &sj);
+  Json s;
+  std::string err;
+  Json::parse(std::string(sj), &s, &err);
+  acp_infer_free(sj);
+  return s;
+}
+
+int main() {
+  acp_engine* e = nullptr;
+  if (acp_infer_init("{\"model\": \"sim\", \"max_batch\": 32, \"kv_pages\": 1500, \"max_tokens_per_step\": 2048, "
+                     "\"max_pages_per_seq\": 40, \"prefix_cache\": true}", &e) != 0) return 1;
+  int bad = 0;
+  long long hits_before = 0;
+  for (int round = 0; round < 3; ++round) {
+    const std::string cfg = "{\"tasks\": 48, \"workers\": 48, \"provider\": \"local\", \"model\": \"sim\", \"max_tokens\": 32, "
+                            "\"prompt_tokens\": 512, \"tools\": 2, \"tool_loop\": true, \"seed\": " + std::to_string(round + 1) + "}";
+    char* out = nullptr;
+    if (acp_hostsim_run(e, cfg.c_str(), &out) != 0 || !out) { fprintf(stderr, "hostsim failed\n"); return 1; }
+    Json r;
+    std::string err;
+    Json::parse(std::string(out), &r, &err);
+    acp_infer_free(out);
+    const Json s = stats(e);
+    const long long hits = s.get("prefix_hits").as_int();
+    // the fake model may end a turn with an empty completion (first token = EOT, 1 in 23): that Task is
+    // terminally Failed (422 -> LLMRequestError), exactly like the reference's 4xx arm
+    long long final_answers = r.get("final_phases").get("FinalAnswer").as_int(0), failed = r.get("final_phases").get("Failed").as_int(0);
+    printf("round %d: reconciles=%lld FinalAnswer=%lld Failed=%lld prefix_hits+=%lld deferrals=%lld cache_pages=%lld\n", round,
+           (long long)r.get("reconciles").as_int(), final_answers, failed, hits - hits_before,
+           (long long)s.get("prefix_deferrals").as_int(), (long long)s.get("prefix_cache_pages").as_int());
+    if (final_answers + failed != 48) { fprintf(stderr, "tasks lost\n"); ++bad; }
+    if (r.get("reconciles").as_int() < 48 + final_answers) { fprintf(stderr, "a Task reached FinalAnswer without two LLM steps\n"); ++bad; }
+    if (round > 0 && hits - hits_before < r.get("reconciles").as_int() - 2) { fprintf(stderr, "warm rounds must hit the shared prefix\n"); ++bad; }
+    if (s.get("kv_pages_free").as_int() + s.get("prefix_cache_pages").as_int() != s.get("kv_pages_total").as_int()) { fprintf(stderr, "page leak\n"); ++bad; }
+    hits_before = hits;
+  }
+  acp_infer_shutdown(e);
+  return bad ? 1 : 0;
+}

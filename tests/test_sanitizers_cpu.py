@@ -21,6 +21,9 @@ BUILDS = {
     "host_tsan": (["-fsanitize=thread"], SOURCES, ["-lpthread"]),
     "engine_sim": (["-fsanitize=thread"], [os.path.join(SAN, "engine_sim_main.cc"), os.path.join(SAN, "fake_model.cc")] + [
         os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc")], ["-lpthread"]),
+    "stack_sim": (["-fsanitize=thread"], [os.path.join(SAN, "stack_sim_main.cc"), os.path.join(SAN, "fake_model.cc")] + [
+        os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc", "host/hostsim.cc",
+                                        "host/llmclient.cc", "host/task.cc")], ["-lpthread"]),
     "fuzz": (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"], [os.path.join(SAN, "fuzz_main.cc")] + [
         os.path.join(CSRC, f) for f in ("chat.cc", "tokenizer.cc", "safetensors.cc")], []),
 }
@@ -74,6 +77,17 @@ def test_real_scheduler_over_a_fake_model_under_tsan(binaries):
                              env=dict(os.environ, TSAN_OPTIONS="exitcode=66", **extra))
         assert "ThreadSanitizer" not in run.stderr, run.stderr[-6000:]
         assert run.returncode == 0 and "bad=0" in run.stdout, (run.returncode, run.stdout[-1500:], run.stderr[-3000:])
+
+
+def test_whole_host_stack_tool_loop_under_tsan(binaries):
+    """Reconcile workers -> LocalClient -> C ABI -> real scheduler -> fake Model, BASELINE config 3's
+    shape (two tool schemas, scripted tool call, ToolCall CRs, fold-back, second LLM step): every
+    FinalAnswer took two LLM steps, warm rounds are served from the shared prefix cache, no page
+    leaks, ThreadSanitizer silent."""
+    exe = _exe(binaries, "stack_sim")
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, TSAN_OPTIONS="exitcode=66"))
+    assert "ThreadSanitizer" not in run.stderr, run.stderr[-6000:]
+    assert run.returncode == 0 and run.stdout.count("round ") == 3, (run.returncode, run.stdout[-1500:], run.stderr[-3000:])
 
 
 def test_untrusted_input_parsers_under_asan_ubsan(binaries, tmp_path):
