@@ -1,5 +1,5 @@
 """Seeded synthetic weights — the numpy statement of the generator the engine runs on the GPU
-(agentcontrolplane_b200/csrc/weights.cu, `synth_weight_kernel`).  Integer-only hashing plus ONE
+(agentcontrolplane_b200/csrc/kernels.cu, `synth_weight_kernel`).  Integer-only hashing plus ONE
 fp32 multiply, so CPU and GPU produce bit-identical bf16 tensors.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
@@ -41,25 +41,39 @@ def _mix(z: np.ndarray) -> np.ndarray:
     return z
 
 
+def _synth_chunk(out: np.ndarray, base: np.uint64, start: int, c0: int, c1: int, scale: np.float32,
+                 plus_one: bool) -> None:
+    with np.errstate(over="ignore"):
+        idx = np.arange(start + c0, start + c1, dtype=np.uint64)
+        z = _mix(base + idx * np.uint64(0xD1B54A32D192ED03))
+        s = ((z & np.uint64(0xFFFF)) + ((z >> np.uint64(16)) & np.uint64(0xFFFF)) +
+             ((z >> np.uint64(32)) & np.uint64(0xFFFF)) + (z >> np.uint64(48))).astype(np.int64)
+        s -= 131070
+        w = s.astype(np.float32) * scale
+        if plus_one:
+            w = w + np.float32(1.0)
+        out[c0:c1] = bf16_round_to_bits(w)
+
+
 def synth_bits(seed: int, tid: int, n: int, std: float, plus_one: bool = False,
                start: int = 0) -> np.ndarray:
-    """bf16 bit patterns of elements [start, start+n) of tensor `tid`."""
+    """bf16 bit patterns of elements [start, start+n) of tensor `tid`.  Large tensors are generated
+    in chunks on a thread pool (numpy releases the GIL inside these element-wise kernels); every
+    element depends only on its own index, so the result does not depend on the chunking."""
     scale = np.float32(std / IH_STD)
     out = np.empty(n, np.uint16)
-    chunk = 1 << 24
     with np.errstate(over="ignore"):
         base = (np.uint64(seed) + np.uint64(tid) * np.uint64(0x9E3779B97F4A7C15)) & MASK
-        for c0 in range(0, n, chunk):
-            c1 = min(n, c0 + chunk)
-            idx = np.arange(start + c0, start + c1, dtype=np.uint64)
-            z = _mix(base + idx * np.uint64(0xD1B54A32D192ED03))
-            s = ((z & np.uint64(0xFFFF)) + ((z >> np.uint64(16)) & np.uint64(0xFFFF)) +
-                 ((z >> np.uint64(32)) & np.uint64(0xFFFF)) + (z >> np.uint64(48))).astype(np.int64)
-            s -= 131070
-            w = s.astype(np.float32) * scale
-            if plus_one:
-                w = w + np.float32(1.0)
-            out[c0:c1] = bf16_round_to_bits(w)
+    chunk = 1 << 22
+    spans = [(c0, min(n, c0 + chunk)) for c0 in range(0, n, chunk)]
+    if len(spans) <= 2:
+        for c0, c1 in spans:
+            _synth_chunk(out, base, start, c0, c1, scale, plus_one)
+        return out
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+        list(pool.map(lambda sp: _synth_chunk(out, base, start, sp[0], sp[1], scale, plus_one), spans))
     return out
 
 

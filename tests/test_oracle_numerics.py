@@ -49,6 +49,17 @@ def test_llama31_rope_scaling_matches_huggingface_fixture():
     assert np.max(np.abs(plain[:, COLS] - g["prompt_logits"])) > 0.05
 
 
+@pytest.mark.skipif(not os.environ.get("ACP_SLOW_TESTS"), reason="~5 min and ~10 GB: generates Llama-3-8B-width weights; "
+                    "set ACP_SLOW_TESTS=1 (the fixture's own generator already asserted this once)")
+def test_fp32_oracle_matches_huggingface_at_8b_width():
+    """Same pin at the REAL width (hidden 4096, 32/8 heads, ffn 14336, vocab 128256), 2 layers:
+    fixture tests/golden/llama_8b_l2_golden.npz from make_llama_8b_l2_golden.py."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "llama_8b_l2_golden.npz"))
+    logits = LlamaOracle(PRESETS["llama-3-8b-l2"], SEED, mode="fp32").forward(g["prompt"], all_logits=True)
+    assert np.max(np.abs(logits[:, COLS] - g["prompt_logits"])) < 5e-4
+    assert np.array_equal(np.argmax(logits, axis=-1), g["greedy_next"])
+
+
 def test_bf16_mode_stays_close_to_fp32_mode():
     cfg = PRESETS["tiny"]
     prompt = GOLD["tiny.prompt"]
