@@ -53,7 +53,11 @@ typedef struct acp_engine acp_engine;
  *   "seed": 11317760                  (0xACB200)
  *   "device": 0, "max_batch": 256, "max_tokens_per_step": 8192, "kv_pages": 2048,
  *   "max_pages_per_seq": 256, "prefix_cache": true, "tp": 1 (tensor-parallel GPUs of THIS process),
- *   "tp_comm": "p2p" | "nccl", "layers": n (truncated depth, dev only)                      */
+ *   "tp_comm": "p2p" | "nccl", "layers": n (truncated depth, dev only),
+ *   "replicas": n (1..16): n data-parallel engines on GPUs device, device+tp, ... behind THIS handle;
+ *              requests are routed stickily (OpenAI `user` field, else a hash of the first two
+ *              messages, else round-robin) so a Task's turns find their retained K/V; tickets are
+ *              global; acp_infer_stats sums the additive counters and lists per-replica objects */
 int acp_infer_init(const char* config_json, acp_engine** out);
 
 /* Non-blocking submit of one chat-completions request (what SendRequest does at

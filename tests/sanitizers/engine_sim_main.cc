@@ -33,7 +33,10 @@ static std::vector<int> make_prompt(uint64_t seed, int agent, int task) {
 int main() {
   acp_engine* e = nullptr;
   const bool no_cache = getenv("ACP_SIM_NO_CACHE") != nullptr;   // second leg: the same load with the prefix cache off
-  const char* cfg = no_cache ? "{\"model\": \"sim\", \"max_batch\": 24, \"kv_pages\": 300, \"max_tokens_per_step\": 512, "
+  const bool replicas = getenv("ACP_SIM_REPLICAS") != nullptr;   // third leg: 4 data-parallel engines behind ONE handle
+  const char* cfg = replicas ? "{\"model\": \"sim\", \"replicas\": 4, \"max_batch\": 8, \"kv_pages\": 120, \"max_tokens_per_step\": 512, "
+                               "\"max_pages_per_seq\": 16, \"prefix_cache\": true}"
+                    : no_cache ? "{\"model\": \"sim\", \"max_batch\": 24, \"kv_pages\": 300, \"max_tokens_per_step\": 512, "
                                "\"max_pages_per_seq\": 16, \"prefix_cache\": false}"
                              : "{\"model\": \"sim\", \"max_batch\": 24, \"kv_pages\": 300, \"max_tokens_per_step\": 512, "
                                "\"max_pages_per_seq\": 16, \"prefix_cache\": true}";
@@ -54,6 +57,7 @@ int main() {
       req.set("model", Json("sim"));
       req.set("max_tokens", Json(kMaxTokens));
       req.set("acp", acp);
+      if (i % 2 == 0) req.set("user", Json("task-" + std::to_string((tid + i) % 5)));   // sticky routing key (replica leg)
       const std::string body = req.dump();
       uint64_t ticket = 0;
       if (acp_infer_submit(e, body.c_str(), body.size(), &ticket) != 0) { ++bad; continue; }
@@ -157,7 +161,7 @@ int main() {
     const long long pf = s0.get("prefill_tokens").as_int(), df = s0.get("prefix_deferrals").as_int();
     printf("cold burst: prefill_tokens=%lld (48 cold copies would be %d) deferrals=%lld hits=%lld\n", pf, 48 * 288, df,
            (long long)s0.get("prefix_hits").as_int());
-    if (!no_cache && (df < 1 || pf > 420 + 48 * 288 / 3)) { fprintf(stderr, "in-flight dedup did not engage\n"); ++bad; }
+    if (!no_cache && !replicas && (df < 1 || pf > 420 + 48 * 288 / 3)) { fprintf(stderr, "in-flight dedup did not engage\n"); ++bad; }
   }
   std::vector<std::thread> th;
   for (int t = 0; t < kThreads; ++t) th.emplace_back(worker, t);
@@ -179,6 +183,10 @@ int main() {
   if (ok + cancelled != kThreads * kPerThread) rc = 1;
   if (free_pages + cached != total) { fprintf(stderr, "page leak: %lld + %lld != %lld\n", free_pages, cached, total); rc = 1; }
   if (no_cache && (hits != 0 || cached != 0)) { fprintf(stderr, "cache is off but was used\n"); rc = 1; }
+  if (replicas && (s.get("replica_count").as_int() != 4 || s.get("replicas").size() != 4)) { fprintf(stderr, "replica stats missing\n"); rc = 1; }
+  if (replicas)
+    for (const Json& r : s.get("replicas").items())
+      if (r.get("requests_done").as_int() + r.get("requests_failed").as_int() < 100) { fprintf(stderr, "a replica got almost no work\n"); rc = 1; }
   if (!no_cache && hits < kThreads * kPerThread / 2) { fprintf(stderr, "too few prefix hits: %lld\n", hits); rc = 1; }
   acp_infer_shutdown(e);
   return rc;

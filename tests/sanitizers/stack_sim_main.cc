@@ -26,10 +26,15 @@ static Json stats(acp_engine* e) {
 
 int main() {
   acp_engine* e = nullptr;
-  if (acp_infer_init("{\"model\": \"sim\", \"max_batch\": 32, \"kv_pages\": 1500, \"max_tokens_per_step\": 2048, "
-                     "\"max_pages_per_seq\": 40, \"prefix_cache\": true}", &e) != 0) return 1;
+  // ACP_SIM_REPLICAS: the same run over 4 data-parallel engines behind one handle — the second LLM step of a
+  // Task must find its first step's pages, i.e. the router must be sticky without any Task id in the request
+  const bool replicas = getenv("ACP_SIM_REPLICAS") != nullptr;
+  if (acp_infer_init(replicas ? "{\"model\": \"sim\", \"replicas\": 4, \"max_batch\": 32, \"kv_pages\": 1500, \"max_tokens_per_step\": 2048, "
+                                "\"max_pages_per_seq\": 40, \"prefix_cache\": true}"
+                              : "{\"model\": \"sim\", \"max_batch\": 32, \"kv_pages\": 1500, \"max_tokens_per_step\": 2048, "
+                                "\"max_pages_per_seq\": 40, \"prefix_cache\": true}", &e) != 0) return 1;
   int bad = 0;
-  long long hits_before = 0;
+  long long hits_before = 0, reused_before = 0;
   for (int round = 0; round < 3; ++round) {
     const std::string cfg = "{\"tasks\": 48, \"workers\": 48, \"provider\": \"local\", \"model\": \"sim\", \"max_tokens\": 32, "
                             "\"prompt_tokens\": 512, \"tools\": 2, \"tool_loop\": true, \"seed\": " + std::to_string(round + 1) + "}";
@@ -49,6 +54,9 @@ int main() {
            (long long)s.get("prefix_deferrals").as_int(), (long long)s.get("prefix_cache_pages").as_int());
     if (final_answers + failed != 48) { fprintf(stderr, "tasks lost\n"); ++bad; }
     if (r.get("reconciles").as_int() < 48 + final_answers) { fprintf(stderr, "a Task reached FinalAnswer without two LLM steps\n"); ++bad; }
+    // second turns reuse >= 21 pages of their own first turn: only possible on the SAME replica
+    if (s.get("prefix_tokens_reused").as_int() - reused_before < (r.get("reconciles").as_int() - 48) * 640) { fprintf(stderr, "second turns did not find their K/V\n"); ++bad; }
+    reused_before = s.get("prefix_tokens_reused").as_int();
     if (round > 0 && hits - hits_before < r.get("reconciles").as_int() - 2) { fprintf(stderr, "warm rounds must hit the shared prefix\n"); ++bad; }
     if (s.get("kv_pages_free").as_int() + s.get("prefix_cache_pages").as_int() != s.get("kv_pages_total").as_int()) { fprintf(stderr, "page leak\n"); ++bad; }
     hits_before = hits;

@@ -72,7 +72,7 @@ def test_real_scheduler_over_a_fake_model_under_tsan(binaries):
     queueing and eviction, and cancellations.  Every response must equal the cache-free reference,
     no page may leak, and ThreadSanitizer must stay silent."""
     exe = _exe(binaries, "engine_sim")
-    for extra in ({}, {"ACP_SIM_NO_CACHE": "1"}):
+    for extra in ({}, {"ACP_SIM_NO_CACHE": "1"}, {"ACP_SIM_REPLICAS": "1"}):
         run = subprocess.run([exe], capture_output=True, text=True, timeout=300,
                              env=dict(os.environ, TSAN_OPTIONS="exitcode=66", **extra))
         assert "ThreadSanitizer" not in run.stderr, run.stderr[-6000:]
@@ -85,9 +85,10 @@ def test_whole_host_stack_tool_loop_under_tsan(binaries):
     FinalAnswer took two LLM steps, warm rounds are served from the shared prefix cache, no page
     leaks, ThreadSanitizer silent."""
     exe = _exe(binaries, "stack_sim")
-    run = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, TSAN_OPTIONS="exitcode=66"))
-    assert "ThreadSanitizer" not in run.stderr, run.stderr[-6000:]
-    assert run.returncode == 0 and run.stdout.count("round ") == 3, (run.returncode, run.stdout[-1500:], run.stderr[-3000:])
+    for extra in ({}, {"ACP_SIM_REPLICAS": "1"}):     # one engine; 4 data-parallel replicas behind one handle (sticky routing)
+        run = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, TSAN_OPTIONS="exitcode=66", **extra))
+        assert "ThreadSanitizer" not in run.stderr, run.stderr[-6000:]
+        assert run.returncode == 0 and run.stdout.count("round ") == 3, (run.returncode, run.stdout[-1500:], run.stderr[-3000:])
 
 
 def test_untrusted_input_parsers_under_asan_ubsan(binaries, tmp_path):
