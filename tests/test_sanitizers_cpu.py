@@ -21,6 +21,8 @@ BUILDS = {
     "host_tsan": (["-fsanitize=thread"], SOURCES, ["-lpthread"]),
     "engine_sim": (["-fsanitize=thread"], [os.path.join(SAN, "engine_sim_main.cc"), os.path.join(SAN, "fake_model.cc")] + [
         os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc")], ["-lpthread"]),
+    "edge_sim": (["-fsanitize=thread"], [os.path.join(SAN, "edge_sim_main.cc"), os.path.join(SAN, "fake_model.cc")] + [
+        os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc")], ["-lpthread"]),
     "stack_sim": (["-fsanitize=thread"], [os.path.join(SAN, "stack_sim_main.cc"), os.path.join(SAN, "fake_model.cc")] + [
         os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc", "host/hostsim.cc",
                                         "host/llmclient.cc", "host/task.cc")], ["-lpthread"]),
@@ -77,6 +79,16 @@ def test_real_scheduler_over_a_fake_model_under_tsan(binaries):
                              env=dict(os.environ, TSAN_OPTIONS="exitcode=66", **extra))
         assert "ThreadSanitizer" not in run.stderr, run.stderr[-6000:]
         assert run.returncode == 0 and "bad=0" in run.stdout, (run.returncode, run.stdout[-1500:], run.stderr[-3000:])
+
+
+def test_scheduler_edge_cases_over_the_fake_model(binaries):
+    """Page-boundary prompt lengths (1 ... 300 tokens, each a prefix of the next), prefill chunked into
+    48-row steps with pages published chunk by chunk, sextuplets submitted together, max_tokens 1, a
+    request that exceeds the context limit (400) and one that exactly fits, on a 63-page pool."""
+    exe = _exe(binaries, "edge_sim")
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, TSAN_OPTIONS="exitcode=66"))
+    assert "ThreadSanitizer" not in run.stderr, run.stderr[-6000:]
+    assert run.returncode == 0 and "bad=0" in run.stdout, (run.returncode, run.stdout[-1500:], run.stderr[-3000:])
 
 
 def test_whole_host_stack_tool_loop_under_tsan(binaries):
