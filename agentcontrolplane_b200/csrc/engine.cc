@@ -79,6 +79,7 @@ int Engine::init(const char* config_json) {
     lim.attn_decode_mode = am == "item" ? 1 : (am == "chunked" || am == "flat") ? 2 : 0;
   }
   if (cfg.find("prefix_cache")) prefix_cache_on_ = cfg.get("prefix_cache").as_bool(true);
+  request_timeout_ms_ = (double)cfg.get("request_timeout_ms").as_int(0);
   if (cfg.find("splitk_target_ctas")) lim.splitk_target_ctas = (int)cfg.get("splitk_target_ctas").as_int(lim.splitk_target_ctas);
   if (lim.max_batch < 1 || lim.max_tokens < 16 || lim.num_pages < 2 || lim.max_pages_per_seq < 1) {
     fprintf(stderr, "[acp_infer] invalid engine limits\n");
@@ -529,9 +530,15 @@ void Engine::fail_all_running(const std::string& msg) {
 void Engine::admit_locked() {
   const int max_batch = model_.limits().max_batch;
   // drop cancelled requests that never started
+  const auto now = clk::now();
   for (auto it = waiting_.begin(); it != waiting_.end();) {
     if ((*it)->cancelled) { finish(*it, 499, "cancelled", "request cancelled", ""); it = waiting_.erase(it); }
-    else ++it;
+    else if (request_timeout_ms_ > 0 && ms_between((*it)->t_submit, now) > request_timeout_ms_) {
+      // the reference declares LLMRequestTimeout (task_controller.go:25) and never applies it; here a request
+      // that outlives the configured budget ends as a TRANSIENT 504: plain error upstream => requeue in 5 s
+      finish(*it, 504, "timeout", "request exceeded request_timeout_ms in the queue", "");
+      it = waiting_.erase(it);
+    } else ++it;
   }
   while (!waiting_.empty() && (int)running_.size() < max_batch) {
     auto& s = waiting_.front();
@@ -601,9 +608,14 @@ void Engine::run() {
       admit_locked();
       // cancelled while running
       bool any_cancel = false;
+      const auto now = clk::now();
       for (auto it = running_.begin(); it != running_.end();) {
         if ((*it)->cancelled) { finish(*it, 499, "cancelled", "request cancelled", ""); it = running_.erase(it); any_cancel = true; }
-        else ++it;
+        else if (request_timeout_ms_ > 0 && ms_between((*it)->t_submit, now) > request_timeout_ms_) {
+          finish(*it, 504, "timeout", "request exceeded request_timeout_ms", "");
+          it = running_.erase(it);
+          any_cancel = true;
+        } else ++it;
       }
       if (any_cancel) { cv_done_.notify_all(); admit_locked(); }
       if (running_.empty()) {

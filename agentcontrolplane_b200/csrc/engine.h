@@ -122,6 +122,7 @@ class Engine {
   int pcache_pages_ = 0;
   uint64_t use_clock_ = 0;
   bool prefix_cache_on_ = true;
+  double request_timeout_ms_ = 0;   // "request_timeout_ms": 0 = none
   int pcache_find_locked(int parent, const int* tokens) const;
   int pcache_insert_locked(int parent, const int* tokens, int page);
   void publish_prefix_locked(Sequence& s);

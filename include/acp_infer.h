@@ -54,6 +54,8 @@ typedef struct acp_engine acp_engine;
  *   "device": 0, "max_batch": 256, "max_tokens_per_step": 8192, "kv_pages": 2048,
  *   "max_pages_per_seq": 256, "prefix_cache": true, "tp": 1 (tensor-parallel GPUs of THIS process),
  *   "tp_comm": "p2p" | "nccl", "layers": n (truncated depth, dev only),
+ *   "request_timeout_ms": n (0 = none): a request older than this, queued or running, ends with status 504
+ *              (transient: plain error upstream => the Task is requeued, state_machine.go:757-789),
  *   "replicas": n (1..16): n data-parallel engines on GPUs device, device+tp, ... behind THIS handle;
  *              requests are routed stickily (OpenAI `user` field, else a hash of the first two
  *              messages, else round-robin) so a Task's turns find their retained K/V; tickets are

@@ -74,5 +74,37 @@ int main() {
          (long long)s.get("kv_pages_free").as_int(), (long long)s.get("prefix_cache_pages").as_int(), (long long)s.get("kv_pages_total").as_int());
   if (s.get("kv_pages_free").as_int() + s.get("prefix_cache_pages").as_int() != s.get("kv_pages_total").as_int()) { fprintf(stderr, "page leak\n"); ++bad; }
   acp_infer_shutdown(e);
+  // request_timeout_ms: a one-sequence engine is held by a long prefill step (420 rows = the fake model's 40 ms
+  // blocker) while three more requests wait: they must end with a transient 504, the blocker itself with 200
+  {
+    acp_engine* t = nullptr;
+    if (acp_infer_init("{\"model\": \"sim\", \"max_batch\": 1, \"kv_pages\": 64, \"max_tokens_per_step\": 512, "
+                       "\"max_pages_per_seq\": 16, \"prefix_cache\": false, \"request_timeout_ms\": 15}", &t) != 0) return 1;
+    std::vector<uint64_t> tk(4);
+    for (int i = 0; i < 4; ++i) {
+      Json ids = Json::array();
+      for (int tok : prompt_of(i == 0 ? 420 : 40, 100 + (uint64_t)i)) ids.push(Json(tok));
+      Json acp = Json::object();
+      acp.set("prompt_token_ids", ids);
+      Json req = Json::object();
+      req.set("model", Json("sim"));
+      req.set("max_tokens", Json(i == 0 ? 1 : 8));
+      req.set("acp", acp);
+      const std::string body = req.dump();
+      acp_infer_submit(t, body.c_str(), body.size(), &tk[(size_t)i]);
+    }
+    int n504 = 0, n200 = 0;
+    for (int i = 0; i < 4; ++i) {
+      acp_infer_wait(t, tk[(size_t)i], 60000);
+      char* out = nullptr; size_t len = 0; int status = 0;
+      acp_infer_result(t, tk[(size_t)i], &out, &len, &status);
+      acp_infer_free(out);
+      if (status == 504) ++n504;
+      if (status == 200 || status == 422) ++n200;
+    }
+    printf("timeout-sim: 504=%d completed=%d\n", n504, n200);
+    if (n504 != 3 || n200 != 1) { fprintf(stderr, "request_timeout_ms did not fire as expected\n"); ++bad; }
+    acp_infer_shutdown(t);
+  }
   return bad ? 1 : 0;
 }
