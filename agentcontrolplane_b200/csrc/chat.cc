@@ -49,6 +49,8 @@ int parse_chat_request(const char* json, size_t len, ChatRequest* out, std::stri
       return 400;
     }
     if (root.get("logprobs").as_bool(false)) { *err = "logprobs are not supported by provider local"; return 400; }
+    for (const char* pen : {"frequency_penalty", "presence_penalty"})
+      if (root.get(pen).as_double(0.0) != 0.0) { *err = std::string(pen) + " is not supported by provider local"; return 400; }
     const Json& rf = root.get("response_format");
     if (rf.is_object() && !rf.get("type").as_string().empty() && rf.get("type").as_string() != "text") {
       *err = "response_format other than text is not supported by provider local";

@@ -272,6 +272,7 @@ def test_unimplemented_completion_parameters_are_refused_not_ignored():
         assert "status" not in host.render_prompt(dict(base, **extra)), extra
     for extra, needle in (({"stop": ["\n"]}, "stop"), ({"stop": "x"}, "stop"), ({"tool_choice": "required"}, "tool_choice"),
                           ({"tool_choice": {"type": "function", "function": {"name": "f"}}}, "tool_choice"),
-                          ({"logprobs": True}, "logprobs"), ({"response_format": {"type": "json_object"}}, "response_format")):
+                          ({"logprobs": True}, "logprobs"), ({"response_format": {"type": "json_object"}}, "response_format"),
+                          ({"frequency_penalty": 0.5}, "frequency_penalty"), ({"presence_penalty": -1}, "presence_penalty")):
         r = host.render_prompt(dict(base, **extra))
         assert r.get("status") == 400 and needle in r["error"], (extra, r)
