@@ -207,6 +207,42 @@ ACP_DEVINL void produce_tiles(const CUtensorMap* tm_k, const CUtensorMap* tm_v, 
   }
 }
 
+// Experimental (ACP_ATTN_PT_PREFETCH=1, unmeasured — profiles/r1_v3_ncu_full_decode_kernels.md shows the
+// decode kernels latency bound with a page-table load in front of every TMA issue): ALL 32 lanes of
+// the producer warp read the CTA's page ids once (one coalesced load, <= 32 pages = 16 tiles) and
+// lane 0 gets them by shuffle, so no TMA issue waits on global memory any more.
+ACP_DEVINL void produce_tiles_prefetched(const CUtensorMap* tm_k, const CUtensorMap* tm_v, uint8_t* stages,
+                                         uint64_t* full_bar, uint64_t* empty_bar, const int* pt_row, int kh,
+                                         int kv_heads, int tile_begin, int tile_end, int last_tok /*exclusive*/,
+                                         int lane) {
+  const int page0 = tile_begin * (TILE_TOK / KV_PAGE);
+  const int pages_here = (last_tok - tile_begin * TILE_TOK + KV_PAGE - 1) / KV_PAGE;
+  const int my_page = (lane < pages_here) ? pt_row[page0 + lane] : 0;
+  int it = 0;
+  for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+    const int s = it % STAGES;
+    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+    if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1u);
+    __syncwarp();
+    const int tok0 = tile * TILE_TOK;
+    const int n_pages = (last_tok - tok0 > KV_PAGE) ? 2 : 1;
+    const int rel = (tile - tile_begin) * (TILE_TOK / KV_PAGE);
+    const int pg0 = __shfl_sync(0xffffffffu, my_page, rel & 31);
+    const int pg1 = __shfl_sync(0xffffffffu, my_page, (rel + 1) & 31);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(n_pages * 4 * BLOCK_BYTES));
+      uint8_t* kdst = stages + s * STAGE_BYTES;
+      uint8_t* vdst = kdst + K_TILE_BYTES;
+      for (int p = 0; p < n_pages; ++p) {
+        const int page = p ? pg1 : pg0;
+        const int row = (page * kv_heads + kh) * 2 * KV_PAGE;
+        tma_load_2d(kdst + p * 2 * BLOCK_BYTES, tm_k, &full_bar[s], 0, row, kEvictFirst);
+        tma_load_2d(vdst + p * 2 * BLOCK_BYTES, tm_v, &full_bar[s], 0, row, kEvictFirst);
+      }
+    }
+  }
+}
+
 struct SmemLayout {
   uint8_t* stages;
   uint64_t* full_bar;
@@ -348,6 +384,7 @@ ACP_DEVINL int find_seq(const int* cum, int n, long long f, int kvh) {  // cum[b
   return lo;
 }
 
+template <bool PT_PREFETCH>
 __global__ void __launch_bounds__(ATTN_THREADS, 2)
 attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                    AttnDecodeArgs a) {
@@ -383,6 +420,13 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   pdl_wait();  // K/V pages and q were written by the previous kernel (rope_kv)
 
   if (warp == CONSUMER_WARPS) {
+    if constexpr (PT_PREFETCH) {
+      if (tile_end - tile_begin <= 16) {
+        produce_tiles_prefetched(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
+                                 a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, tile_begin, tile_end, tok_end, lane);
+        return;
+      }
+    }
     if (lane == 0)
       produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
                     a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, tile_begin, tile_end, tok_end);
@@ -468,6 +512,7 @@ attn_merge_kernel(AttnDecodeArgs a) {
 // Per-item variant: CTA = (sequence, kv head), the whole context of the item, cross-warp merge in
 // shared memory, final bf16 output written directly (no workspace, no merge kernel).  Used when
 // there are enough items to fill the machine and every item is short (launch_attn_decode picks).
+template <bool PT_PREFETCH>
 __global__ void __launch_bounds__(ATTN_THREADS, 2)
 attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                         AttnDecodeArgs a) {
@@ -494,6 +539,13 @@ attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
   pdl_wait();
 
   if (warp == CONSUMER_WARPS) {
+    if constexpr (PT_PREFETCH) {
+      if (n_tiles <= 16) {
+        produce_tiles_prefetched(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
+                                 a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, cached, lane);
+        return;
+      }
+    }
     if (lane == 0)
       produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
                     a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, cached);
@@ -660,9 +712,11 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
 }  // namespace
 
 int attn_setup_attributes() {
-  cudaError_t e0 = cudaFuncSetAttribute(attn_decode_item_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  cudaError_t e0 = cudaFuncSetAttribute(attn_decode_item_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_item_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
   if (e0 != cudaSuccess) { fprintf(stderr, "[acp_infer] attention cudaFuncSetAttribute failed\n"); return -5; }
-  cudaError_t e1 = cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  cudaError_t e1 = cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
   cudaError_t e2 = cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     fprintf(stderr, "[acp_infer] attention cudaFuncSetAttribute failed\n");
@@ -685,19 +739,30 @@ size_t attn_decode_ws_floats(int max_batch, int heads, int kv_heads, int max_chu
   return (size_t)max_batch * kv_heads * max_chunks * CONSUMER_WARPS * (heads / kv_heads) * 130;
 }
 
+// ACP_ATTN_PT_PREFETCH=1: decode kernels with the page ids of a CTA loaded once by the producer warp
+static bool pt_prefetch_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACP_ATTN_PT_PREFETCH"); v = (e && *e == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnDecodeArgs& a,
                        cudaStream_t s) {
   if (a.num_seqs <= 0) return 0;
   if (a.heads % a.kv_heads != 0 || a.heads / a.kv_heads > 16) return -1;
   if (a.per_item) {
-    cudaError_t e = acp_launch(attn_decode_item_kernel, dim3(a.num_seqs, a.kv_heads), dim3(ATTN_THREADS), ATTN_SMEM,
-                               s, tm_k, tm_v, a);
+    cudaError_t e = pt_prefetch_enabled()
+                        ? acp_launch(attn_decode_item_kernel<true>, dim3(a.num_seqs, a.kv_heads), dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a)
+                        : acp_launch(attn_decode_item_kernel<false>, dim3(a.num_seqs, a.kv_heads), dim3(ATTN_THREADS), ATTN_SMEM,
+                                     s, tm_k, tm_v, a);
     if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode_item launch: %s\n", cudaGetErrorString(e)); return -5; }
     return 0;
   }
   if (a.total_chunks <= 0) return -1;
-  cudaError_t e = acp_launch(attn_decode_kernel, dim3((unsigned)(a.total_chunks * a.kv_heads)), dim3(ATTN_THREADS),
-                             ATTN_SMEM, s, tm_k, tm_v, a);
+  cudaError_t e = pt_prefetch_enabled()
+                      ? acp_launch(attn_decode_kernel<true>, dim3((unsigned)(a.total_chunks * a.kv_heads)), dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a)
+                      : acp_launch(attn_decode_kernel<false>, dim3((unsigned)(a.total_chunks * a.kv_heads)), dim3(ATTN_THREADS),
+                                   ATTN_SMEM, s, tm_k, tm_v, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode launch: %s\n", cudaGetErrorString(e)); return -5; }
   e = acp_launch(attn_merge_kernel, dim3(a.num_seqs, a.heads), dim3(128), 0, s, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_merge launch: %s\n", cudaGetErrorString(e)); return -5; }
