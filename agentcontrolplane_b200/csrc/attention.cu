@@ -890,11 +890,15 @@ attn_decode_item_half_kernel(const __grid_constant__ CUtensorMap tm_k, const __g
 // =================================================================================
 // prefill (causal, chunk-capable: queries may start at any position of the sequence)
 // =================================================================================
-__global__ void __launch_bounds__(ATTN_THREADS, 2)
+// <NS, MINB>: ring depth and CTAs per SM.  <3, 2> is the measured default; <2, 3> (ACP_ATTN_PREFILL_3CTA=1,
+// experimental, unmeasured) trades a stage and ~32 registers (spilled) for a third CTA per SM — the kernel is
+// latency bound at 2 warps per scheduler (profiles/r1_v2_ncu_prefill_kernels.md).
+template <int NS, int MINB>
+__global__ void __launch_bounds__(ATTN_THREADS, MINB)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                     AttnPrefillArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  SmemLayout L = carve(smem_raw);
+  SmemLayout L = carve<NS>(smem_raw);
   const int blk = blockIdx.x, kh = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = a.heads / a.kv_heads;
@@ -911,7 +915,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&L.full_bar[s], 1);
       mbar_init(&L.empty_bar[s], CONSUMER_WARPS);
     }
@@ -921,7 +925,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   pdl_wait();
   if (warp == CONSUMER_WARPS) {
     if (lane == 0)
-      produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
+      produce_tiles<NS>(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
                     a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, last_pos + 1);
     return;
   }
@@ -945,8 +949,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   st.l[0] = st.l[1] = 0.f;
   const float sl2e = a.scale * 1.4426950408889634f;
   for (int it = 0; it < n_tiles; ++it) {
-    const int s = it % STAGES;
-    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+    const int s = it % NS;
+    const uint32_t ph = (uint32_t)(it / NS) & 1u;
     mbar_wait(&L.full_bar[s], ph);
     uint8_t* kt = L.stages + s * STAGE_BYTES;
     uint8_t* vt = kt + K_TILE_BYTES;
@@ -991,7 +995,8 @@ int attn_setup_attributes() {
   if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_item_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_H);
   if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_H);
   cudaError_t e1 = cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
-  cudaError_t e2 = cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  cudaError_t e2 = cudaFuncSetAttribute(attn_prefill_kernel<STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(attn_prefill_kernel<STAGES_H, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_H);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     fprintf(stderr, "[acp_infer] attention cudaFuncSetAttribute failed\n");
     return -5;
@@ -1061,7 +1066,9 @@ int launch_attn_prefill(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const 
   const int G = a.heads / a.kv_heads;
   if (a.heads % a.kv_heads != 0 || G > 16 || (16 % G) != 0) return -1;
   dim3 grid(num_blocks, a.kv_heads);
-  cudaError_t e = acp_launch(attn_prefill_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
+  static const bool three = [] { const char* e = getenv("ACP_ATTN_PREFILL_3CTA"); return e && *e == '1'; }();
+  cudaError_t e = three ? acp_launch(attn_prefill_kernel<STAGES_H, 3>, grid, dim3(ATTN_THREADS), ATTN_SMEM_H, s, tm_k, tm_v, a)
+                        : acp_launch(attn_prefill_kernel<STAGES, 2>, grid, dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_prefill launch: %s\n", cudaGetErrorString(e)); return -5; }
   return 0;
 }
