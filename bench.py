@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="dev only: truncate depth (result is then NOT a bench value)")
     ap.add_argument("--config", type=int, default=1, choices=sorted(WORKLOADS),
                     help="BASELINE.json config index (1 = default; 3 = 70B TP=8: run as ONE process on an 8-GPU box, --gpus 1)")
-    ap.add_argument("--max-tokens-per-step", type=int, default=4096, help="engine knob: token rows per prefill step (4096 measured 1.3 % faster than 8192)")
+    ap.add_argument("--max-tokens-per-step", type=int, default=4096, help="engine knob: token rows per prefill step (4096 measured 1.3 %% faster than 8192)")
     ap.add_argument("--tp", type=int, default=0, help="dev only: override the tensor-parallel degree of --config 3")
     args = ap.parse_args()
     WORKLOAD = dict(WORKLOADS[args.config])
