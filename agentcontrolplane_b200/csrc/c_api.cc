@@ -47,8 +47,9 @@ const char* acp_infer_version(void) { return "acp_infer 0.1.0 sm_100a"; }
 int acp_infer_init(const char* config_json, acp_engine** out) {
   if (!out) return ACP_ERR_INVALID;
   *out = nullptr;
+  acp_engine* e = nullptr;
   try {
-    acp_engine* e = new (std::nothrow) acp_engine();
+    e = new (std::nothrow) acp_engine();
     if (!e) return ACP_ERR_NOMEM;
     acp::Json cfg;
     std::string perr;
@@ -75,8 +76,10 @@ int acp_infer_init(const char* config_json, acp_engine** out) {
     *out = e;
     return ACP_OK;
   } catch (const std::bad_alloc&) {
+    try { delete e; } catch (...) {}
     return ACP_ERR_NOMEM;
   } catch (...) {
+    try { delete e; } catch (...) {}
     return ACP_ERR_INVALID;
   }
 }

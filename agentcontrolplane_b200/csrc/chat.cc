@@ -106,9 +106,13 @@ int parse_chat_request(const char* json, size_t len, ChatRequest* out, std::stri
     r.tools.push_back(std::move(td));
   }
   SamplingParams& sp = r.sampling;
-  if (root.find("max_completion_tokens")) sp.max_tokens = (int)root.get("max_completion_tokens").as_int(sp.max_tokens);
-  if (root.find("max_tokens") && !root.get("max_tokens").is_null()) sp.max_tokens = (int)root.get("max_tokens").as_int(sp.max_tokens);
-  if (sp.max_tokens <= 0) { *err = "max_tokens must be positive"; return 400; }
+  for (const char* key : {"max_completion_tokens", "max_tokens"}) {
+    const Json* mt = root.find(key);
+    if (!mt || mt->is_null()) continue;
+    const long long v = mt->as_int(0);
+    if (v <= 0) { *err = "max_tokens must be positive"; return 400; }
+    sp.max_tokens = (int)(v > 1000000000LL ? 1000000000LL : v);
+  }
   if (root.find("temperature") && !root.get("temperature").is_null()) sp.temperature = (float)root.get("temperature").as_double(0.0);
   if (sp.temperature < 0.f) { *err = "temperature must be >= 0"; return 400; }
   if (root.find("top_p") && !root.get("top_p").is_null()) sp.top_p = (float)root.get("top_p").as_double(1.0);

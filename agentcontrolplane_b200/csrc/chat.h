@@ -34,7 +34,7 @@ struct ToolDef {  // llmclient.Tool (acp/internal/llmclient/llm_client.go:33-50)
 };
 
 struct SamplingParams {
-  int max_tokens = 256;
+  int max_tokens = 0;       // 0 = the request set none: the engine fills in its default (engine.cc submit)
   float temperature = 0.f;  // the reference path sends temperature 0 => greedy
   int top_k = 0;
   float top_p = 1.f;

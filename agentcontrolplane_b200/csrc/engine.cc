@@ -69,6 +69,11 @@ int Engine::init(const char* config_json) {
   }
   if (cfg.find("seed")) mc.seed = (uint64_t)cfg.get("seed").as_int((long long)mc.seed);
   if (cfg.find("layers")) mc.layers = (int)cfg.get("layers").as_int(mc.layers);  // truncated-depth runs
+  if (mc.layers < 1 || mc.layers > 1024 || mc.hidden < 128 || mc.ffn < 64 || mc.vocab < 128 || mc.heads < 1 || mc.kv_heads < 1) {
+    fprintf(stderr, "[acp_infer] invalid model dimensions (layers=%d hidden=%d ffn=%d vocab=%d heads=%d kv_heads=%d)\n",
+            mc.layers, mc.hidden, mc.ffn, mc.vocab, mc.heads, mc.kv_heads);
+    return -1;
+  }
   ModelLimits lim;
   lim.max_batch = (int)cfg.get("max_batch").as_int(lim.max_batch);
   lim.max_tokens = (int)cfg.get("max_tokens_per_step").as_int(lim.max_tokens);
@@ -81,10 +86,19 @@ int Engine::init(const char* config_json) {
   if (cfg.find("prefix_cache")) prefix_cache_on_ = cfg.get("prefix_cache").as_bool(true);
   request_timeout_ms_ = (double)cfg.get("request_timeout_ms").as_int(0);
   if (cfg.find("splitk_target_ctas")) lim.splitk_target_ctas = (int)cfg.get("splitk_target_ctas").as_int(lim.splitk_target_ctas);
-  if (lim.max_batch < 1 || lim.max_tokens < 16 || lim.num_pages < 2 || lim.max_pages_per_seq < 1) {
+  if (lim.max_batch < 1 || lim.max_tokens < 16 || lim.num_pages < 2 || lim.max_pages_per_seq < 1 ||
+      lim.max_batch > (1 << 16) || lim.max_tokens > (1 << 20) || lim.max_pages_per_seq > (1 << 16)) {
     fprintf(stderr, "[acp_infer] invalid engine limits\n");
     return -1;
   }
+  // a decode step has one token row per running sequence: the row budget of a step can never be
+  // smaller than the batch (prefill chunking is result-invariant, so raising it changes no output)
+  if (lim.max_tokens < lim.max_batch) {
+    fprintf(stderr, "[acp_infer] max_tokens_per_step %d < max_batch %d: raised to %d\n", lim.max_tokens, lim.max_batch, lim.max_batch);
+    lim.max_tokens = lim.max_batch;
+  }
+  default_max_tokens_ = (int)cfg.get("default_max_tokens").as_int(default_max_tokens_);
+  if (default_max_tokens_ < 1) default_max_tokens_ = 1;
   const int device = (int)cfg.get("device").as_int(0);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -121,7 +135,9 @@ int Engine::init(const char* config_json) {
     for (int i = 0; i < tp_; ++i)
       inits.emplace_back([&, i] {
         Model* m = i == 0 ? &model_ : extra_[i - 1].get();
-        rcs[i] = m->init(mc, lim, devs[i], i, tp_, comms_[i], i == 0 ? nullptr : &model_, ckpt_.get());
+        // an exception escaping a std::thread is std::terminate: report it as an init failure instead
+        try { rcs[i] = m->init(mc, lim, devs[i], i, tp_, comms_[i], i == 0 ? nullptr : &model_, ckpt_.get()); }
+        catch (...) { rcs[i] = -4; }
       });
     for (auto& t : inits) t.join();
     for (int r : rcs) if (r != 0) return r;
@@ -211,8 +227,11 @@ void Engine::shutdown() {
       kv.second->status = 503;
       kv.second->error_type = "engine_shutdown";
       kv.second->error_msg = "engine is shutting down";
+      finished_unreported_.push_back(kv.first);   // a poller (integration/go/inference) must see them
     }
   }
+  running_.clear();
+  waiting_.clear();
   cv_done_.notify_all();
   if (ev0_) { cudaEventDestroy(ev0_); ev0_ = nullptr; }
   if (ev1_) { cudaEventDestroy(ev1_); ev1_ = nullptr; }
@@ -245,6 +264,14 @@ int Engine::submit(const char* json, size_t len, uint64_t* ticket) {
   if (status == 0) {
     s->prompt_len = (int)s->tokens.size();
     s->sampling = req.sampling;
+    if (s->sampling.max_tokens <= 0) {
+      // The reference sends no max_tokens unless LLM.spec.parameters.maxTokens is set
+      // (langchaingo_client.go:83-115) and the provider then generates until it stops by itself.
+      // Here: everything the context still holds, capped by "default_max_tokens" because KV pages for
+      // prompt + max_tokens are reserved at admission.
+      const long long left = (long long)max_ctx_tokens_ - s->prompt_len;
+      s->sampling.max_tokens = (int)std::max(1LL, std::min<long long>(left, default_max_tokens_));
+    }
     s->tools = std::move(req.tools);
     s->force_tokens = std::move(req.force_tokens);
     s->return_logits = std::max(0, std::min(req.return_logits, 64));
@@ -345,6 +372,20 @@ int Engine::result(uint64_t ticket, std::string* body, int* status) {
   if (s->finish_reason == "stop" && !text_ids.empty()) text_ids.pop_back();  // drop the stop token
   const std::string text = tok_->decode(text_ids);
   ParsedCompletion pc = parse_completion(text, s->tools, "call_" + std::to_string(ticket) + "_");
+  if (s->finish_reason == "length" && !s->tools.empty() && pc.tool_calls.empty()) {
+    size_t p = 0;
+    while (p < text.size() && (text[p] == ' ' || text[p] == '\n' || text[p] == '\t' || text[p] == '\r')) ++p;
+    if (p < text.size() && text[p] == '{') {
+      // A tool call cut by the completion budget would otherwise be recorded by the Task controller
+      // as a successful FinalAnswer holding half a JSON object (processLLMResponse,
+      // state_machine.go:608): surface a terminal 4xx instead (retrying gives the same cut).
+      *status = 422;
+      *body = build_error_response(422, "truncated_tool_call",
+                                   "completion reached max_tokens (" + std::to_string(s->sampling.max_tokens) +
+                                       ") inside a tool call; raise LLM.spec.parameters.maxTokens");
+      return 0;
+    }
+  }
   if (pc.tool_calls.empty() && pc.content.empty()) {
     // The Task controller loops forever on an empty assistant message
     // (state_machine.go:608/641 + checkToolCalls with zero ToolCalls): surface a terminal 4xx.
@@ -515,6 +556,7 @@ void Engine::finish(const std::shared_ptr<Sequence>& s, int status, const std::s
   s->t_done = clk::now();
   if (status == 200) ++stats_.requests_done; else ++stats_.requests_failed;
   finished_unreported_.push_back(s->ticket);
+  cv_done_.notify_all();
 }
 
 void Engine::fail_all_running(const std::string& msg) {

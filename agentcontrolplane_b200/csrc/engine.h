@@ -134,6 +134,7 @@ class Engine {
   EngineStats stats_;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   int max_ctx_tokens_ = 0;
+  int default_max_tokens_ = 1024;  // completion budget of a request that sets no max_tokens ("default_max_tokens")
 };
 
 }  // namespace acp

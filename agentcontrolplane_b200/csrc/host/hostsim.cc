@@ -9,6 +9,7 @@
 #include <unistd.h>
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <set>
@@ -522,6 +523,9 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
   bc.BaseURL = cfg.get("baseURL").as_string();
   bc.MaxTokens = (int)cfg.get("max_tokens").as_int(64);
   const int prompt_tokens = (int)cfg.get("prompt_tokens").as_int(0);
+  // BASELINE config 2: window lengths log-uniform on [prompt_tokens_min, prompt_tokens_max] (seeded per Task)
+  const int pt_min = (int)cfg.get("prompt_tokens_min").as_int(0), pt_max = (int)cfg.get("prompt_tokens_max").as_int(0);
+  const bool mixed = pt_min > 0 && pt_max >= pt_min;
   const int n_tools = (int)cfg.get("tools").as_int(0);
   const bool tool_loop = cfg.get("tool_loop").as_bool(false);
   const uint64_t seed = (uint64_t)cfg.get("seed").as_int(1);
@@ -572,7 +576,18 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
     user_len = std::max(16, prompt_tokens - overhead);
     window_tokens = overhead + user_len;
   }
+  long long window_sum = 0;
   for (int i = 0; i < n_tasks; ++i) {
+    int this_user_len = user_len;
+    if (mixed) {
+      // length = exp(U(ln min, ln max)), U from the splitmix of (length seed, task index); the length
+      // seed is fixed per configuration ("length_seed") so that every step runs the same distribution
+      const uint64_t ls = (uint64_t)cfg.get("length_seed").as_int(0xC0F162);
+      const double u = (double)(mix64(ls * 0x9E3779B97F4A7C15ull + (uint64_t)i) >> 11) / 9007199254740992.0;
+      const int target = (int)std::exp(std::log((double)pt_min) + u * (std::log((double)pt_max) - std::log((double)pt_min)));
+      this_user_len = std::max(16, target - overhead);
+    }
+    window_sum += overhead + this_user_len;
     task::Task t;
     t.Name = "task-" + std::to_string(i);
     t.UID = "uid-" + std::to_string(i);
@@ -580,7 +595,7 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
     t.Status.Phase = "ReadyForLLM";
     t.Status.Status = "Ready";
     t.Status.ContextWindow = task::buildInitialContextWindow(
-        {}, system_prompt, prompt_tokens > 0 ? synth_text(seed, i, user_len) : std::string("What is the capital of France?"));
+        {}, system_prompt, (prompt_tokens > 0 || mixed) ? synth_text(seed, i, this_user_len) : std::string("What is the capital of France?"));
     store.Put("Task", t.Name, task::task_to_json(t));
   }
 
@@ -685,6 +700,7 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
   out.set("store_writes", Json(store.writes()));
   out.set("store_reads", Json(store.reads()));
   out.set("prompt_tokens", Json(prompt_tokens > 0 ? window_tokens : overhead + user_len));
+  out.set("prompt_tokens_total", Json(window_sum));
   Json ph = Json::object();
   for (auto& kv : phases) ph.set(kv.first, Json(kv.second));
   out.set("final_phases", ph);

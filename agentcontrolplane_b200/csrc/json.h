@@ -38,7 +38,13 @@ class Json {
   bool as_bool(bool def = false) const { return type_ == Bool ? b_ : def; }
   double as_double(double def = 0) const { return type_ == Number ? d_ : def; }
   long long as_int(long long def = 0) const {
-    return type_ == Number ? (is_int_ ? i_ : (long long)d_) : def;
+    if (type_ != Number) return def;
+    if (is_int_) return i_;
+    // out-of-range / NaN doubles (untrusted request bodies): the cast would be undefined behaviour
+    if (!(d_ == d_)) return def;
+    if (d_ >= 9.2e18) return 9200000000000000000LL;
+    if (d_ <= -9.2e18) return -9200000000000000000LL;
+    return (long long)d_;
   }
   const std::string& as_string() const { static const std::string e; return type_ == String ? s_ : e; }
   const std::vector<Json>& items() const { return a_; }

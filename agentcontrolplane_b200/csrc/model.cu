@@ -22,6 +22,8 @@ bool model_preset(const std::string& name, ModelConfig* c) {
   m.name = name;
   if (name == "tiny") { m.hidden = 512; m.layers = 2; m.heads = 4; m.kv_heads = 1; m.ffn = 1024; }
   else if (name == "tiny-g2") { m.hidden = 512; m.layers = 3; m.heads = 4; m.kv_heads = 2; m.ffn = 1536; }
+  // the head grouping of one Llama-3-70B tensor-parallel shard at TP=8: 8 query heads on 1 KV head
+  else if (name == "tiny-g8") { m.hidden = 1024; m.layers = 2; m.heads = 8; m.kv_heads = 1; m.ffn = 2048; }
   else if (name == "llama-3-8b-l2") { m.hidden = 4096; m.layers = 2; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; }
   else if (name == "llama-3-8b") { m.hidden = 4096; m.layers = 32; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; }
   else if (name == "llama-3-70b") { m.hidden = 8192; m.layers = 80; m.heads = 64; m.kv_heads = 8; m.ffn = 28672; }

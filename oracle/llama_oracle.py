@@ -64,6 +64,8 @@ class LlamaConfig:
 PRESETS = {
     "tiny": LlamaConfig("tiny", hidden=512, layers=2, heads=4, kv_heads=1, ffn=1024),
     "tiny-g2": LlamaConfig("tiny-g2", hidden=512, layers=3, heads=4, kv_heads=2, ffn=1536),
+    # the head grouping of one Llama-3-70B shard at TP=8 (8 query heads on 1 KV head)
+    "tiny-g8": LlamaConfig("tiny-g8", hidden=1024, layers=2, heads=8, kv_heads=1, ffn=2048),
     "llama-3-8b-l2": LlamaConfig("llama-3-8b-l2", hidden=4096, layers=2, heads=32, kv_heads=8,
                                  ffn=14336),
     "llama-3-8b": LlamaConfig("llama-3-8b", hidden=4096, layers=32, heads=32, kv_heads=8, ffn=14336),

@@ -31,7 +31,11 @@ def _prompt(rng, n):
     return [128000] + [int(t) for t in rng.integers(0, 256, size=n - 1)]
 
 
-@pytest.fixture(scope="module", params=["tiny", "tiny-g2"])
+# tiny / tiny-g2: hidden 512, G = 4 / 2.  tiny-g8: the head grouping of a Llama-3-70B TP=8 shard (8 query
+# heads on 1 KV head).  llama-3-8b-l2: the REAL Llama-3-8B width (hidden 4096, 32 q / 8 kv heads, ffn 14336,
+# vocab 128256) at 2 layers, where the numpy oracle still finishes in seconds; full depth is covered by
+# tests/test_fulldepth_gpu.py.
+@pytest.fixture(scope="module", params=["tiny", "tiny-g2", "tiny-g8", "llama-3-8b-l2"])
 def eng(request):
     e = Engine({"model": request.param, "max_batch": 64, "kv_pages": 512, "max_tokens_per_step": 1024})
     e.model_name = request.param
@@ -269,3 +273,33 @@ def test_long_context_chunked_prefill(eng):
     assert eng.wait(t, 10000)
     st, body = eng.result(t)
     assert st == 400 and body["error"]["type"] == "context_length_exceeded"
+
+
+def test_config1_shape_64_windows_of_512_tokens(eng):
+    """BASELINE config 1's batch shape: 64 concurrent Tasks x 512-token windows, greedy.  Every
+    sequence is compared with the oracle on its first tokens (a sample at the real 8B width, where one
+    oracle pass costs seconds), and all 64 must equal what the same prompt produces alone."""
+    cfg = PRESETS[eng.model_name]
+    rng = np.random.default_rng(64512)
+    prompts = [_prompt(rng, 512) for _ in range(64)]
+    n_new = 6
+    big = Engine({"model": eng.model_name, "max_batch": 64, "kv_pages": 64 * 18 + 8, "max_tokens_per_step": 4096,
+                  "prefix_cache": False})
+    try:
+        ts = [big.submit({"model": eng.model_name, "max_tokens": n_new, "acp": {"prompt_token_ids": p}}) for p in prompts]
+        outs = []
+        for t in ts:
+            assert big.wait(t, 300000)
+            st, body = big.result(t)
+            assert st == 200, body
+            outs.append(body["acp"]["token_ids"])
+        s = big.stats()
+        assert s["prefill_tokens"] == 64 * 512 and s["decode_tokens"] >= 64 * (n_new - 1) - 64
+        alone, _, _ = _run(eng, prompts[5], n_new)
+        assert alone == outs[5]
+    finally:
+        big.close()
+    sample = range(64) if cfg.hidden <= 1024 else (0, 13, 31, 63)
+    for i in sample:
+        want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(prompts[i], n_new, eos=(128001, 128008, 128009))
+        assert_tokens_match(outs[i], want, margins, where=i)
