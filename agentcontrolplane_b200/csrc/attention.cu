@@ -994,6 +994,7 @@ int attn_setup_attributes() {
   if (e0 != cudaSuccess) { fprintf(stderr, "[acp_infer] attention cudaFuncSetAttribute failed\n"); return -5; }
   if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_item_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_H);
   if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_H);
+  if (attn_prefill_tc_setup() != 0) return -5;
   cudaError_t e1 = cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
   cudaError_t e2 = cudaFuncSetAttribute(attn_prefill_kernel<STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
   if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(attn_prefill_kernel<STAGES_H, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_H);
@@ -1058,7 +1059,14 @@ int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const A
   return 0;
 }
 
-int attn_prefill_block_tokens(int heads, int kv_heads) { return (16 / (heads / kv_heads)) * CONSUMER_WARPS; }
+bool attn_prefill_tc_enabled() {
+  static const bool on = [] { const char* e = getenv("ACP_ATTN_PREFILL_TC"); return !(e && *e == '0'); }();
+  return on;
+}
+int attn_prefill_block_tokens(int heads, int kv_heads) {
+  if (attn_prefill_tc_enabled()) return attn_prefill_tc_block_tokens(heads, kv_heads);
+  return (16 / (heads / kv_heads)) * CONSUMER_WARPS;
+}
 
 int launch_attn_prefill(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnPrefillArgs& a,
                         int num_blocks, cudaStream_t s) {

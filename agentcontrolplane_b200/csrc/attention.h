@@ -57,6 +57,14 @@ size_t attn_decode_ws_floats(int max_batch, int heads, int kv_heads, int max_chu
 int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnDecodeArgs& a,
                        cudaStream_t s);
 int attn_prefill_block_tokens(int heads, int kv_heads);
+// tcgen05 prefill attention (attention_prefill_tc.cu): 128 query rows = 128/G tokens x G heads per CTA
+int attn_prefill_tc_setup();
+int attn_prefill_tc_block_tokens(int heads, int kv_heads);
+int attn_make_kv_half_map(CUtensorMap* out, const void* base, uint64_t num_pages, int kv_heads);
+int attn_make_q_map(CUtensorMap* out, const void* qbuf, uint64_t rows, int heads, int kv_heads);
+int launch_attn_prefill_tc(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                           const AttnPrefillArgs& a, int num_blocks, cudaStream_t s);
+bool attn_prefill_tc_enabled();   // ACP_ATTN_PREFILL_TC=0 selects round 1's mma.sync kernel (A/B only)
 int launch_attn_prefill(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnPrefillArgs& a,
                         int num_blocks, cudaStream_t s);
 

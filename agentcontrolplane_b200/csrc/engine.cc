@@ -775,9 +775,15 @@ bool Engine::step() {
   const int* toks = model_.host_tokens();
   const auto now = clk::now();
   std::lock_guard<std::mutex> lk(mu_);
-  if (prefill) { ++stats_.prefill_steps; stats_.prefill_tokens += T; stats_.prefill_ms += step_ms; }
+  double qk_pairs = 0;   // (query token, visible key) pairs of this step
+  for (int b = 0; b < B; ++b) {
+    const double c0 = part[b]->n_cached, q = take[b];
+    qk_pairs += q * c0 + q * (q + 1) / 2;
+  }
+  const double flops = model_.config().step_flops(T, ns, qk_pairs);
+  if (prefill) { ++stats_.prefill_steps; stats_.prefill_tokens += T; stats_.prefill_ms += step_ms; stats_.prefill_flops += flops; }
   else {
-    ++stats_.decode_steps; stats_.decode_tokens += B; stats_.decode_ms += step_ms;
+    ++stats_.decode_steps; stats_.decode_tokens += B; stats_.decode_ms += step_ms; stats_.decode_flops += flops;
     for (int b = 0; b < B; ++b) stats_.decode_ctx_tokens += part[b]->n_cached;  // keys read (excl. own)
     if (stats_.decode_step_ms.size() < 65536) stats_.decode_step_ms.push_back(step_ms);
   }
@@ -875,6 +881,8 @@ std::string Engine::stats_json() {
   j.set("prefill_steps", Json(stats_.prefill_steps));
   j.set("prefill_tokens", Json(stats_.prefill_tokens));
   j.set("prefill_ms", Json(stats_.prefill_ms));
+  j.set("prefill_flops_algorithmic", Json(stats_.prefill_flops));
+  j.set("decode_flops_algorithmic", Json(stats_.decode_flops));
   j.set("requests_done", Json(stats_.requests_done));
   j.set("requests_failed", Json(stats_.requests_failed));
   j.set("kernel_launches", Json(model_.launches()));
@@ -893,6 +901,7 @@ std::string Engine::stats_json() {
   if (!v.empty()) {
     std::sort(v.begin(), v.end());
     j.set("decode_step_ms_p50", Json((double)v[v.size() / 2]));
+    j.set("decode_step_ms_p99", Json((double)v[std::min(v.size() - 1, (size_t)(v.size() * 0.99))]));
     j.set("decode_step_ms_min", Json((double)v.front()));
     j.set("decode_step_ms_max", Json((double)v.back()));
   }

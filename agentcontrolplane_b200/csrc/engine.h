@@ -62,6 +62,7 @@ struct EngineStats {
   long long decode_steps = 0, decode_tokens = 0, decode_ctx_tokens = 0;
   long long prefill_steps = 0, prefill_tokens = 0;
   double decode_ms = 0, prefill_ms = 0;
+  double prefill_flops = 0, decode_flops = 0;   // algorithmic FLOPs: GEMMs + causal attention + LM head
   long long requests_done = 0, requests_failed = 0;
   std::vector<float> decode_step_ms;
 };

@@ -48,6 +48,24 @@ int tma_encode_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64
   return 0;
 }
 
+int tma_encode_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint32_t box0, uint32_t box1, uint32_t box2) {
+  if (tma_init() != 0) return -5;
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstride[2] = {(cuuint64_t)d0 * 2, (cuuint64_t)d0 * d1 * 2};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[acp_infer] cuTensorMapEncodeTiled(3d) failed (%d) dims=%llu x %llu x %llu box=%u x %u x %u\n", (int)r,
+            (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, box0, box1, box2);
+    return -5;
+  }
+  return 0;
+}
+
 // Weights are stored TILED in HBM: tile (m_tile, kb) = 128 rows x 64 bf16 = 16 KiB CONTIGUOUS,
 // tiles ordered [m_tile][kb].  One TMA box is then one contiguous 16 KiB read (DRAM-page friendly)
 // instead of 128 segments of 128 B strided by a whole weight row.  Seen by TMA as a 2-D tensor

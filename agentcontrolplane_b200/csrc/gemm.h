@@ -17,6 +17,9 @@ struct TmaMaps {
 int tma_init();  // resolves cuTensorMapEncodeTiled through cudart; 0 on success
 int tma_encode_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                        uint32_t box_rows);
+// 3-D bf16 tensor {d0 (contiguous), d1, d2} with byte strides {d0*2 for d1, d0*d1*2 for d2}, 128-byte swizzle
+int tma_encode_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint32_t box0, uint32_t box1, uint32_t box2);
 int tma_make_weight(TmaMaps* m, const void* base, uint64_t rows, uint64_t cols);
 int tma_make_act(TmaMaps* m, const void* base, uint64_t rows, uint64_t cols);
 

@@ -403,8 +403,22 @@ extern "C" int acp_host_task_step(acp_engine* engine, const char* input_json, ch
   const std::string op = in.get("op").as_string();
   std::string err, request_json;
   task::Result res;
+  // cluster objects the step may look up: [{"kind": "Agent"|"LLM"|"Secret"|"ContactChannel", "object": {...}}]
+  for (const Json& o : in.get("objects").items())
+    store.Put(o.get("kind").as_string(), o.get("object").get("metadata").get("name").as_string(), o.get("object"));
   if (op == "checkToolCalls") {
     res = sm.checkToolCalls(&t, &err);
+  } else if (op == "sendLLMRequestFromCluster") {
+    // the whole ReadyForLLM arm: validateTaskAndAgent, getLLMAndCredentials, CreateClient, collectTools, LLM step
+    task::MCPToolsByServer mcp;
+    for (const auto& kv : in.get("mcp").members()) mcp[kv.first] = kv.second.items();
+    store.Put("Task", t.Name, task::task_to_json(t));
+    llmclient::Context ctx;
+    res = sm.sendLLMRequestFromCluster(ctx, &t, mcp, engine, &err);
+  } else if (op == "collectTools") {
+    task::MCPToolsByServer mcp;
+    for (const auto& kv : in.get("mcp").members()) mcp[kv.first] = kv.second.items();
+    tools = sm.collectTools(in.get("agent"), mcp);
   } else {
     const Json& llm = in.get("llm");
     const std::string provider = llm.get("provider").as_string();
@@ -441,6 +455,20 @@ extern "C" int acp_host_task_step(acp_engine* engine, const char* input_json, ch
     for (Json& j : store.ListToolCalls(t.Name, t.Status.ToolCallRequestID)) tcs.push(j);
   out.set("toolcalls", tcs);
   out.set("store_writes", Json(store.writes() - writes0));
+  if (op == "collectTools") {
+    Json tj = Json::array();
+    for (const Tool& tl : tools) {
+      Json o = Json::object(), fn = Json::object();
+      fn.set("name", Json(tl.Function.Name));
+      fn.set("description", Json(tl.Function.Description));
+      fn.set("parameters", tl.Function.Parameters);
+      o.set("type", Json(tl.Type));
+      o.set("function", fn);
+      o.set("acpToolType", Json(tl.ACPToolType));
+      tj.push(o);
+    }
+    out.set("tools", tj);
+  }
   if (!request_json.empty()) out.set("request_json", Json(request_json));
   return ret_json(out, out_json);
 }
@@ -577,6 +605,8 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
     window_tokens = overhead + user_len;
   }
   long long window_sum = 0;
+  int window_max = 0;
+  const bool dry_run = cfg.get("dry_run").as_bool(false);   // sizes only: no Task is reconciled
   for (int i = 0; i < n_tasks; ++i) {
     int this_user_len = user_len;
     if (mixed) {
@@ -588,6 +618,8 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
       this_user_len = std::max(16, target - overhead);
     }
     window_sum += overhead + this_user_len;
+    window_max = std::max(window_max, overhead + this_user_len);
+    if (dry_run) continue;
     task::Task t;
     t.Name = "task-" + std::to_string(i);
     t.UID = "uid-" + std::to_string(i);
@@ -682,7 +714,7 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
     }
   };
   std::vector<std::thread> pool;
-  for (int w = 0; w < workers; ++w) pool.emplace_back(worker);
+  for (int w = 0; w < workers && !dry_run; ++w) pool.emplace_back(worker);
   for (auto& th : pool) th.join();
   const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
@@ -701,6 +733,7 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
   out.set("store_reads", Json(store.reads()));
   out.set("prompt_tokens", Json(prompt_tokens > 0 ? window_tokens : overhead + user_len));
   out.set("prompt_tokens_total", Json(window_sum));
+  out.set("prompt_tokens_max", Json(window_max));
   Json ph = Json::object();
   for (auto& kv : phases) ph.set(kv.first, Json(kv.second));
   out.set("final_phases", ph);

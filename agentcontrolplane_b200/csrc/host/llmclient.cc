@@ -108,13 +108,32 @@ static Json tools_to_wire(const std::vector<Tool>& tools) {
   return arr;
 }
 
+BaseConfig base_config_from_json(const Json& p) {
+  BaseConfig bc;
+  bc.Model = p.get("model").as_string();
+  bc.BaseURL = p.get("baseUrl").as_string();
+  if (bc.BaseURL.empty()) bc.BaseURL = p.get("baseURL").as_string();   // spelling used by this repo's test hooks
+  bc.Temperature = p.get("temperature").as_string();
+  bc.TopP = p.get("topP").as_string();
+  bc.MaxTokens = (int)p.get("maxTokens").as_int(0);
+  bc.TopK = (int)p.get("topK").as_int(0);
+  return bc;
+}
+
 std::string build_chat_request_json(const std::string& model, const std::vector<Message>& messages,
                                     const std::vector<Tool>& tools, int max_tokens,
-                                    const Json* acp_ext) {
+                                    const Json* acp_ext, const BaseConfig* sampling) {
   Json body = Json::object();
   body.set("model", Json(model));
   body.set("messages", messages_to_wire(messages));
-  body.set("temperature", Json(0));  // ChatRequest.Temperature has no omitempty; ACP sets none
+  // ChatRequest.Temperature has no omitempty and ACP's SendRequest sets no option: the reference
+  // sends 0 (greedy).  The local provider forwards LLM.spec.parameters when they are set.
+  double temperature = 0.0;
+  if (sampling && !sampling->Temperature.empty()) temperature = atof(sampling->Temperature.c_str());
+  if (temperature == 0.0) body.set("temperature", Json(0));
+  else body.set("temperature", Json(temperature));
+  if (sampling && !sampling->TopP.empty()) body.set("top_p", Json(atof(sampling->TopP.c_str())));
+  if (sampling && sampling->TopK > 0) body.set("top_k", Json(sampling->TopK));
   if (max_tokens > 0) body.set("max_tokens", Json(max_tokens));
   if (!tools.empty()) body.set("tools", tools_to_wire(tools));  // :93-99 only when present
   if (acp_ext && acp_ext->is_object()) body.set("acp", *acp_ext);
@@ -157,7 +176,7 @@ bool LocalClient::SendRequest(const Context& ctx, const std::vector<Message>& me
     return false;
   }
   const std::string body = build_chat_request_json(cfg_.Model, messages, tools, cfg_.MaxTokens,
-                                                   has_ext_ ? &ext_ : nullptr);
+                                                   has_ext_ ? &ext_ : nullptr, &cfg_);
   uint64_t ticket = 0;
   int rc = acp_infer_submit(engine_, body.data(), body.size(), &ticket);
   if (rc != ACP_OK) {

@@ -59,12 +59,21 @@ class LLMClient {
 };
 
 // acp.BaseConfig subset the hot path passes on (langchaingo_client.go:33-39): Model, BaseURL
-struct BaseConfig { std::string Model, BaseURL; int MaxTokens = 0; };
+// acp.BaseConfig (acp/api/v1alpha1/llm_types.go:41-71).  Temperature / TopP are STRINGS in the CRD
+// (pattern-validated decimals); MaxTokens / TopK are optional ints (0 = unset).  The reference's
+// langchaingo path reads only Model and BaseURL (langchaingo_client.go:31-73); the local provider
+// honours all of them.
+struct BaseConfig {
+  std::string Model, BaseURL, Temperature, TopP;
+  int MaxTokens = 0, TopK = 0;
+};
+// BaseConfig from the JSON of LLM.spec.parameters (field names of the CRD)
+BaseConfig base_config_from_json(const Json& params);
 
 // wire conversion shared by both clients
 std::string build_chat_request_json(const std::string& model, const std::vector<Message>& messages,
                                     const std::vector<Tool>& tools, int max_tokens,
-                                    const Json* acp_ext);
+                                    const Json* acp_ext, const BaseConfig* sampling = nullptr);
 // convertFromLangchainResponse (langchaingo_client.go:208-282) on an OpenAI chat.completion body
 bool convert_from_response_json(const std::string& body, Message* out, std::string* err);
 

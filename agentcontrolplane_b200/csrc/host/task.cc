@@ -286,9 +286,149 @@ std::vector<Tool> ConvertMCPTools(const std::vector<Json>& mcpTools, const std::
   return out;
 }
 
+Tool ToolFromContactChannel(const Json& channel) {
+  Tool t;
+  t.Type = "function";
+  t.Function.Parameters = message_param_schema();
+  const std::string name = channel.get("metadata").get("name").as_string();
+  const Json& spec = channel.get("spec");
+  const std::string type = spec.get("type").as_string();
+  if (type == "email") {
+    t.Function.Name = name + "__human_contact_email";
+    t.Function.Description = spec.get("email").get("contextAboutUser").as_string();
+    if (t.Function.Description.empty()) t.Function.Description = "Contact a human via email";
+  } else if (type == "slack") {
+    t.Function.Name = name + "__human_contact_slack";
+    t.Function.Description = spec.get("slack").get("contextAboutChannelOrUser").as_string();
+    if (t.Function.Description.empty()) t.Function.Description = "Contact a human via Slack";
+  } else {
+    t.Function.Name = name + "__human_contact";
+    t.Function.Description = "Contact a human via " + type + " channel";
+  }
+  t.ACPToolType = "HumanContact";
+  return t;
+}
+
 // ---------------------------------------------------------------------------------
 // state machine
 // ---------------------------------------------------------------------------------
+// apierrors.NewNotFound(...).Error() for a GET of `kind` `name` (what the reference stores in Status.Error)
+static std::string not_found_error(const std::string& resource, const std::string& name) {
+  return resource + ".acp.humanlayer.dev \"" + name + "\" not found";
+}
+
+Result StateMachine::validateTaskAndAgent(Task* task, Task* statusUpdate, Json* agent, bool* ok, std::string* err) {
+  (void)err;
+  *ok = false;
+  TaskStatus& st = statusUpdate->Status;
+  if (!store_->Get("Agent", task->AgentName, agent)) {   // apierrors.IsNotFound (:384-391)
+    st.Ready = false;
+    st.Status = "Pending";
+    st.Phase = "Pending";
+    st.StatusDetail = "Waiting for Agent to exist";
+    st.Error.clear();
+    recorder_->Emit("Normal", "Waiting", "Waiting for Agent to exist");
+    store_->Put("Task", task->Name, task_to_json(*statusUpdate));
+    *task = *statusUpdate;
+    Result r; r.RequeueAfter = DefaultRequeueDelay;
+    return r;
+  }
+  if (!agent->get("status").get("ready").as_bool(false)) {  // :408-420
+    const std::string msg = "Waiting for agent \"" + agent->get("metadata").get("name").as_string() + "\" to become ready";
+    st.Ready = false;
+    st.Status = "Pending";
+    st.Phase = "Pending";
+    st.StatusDetail = msg;
+    st.Error.clear();
+    recorder_->Emit("Normal", "Waiting", msg);
+    store_->Put("Task", task->Name, task_to_json(*statusUpdate));
+    *task = *statusUpdate;
+    Result r; r.RequeueAfter = DefaultRequeueDelay;
+    return r;
+  }
+  *ok = true;
+  return Result();
+}
+
+bool StateMachine::getLLMAndCredentials(const Json& agent, Task* task, Task* statusUpdate, Json* llm,
+                                        std::string* apiKey, std::string* err) {
+  TaskStatus& st = statusUpdate->Status;
+  auto fail = [&](const std::string& detail, const std::string& error, const std::string& reason, const std::string& event) {
+    st.Ready = false;
+    st.Status = "Error";
+    st.Phase = "Failed";
+    st.StatusDetail = detail;
+    st.Error = error;
+    recorder_->Emit("Warning", reason, event);
+    store_->Put("Task", task->Name, task_to_json(*statusUpdate));
+    *task = *statusUpdate;
+    *err = error;
+    return false;
+  };
+  const std::string llm_name = agent.get("spec").get("llmRef").get("name").as_string();
+  if (!store_->Get("LLM", llm_name, llm)) {   // :485-497
+    const std::string e = not_found_error("llms", llm_name);
+    return fail("Failed to get LLM: " + e, e, "LLMFetchFailed", e);
+  }
+  const Json& spec = llm->get("spec");
+  const Json& key_from = spec.get("apiKeyFrom");
+  apiKey->clear();
+  if (spec.get("provider").as_string() == "local" && !key_from.is_object())
+    return true;   // no credentials: the engine lives in this process (the reference would nil-deref at :504)
+  const std::string secret_name = key_from.get("secretKeyRef").get("name").as_string();
+  Json secret;
+  if (!store_->Get("Secret", secret_name, &secret)) {   // :501-517
+    // core/v1 objects have no API group in the NotFound text
+    const std::string e_core = "secrets \"" + secret_name + "\" not found";
+    return fail("Failed to get API key secret: " + e_core, e_core, "APIKeySecretFetchFailed", e_core);
+  }
+  *apiKey = secret.get("data").get(key_from.get("secretKeyRef").get("key").as_string()).as_string();
+  if (apiKey->empty())   // :520-535
+    return fail("API key is empty", "API key is empty", "EmptyAPIKey", "API key is empty");
+  return true;
+}
+
+std::vector<Tool> StateMachine::collectTools(const Json& agent, const MCPToolsByServer& mcp) {
+  std::vector<Tool> tools;
+  const Json& spec = agent.get("spec");
+  for (const Json& ref : spec.get("mcpServers").items()) {          // :545-554
+    auto it = mcp.find(ref.get("name").as_string());
+    if (it == mcp.end()) continue;
+    for (Tool& t : ConvertMCPTools(it->second, it->first)) tools.push_back(std::move(t));
+  }
+  for (const Json& ref : agent.get("status").get("validHumanContactChannels").items()) {   // :557-567
+    Json ch;
+    if (!store_->Get("ContactChannel", ref.get("name").as_string(), &ch)) continue;
+    tools.push_back(ToolFromContactChannel(ch));
+  }
+  std::vector<std::pair<std::string, std::string>> subs;               // :570-580
+  for (const Json& ref : spec.get("subAgents").items()) {
+    Json sub;
+    if (!store_->Get("Agent", ref.get("name").as_string(), &sub)) continue;
+    subs.emplace_back(sub.get("metadata").get("name").as_string(), sub.get("spec").get("description").as_string());
+  }
+  for (Tool& t : ConvertSubAgents(subs)) tools.push_back(std::move(t));
+  return tools;
+}
+
+Result StateMachine::sendLLMRequestFromCluster(const llmclient::Context& ctx, Task* task, const MCPToolsByServer& mcp,
+                                               acp_engine* engine, std::string* err) {
+  err->clear();
+  Task statusUpdate = *task;
+  Json agent;
+  bool ok = false;
+  Result r = validateTaskAndAgent(task, &statusUpdate, &agent, &ok, err);   // :183-186
+  if (!ok) return r;
+  Json llm;
+  std::string apiKey;
+  if (!getLLMAndCredentials(agent, task, &statusUpdate, &llm, &apiKey, err)) return Result();   // :188-191
+  const std::string provider = llm.get("spec").get("provider").as_string();
+  const llmclient::BaseConfig bc = llmclient::base_config_from_json(llm.get("spec").get("parameters"));
+  ClientFactory factory = [&](std::string* cerr) { return llmclient::NewLLMClient(provider, apiKey, bc, engine, cerr); };
+  const std::vector<Tool> tools = collectTools(agent, mcp);   // :220
+  return sendLLMRequest(ctx, task, tools, factory, err);
+}
+
 Result StateMachine::sendLLMRequest(const llmclient::Context& ctx, Task* task, const std::vector<Tool>& tools,
                                     const ClientFactory& factory, std::string* err) {
   err->clear();

@@ -88,6 +88,12 @@ std::string GetUserMessagePreview(const std::string& userMessage, const std::vec
 std::string GenerateK8sRandomString(int n);
 std::vector<Tool> ConvertSubAgents(const std::vector<std::pair<std::string, std::string>>& agents);
 std::vector<Tool> ConvertMCPTools(const std::vector<Json>& mcpTools, const std::string& serverName);
+// llmclient.ToolFromContactChannel (acp/internal/llmclient/llm_client.go:53-99); `channel` is the
+// ContactChannel CR as JSON (metadata.name, spec.type, spec.email.contextAboutUser, spec.slack.contextAboutChannelOrUser)
+Tool ToolFromContactChannel(const Json& channel);
+
+// mcpManager.GetTools (out of scope: the MCP servers themselves): server name -> its tool list
+using MCPToolsByServer = std::map<std::string, std::vector<Json>>;
 
 using ClientFactory = std::function<std::unique_ptr<llmclient::LLMClient>(std::string* err)>;
 
@@ -103,6 +109,21 @@ class StateMachine {
                          const std::vector<Tool>& tools, std::string* err);
   Result handleLLMError(Task* statusUpdate, const llmclient::Error& e, std::string* err);
   Result checkToolCalls(Task* task, std::string* err);
+  // ---- the whole ReadyForLLM arm of the reference, Kubernetes lookups included (emulated store) ----
+  // validateTaskAndAgent (state_machine.go:379-424): Agent exists and Status.Ready; *agent = the CR.
+  // Returns a non-zero Result (RequeueAfter 5 s) when the Task has to wait; *ok tells them apart.
+  Result validateTaskAndAgent(Task* task, Task* statusUpdate, Json* agent, bool* ok, std::string* err);
+  // getLLMAndCredentials (state_machine.go:480-538).  provider `local` needs no Secret: the
+  // reference dereferences llm.Spec.APIKeyFrom unconditionally (:504) and rejects an empty key
+  // (:520-535); both are skipped for `local` when apiKeyFrom is absent.
+  bool getLLMAndCredentials(const Json& agent, Task* task, Task* statusUpdate, Json* llm, std::string* apiKey,
+                            std::string* err);
+  // collectTools (state_machine.go:540-583): MCP server tools, contact channels, sub-agents, in that order
+  std::vector<Tool> collectTools(const Json& agent, const MCPToolsByServer& mcp);
+  // sendLLMRequest exactly as the reference runs it (state_machine.go:162-288): lease, a5, a6,
+  // CreateClient from the LLM CR (provider switch), a8, then the LLM step above.
+  Result sendLLMRequestFromCluster(const llmclient::Context& ctx, Task* task, const MCPToolsByServer& mcp,
+                                   acp_engine* engine, std::string* err);
   // when true the per-step Lease create/delete of acquireTaskLease/releaseTaskLease
   // (state_machine.go:1069-1145) is emulated as two store writes (reference behaviour)
   bool emulate_lease = true;

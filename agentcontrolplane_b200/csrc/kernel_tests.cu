@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "gemm_tcgen05.cuh"
+#include "attention.h"
 #include <string.h>
 #include <vector>
 
@@ -112,6 +113,102 @@ extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int 
       float ms = 0.f;
       ACP_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
       if (it >= 2) total += ms;  // two warm-up launches
+    }
+    *elapsed_ms = total / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  return 0;
+}
+
+
+extern "C" int acp_kernel_attn_prefill(const uint16_t* q, const uint16_t* k, const uint16_t* v, int heads, int kv_heads,
+                                       int q_len, int ctx, int impl, uint16_t* out, int iters, float* elapsed_ms) {
+  if (acp_kernel_device_count() <= 0) {
+    fprintf(stderr, "[acp_infer] no CUDA device: kernels cannot run (no CPU fallback)\n");
+    return -5;
+  }
+  if (!q || !k || !v || !out || q_len <= 0 || ctx < q_len || heads % kv_heads) return -1;
+  if (attn_setup_attributes() != 0) return -5;
+  const int n_pages_seq = (ctx + KV_PAGE - 1) / KV_PAGE;
+  const int num_pages = n_pages_seq + 3;     // page 0 reserved (all zero), two spare
+  const int max_pages = n_pages_seq + 2;
+  // shuffled page table: page i of the sequence -> physical page perm[i] in 1..num_pages-1
+  std::vector<int> pt(max_pages, 0);
+  for (int i = 0; i < n_pages_seq; ++i) pt[i] = 1 + (int)(((long long)i * 7 + 3) % (num_pages - 1));
+  {  // make it a permutation (7 may share a factor with num_pages - 1): fall back to reversed order
+    std::vector<char> seen(num_pages, 0);
+    bool ok = true;
+    for (int i = 0; i < n_pages_seq; ++i) { if (seen[pt[i]]) ok = false; seen[pt[i]] = 1; }
+    if (!ok) for (int i = 0; i < n_pages_seq; ++i) pt[i] = num_pages - 1 - i;
+  }
+  const size_t blk_elems = (size_t)KV_PAGE * HEAD_DIM;   // one (page, kv head) block
+  std::vector<uint16_t> kc((size_t)num_pages * kv_heads * blk_elems, 0), vc(kc.size(), 0);
+  for (int t = 0; t < ctx; ++t)
+    for (int h = 0; h < kv_heads; ++h)
+      for (int d = 0; d < HEAD_DIM; ++d) {
+        const size_t dst = ((size_t)pt[t / KV_PAGE] * kv_heads + h) * blk_elems + (size_t)(d >> 6) * (KV_PAGE * 64) +
+                           (size_t)(t % KV_PAGE) * 64 + (d & 63);
+        kc[dst] = k[((size_t)t * kv_heads + h) * HEAD_DIM + d];
+        vc[dst] = v[((size_t)t * kv_heads + h) * HEAD_DIM + d];
+      }
+  const int T_cap = ((q_len + 255) / 256) * 256;
+  DevBuf dq, dk, dv, dout, dints, dflush;
+  const size_t q_elems = (size_t)q_len * heads * HEAD_DIM;
+  if (dq.alloc((size_t)T_cap * heads * HEAD_DIM * 2) || dk.alloc(kc.size() * 2) || dv.alloc(vc.size() * 2) ||
+      dout.alloc((size_t)T_cap * heads * HEAD_DIM * 2))
+    return -5;
+  ACP_CUDA_CHECK(cudaMemset(dq.p, 0, (size_t)T_cap * heads * HEAD_DIM * 2));
+  ACP_CUDA_CHECK(cudaMemset(dout.p, 0xff, (size_t)T_cap * heads * HEAD_DIM * 2));
+  ACP_CUDA_CHECK(cudaMemcpy(dq.p, q, q_elems * 2, cudaMemcpyHostToDevice));
+  ACP_CUDA_CHECK(cudaMemcpy(dk.p, kc.data(), kc.size() * 2, cudaMemcpyHostToDevice));
+  ACP_CUDA_CHECK(cudaMemcpy(dv.p, vc.data(), vc.size() * 2, cudaMemcpyHostToDevice));
+  const int blk_tokens = impl ? attn_prefill_tc_block_tokens(heads, kv_heads) : (16 / (heads / kv_heads)) * 4;
+  const int n_blocks = (q_len + blk_tokens - 1) / blk_tokens;
+  // packed ints: blk_seq[n_blocks] blk_tok0[n_blocks] q_start[1] q_len[1] ctx_len[1] page_table[max_pages]
+  std::vector<int> ints;
+  for (int i = 0; i < n_blocks; ++i) ints.push_back(0);
+  for (int i = 0; i < n_blocks; ++i) ints.push_back(i * blk_tokens);
+  ints.push_back(0); ints.push_back(q_len); ints.push_back(ctx);
+  for (int p : pt) ints.push_back(p);
+  if (dints.alloc(ints.size() * 4)) return -5;
+  ACP_CUDA_CHECK(cudaMemcpy(dints.p, ints.data(), ints.size() * 4, cudaMemcpyHostToDevice));
+  const int* di = (const int*)dints.p;
+  AttnPrefillArgs pa;
+  pa.q = (const __nv_bfloat16*)dq.p; pa.out = (__nv_bfloat16*)dout.p;
+  pa.blk_seq = di; pa.blk_tok0 = di + n_blocks; pa.q_start = di + 2 * n_blocks; pa.q_len = di + 2 * n_blocks + 1;
+  pa.ctx_len = di + 2 * n_blocks + 2; pa.page_table = di + 2 * n_blocks + 3; pa.max_pages = max_pages;
+  pa.heads = heads; pa.kv_heads = kv_heads; pa.scale = 1.0f / sqrtf((float)HEAD_DIM);
+  CUtensorMap tq, tk, tv;
+  if (impl) {
+    if (attn_make_q_map(&tq, dq.p, (uint64_t)T_cap, heads, kv_heads) != 0) return -5;
+    if (attn_make_kv_half_map(&tk, dk.p, num_pages, kv_heads) != 0 || attn_make_kv_half_map(&tv, dv.p, num_pages, kv_heads) != 0) return -5;
+  } else {
+    if (attn_make_kv_map(&tk, dk.p, num_pages, kv_heads) != 0 || attn_make_kv_map(&tv, dv.p, num_pages, kv_heads) != 0) return -5;
+  }
+  auto launch = [&]() { return impl ? launch_attn_prefill_tc(tq, tk, tv, pa, n_blocks, 0) : launch_attn_prefill(tk, tv, pa, n_blocks, 0); };
+  int rc = launch();
+  if (rc != 0) return rc;
+  ACP_CUDA_CHECK(cudaDeviceSynchronize());
+  ACP_CUDA_CHECK(cudaMemcpy(out, dout.p, q_elems * 2, cudaMemcpyDeviceToHost));
+  if (iters > 0 && elapsed_ms != nullptr) {
+    const size_t flush_n = (size_t)64 << 20;
+    if (dflush.alloc(flush_n * 4)) return -5;
+    ACP_CUDA_CHECK(cudaMemset(dflush.p, 0, flush_n * 4));
+    cudaEvent_t e0, e1;
+    ACP_CUDA_CHECK(cudaEventCreate(&e0));
+    ACP_CUDA_CHECK(cudaEventCreate(&e1));
+    float total = 0.f;
+    for (int it = 0; it < iters + 2; ++it) {
+      l2_flush_kernel<<<1184, 256>>>((float*)dflush.p, flush_n);
+      ACP_CUDA_CHECK(cudaEventRecord(e0, 0));
+      rc = launch();
+      if (rc != 0) return rc;
+      ACP_CUDA_CHECK(cudaEventRecord(e1, 0));
+      ACP_CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      ACP_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      if (it >= 2) total += ms;
     }
     *elapsed_ms = total / iters;
     cudaEventDestroy(e0);

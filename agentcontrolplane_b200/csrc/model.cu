@@ -221,6 +221,8 @@ int Model::alloc_all() {
     ACP_TRY(tma_make_weight(&L.m_down, L.wdown, H, ffn_l_));
     ACP_TRY(attn_make_kv_map(&L.tm_k, L.k_cache, lim_.num_pages, kvh_l_));
     ACP_TRY(attn_make_kv_map(&L.tm_v, L.v_cache, lim_.num_pages, kvh_l_));
+    ACP_TRY(attn_make_kv_half_map(&L.tm_k32, L.k_cache, lim_.num_pages, kvh_l_));
+    ACP_TRY(attn_make_kv_half_map(&L.tm_v32, L.v_cache, lim_.num_pages, kvh_l_));
   }
   ACP_TRY(dmalloc_t(allocs_, &embed_, (size_t)c.vocab * H));
   ACP_TRY(dmalloc_t(allocs_, &lm_head_, (size_t)lm_rows_l_ * H));
@@ -239,6 +241,7 @@ int Model::alloc_all() {
   if (2 * ffn_l_ > max_m) max_m = 2 * ffn_l_;
   if (c.hidden > max_m) max_m = c.hidden;
   ACP_TRY(dmalloc_t(allocs_, &gemm_bf16_, (size_t)T * max_m, true));
+  ACP_TRY(attn_make_q_map(&tm_q_, qbuf_, (uint64_t)T, heads_l_, kvh_l_));
   ACP_TRY(tma_make_act(&m_xn_, xn_, T, H));
   ACP_TRY(tma_make_act(&m_attn_, attn_, T, qdim_l_));
   ACP_TRY(tma_make_act(&m_h_, h_, T, ffn_l_));
@@ -682,7 +685,8 @@ int Model::forward(const StepInput& in) {
       pa.q = qbuf_; pa.out = attn_; pa.blk_seq = d_bseq; pa.blk_tok0 = d_btok0; pa.q_start = d_qstart;
       pa.q_len = d_qlen; pa.ctx_len = d_ctx; pa.page_table = d_pt; pa.max_pages = lim_.max_pages_per_seq;
       pa.heads = heads_l_; pa.kv_heads = kvh_l_; pa.scale = scale;
-      PROF("attn_prefill", launch_attn_prefill(L.tm_k, L.tm_v, pa, in.n_blocks, stream_));
+      if (attn_prefill_tc_enabled()) PROF("attn_prefill", launch_attn_prefill_tc(tm_q_, L.tm_k32, L.tm_v32, pa, in.n_blocks, stream_));
+      else PROF("attn_prefill", launch_attn_prefill(L.tm_k, L.tm_v, pa, in.n_blocks, stream_));
       ++launches_;
     }
     if (tp_size_ > 1 && have_peers_) {

@@ -38,6 +38,15 @@ struct ModelConfig {
     return 2.0 * (per_layer * layers + (double)vocab * hidden + hidden);
   }
   double kv_bytes_per_token() const { return 2.0 * kv_dim() * 2.0 * layers; }
+  // algorithmic FLOPs of one step: 2 per weight per token row for the layer matrices,
+  // 2 per LM-head weight per SAMPLED row, and QK^T + PV = 4 * head_dim per (query head, visible key)
+  double layer_params() const {
+    return ((double)qkv_dim() * hidden + (double)hidden * q_dim() + 3.0 * ffn * hidden) * layers;
+  }
+  double step_flops(double token_rows, double sampled_rows, double query_key_pairs) const {
+    return 2.0 * layer_params() * token_rows + 2.0 * (double)vocab * hidden * sampled_rows +
+           4.0 * q_dim() * query_key_pairs * layers;
+  }
 };
 bool model_preset(const std::string& name, ModelConfig* out);
 class Checkpoint;
@@ -152,7 +161,8 @@ class Model {
     __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;
     __nv_bfloat16 *k_cache, *v_cache;
     TmaMaps m_qkv, m_o, m_gu, m_down;
-    CUtensorMap tm_k, tm_v;
+    CUtensorMap tm_k, tm_v;       // box = one (page, kv head) block, both dim halves (decode kernels)
+    CUtensorMap tm_k32, tm_v32;   // box = one dim half of a page (tcgen05 prefill kernel)
   };
   std::vector<Layer> layers_;
   __nv_bfloat16 *embed_ = nullptr, *lm_head_ = nullptr, *final_norm_ = nullptr;
@@ -162,6 +172,7 @@ class Model {
   __nv_bfloat16 *x_ = nullptr, *xn_ = nullptr, *qbuf_ = nullptr, *attn_ = nullptr, *h_ = nullptr,
                 *xs_ = nullptr, *gemm_bf16_ = nullptr;
   TmaMaps m_xn_, m_attn_, m_h_, m_xs_;
+  CUtensorMap tm_q_;   // qbuf_ as {128 dims, heads, rows} for the prefill attention's Q tiles
   float* ws_ = nullptr;  // split-K partial planes
   size_t ws_bytes_ = 0;
   float *amax_val_ = nullptr, *logits_ = nullptr;

@@ -3,10 +3,12 @@
 
   python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-One "step" = one pass of the hot path over one batch of synthetic Task CRs: BASELINE config 1,
-64 concurrent Tasks, each context window rendered to exactly 512 prompt tokens, greedy,
-max_tokens 64, Llama-3-8B shapes with seeded synthetic bf16 weights (no checkpoints or network
-in this image).  Every Task goes  Task CR JSON -> sendLLMRequest (C++ mirror of the reference's
+One "step" = one pass of the hot path over one batch of synthetic Task CRs: BASELINE config 2 (the
+largest single-GPU configuration, the one nearest north_star's ">= 1000 concurrent Task CRs"):
+512 concurrent Tasks, context windows log-uniform on [128, 4096] tokens (seeded, mean ~1150),
+continuous batching, greedy, max_tokens 64, Llama-3-8B shapes with seeded synthetic bf16 weights (no
+checkpoints or network in this image).  Config 1 (64 Tasks x 512 tokens) is run on the same engine
+after the timed region and reported under the extra key "config1".  Every Task goes  Task CR JSON -> sendLLMRequest (C++ mirror of the reference's
 Task step) -> LLMClient.SendRequest -> C ABI (host JSON in, host JSON out) -> continuous-batching
 CUDA engine -> assistant message -> processLLMResponse -> status writes.
 
@@ -16,8 +18,9 @@ Reported on ONE JSON line (rank 0):
           already resident: weights + KV in HBM)
   e2e     the same reconciles / wall seconds measured around the host call, host buffers,
           H2D (step descriptors, page tables, token ids) and D2H (sampled tokens) inside
-  decode_tokens_per_s, p50_decode_step_ms, roofline (algorithmic HBM bytes per decode step /
-  device time per decode step vs MEASURED_PEAKS.json), cpu_baseline (the reference's CPU reconcile
+  decode_tokens_per_s, p50/p99_decode_step_ms, roofline (algorithmic HBM bytes per decode step /
+  device time per decode step vs MEASURED_PEAKS.json hbm_gbs), roofline_prefill (algorithmic FLOPs of
+  the prefill steps incl. causal attention / their device time vs bf16_tflops_sustained), cpu_baseline (the reference's CPU reconcile
   loop restated in C++ against a loopback stub completion server, same box, core count stated).
 
 N > 1: one engine replica per GPU (request-level data parallelism, no collective on the data
@@ -42,7 +45,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
+    # BASELINE.json configs[2]: the largest single-GPU configuration (default since round 2)
+    2: {"name": "llama-3-8b provider:local, 512 concurrent Task CRs, context windows log-uniform 128..4096 tokens (mean ~1150), "
+                "continuous batching, greedy, max_tokens 64",
+        "model": "llama-3-8b", "tasks": 512, "prompt_tokens": 0, "prompt_min": 128, "prompt_max": 4096, "max_tokens": 64,
+        "tp": 1, "tools": 0, "tool_loop": False},
+    # BASELINE.json configs[1]: 64 Tasks x 512 tokens (round 1's driver line; now the "config1" extra key)
     1: {"name": "llama-3-8b provider:local, 64 concurrent Task CRs, 512-token context, greedy, max_tokens 64",
         "model": "llama-3-8b", "tasks": 64, "prompt_tokens": 512, "max_tokens": 64, "tp": 1, "tools": 0, "tool_loop": False},
     # BASELINE.json configs[3]: 70B tensor-parallel over 8 GPUs of ONE process, tool-call loop
@@ -50,7 +58,11 @@ WORKLOADS = {
     3: {"name": "llama-3-70b TP=8 provider:local, 256 concurrent Task CRs with tool-call loop, 512-token context, greedy, max_tokens 64",
         "model": "llama-3-70b", "tasks": 256, "prompt_tokens": 512, "max_tokens": 64, "tp": 8, "tools": 2, "tool_loop": True},
 }
-WORKLOAD = WORKLOADS[1]
+WORKLOAD = WORKLOADS[2]
+# DRAM bytes of ONE decode step from the committed `ncu --set full` captures (dram__bytes_read + write)
+NCU_TRAFFIC = {1: 20.00e9}
+NCU_TRAFFIC_SOURCE = {1: "profiles/r1_v3_ncu_full_decode_kernels.md: 32 x (QKV 51.2 + attention 146.0 + O 34.1 "
+                         "+ gate/up 238.4 + down 122.3 MB) + LM head 1054.4 MB, ctx 515"}
 
 
 def measured_peaks():
@@ -61,6 +73,29 @@ def measured_peaks():
         except Exception:  # noqa: BLE001
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    """Sustained dense bf16 TFLOP/s (the prefill GEMMs run inside a long step, B200_PROFILING.md)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def window_cfg(w: dict) -> dict:
+    """hostsim keys describing the context-window lengths of a workload"""
+    if w.get("prompt_min"):
+        return {"prompt_tokens_min": w["prompt_min"], "prompt_tokens_max": w["prompt_max"]}
+    return {"prompt_tokens": w["prompt_tokens"]}
+
+
+def window_desc(w: dict) -> str:
+    return (f"windows log-uniform {w['prompt_min']}..{w['prompt_max']} tokens" if w.get("prompt_min")
+            else f"windows of {w['prompt_tokens']} tokens")
 
 
 class ClockSampler:
@@ -114,7 +149,7 @@ def run_reference(args) -> dict:
     cores = os.cpu_count() or 1
     with host.StubServer() as srv:
         cfg = {"tasks": 2000, "workers": cores, "provider": "openai", "model": "gpt-4o", "baseURL": srv.base_url,
-               "prompt_tokens": WORKLOAD["prompt_tokens"], "seed": 1}
+               "seed": 1, **window_cfg(WORKLOAD)}
         # size one step to >= ~2 s of CPU work
         cfg["tasks"] = 2000
         while True:
@@ -135,7 +170,7 @@ def run_reference(args) -> dict:
         wall = time.perf_counter() - t0
         one = host.hostsim_run(dict(cfg, workers=1, tasks=max(100, cfg["tasks"] // cores)))
     value = total / wall
-    sample = f"{cfg['tasks']} Task reconciles per step, windows of {WORKLOAD['prompt_tokens']} tokens, stub completion server on loopback"
+    sample = f"{cfg['tasks']} Task reconciles per step, {window_desc(WORKLOAD)}, stub completion server on loopback"
     return {"impl": "reference", "metric": "task_reconciles_per_s", "value": value, "unit": "reconciles/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -154,7 +189,7 @@ def cpu_baseline_sample() -> dict:
     cores = os.cpu_count() or 1
     with host.StubServer() as srv:
         cfg = {"tasks": 400, "workers": cores, "provider": "openai", "model": "gpt-4o", "baseURL": srv.base_url,
-               "prompt_tokens": WORKLOAD["prompt_tokens"], "seed": 7}
+               "seed": 7, **window_cfg(WORKLOAD)}
         # grow the sample until it is ~10 s of CPU work (thread start-up dominates tiny samples)
         cfg["tasks"] = 2000
         while True:
@@ -166,7 +201,7 @@ def cpu_baseline_sample() -> dict:
             cfg["tasks"] = int(cfg["tasks"] * max(2.0, min(16.0, 10.0 / max(wall, 1e-3))))
         one = host.hostsim_run(dict(cfg, workers=1, tasks=max(200, cfg["tasks"] // (2 * cores))))
     return {"value": r["reconciles"] / wall, "unit": "reconciles/s", "cores": cores, "kind": "port",
-            "sample": f"{cfg['tasks']} Task reconciles ({WORKLOAD['prompt_tokens']}-token windows) of the restated Go loop "
+            "sample": f"{cfg['tasks']} Task reconciles ({window_desc(WORKLOAD)}) of the restated Go loop "
                       f"over HTTP to a loopback stub completion server, {wall:.1f} s",
             "single_worker_value": one["reconciles_per_s"], "p50_step_ms": r["step_ms_p50"]}
 
@@ -180,13 +215,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default=WORKLOAD["model"])
     ap.add_argument("--layers", type=int, default=0, help="dev only: truncate depth (result is then NOT a bench value)")
-    ap.add_argument("--config", type=int, default=1, choices=sorted(WORKLOADS),
-                    help="BASELINE.json config index (1 = default; 3 = 70B TP=8: run as ONE process on an 8-GPU box, --gpus 1)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS),
+                    help="BASELINE.json config index (2 = default; 1 = 64 x 512; 3 = 70B TP=8: run as ONE process on an 8-GPU box, --gpus 1)")
     ap.add_argument("--max-tokens-per-step", type=int, default=4096, help="engine knob: token rows per prefill step (4096 measured 1.3 %% faster than 8192)")
     ap.add_argument("--tp", type=int, default=0, help="dev only: override the tensor-parallel degree of --config 3")
     args = ap.parse_args()
     WORKLOAD = dict(WORKLOADS[args.config])
-    if args.config != 1:
+    if args.config == 3:
         if args.model == WORKLOADS[1]["model"]:
             args.model = WORKLOAD["model"]
         else:
@@ -225,8 +260,15 @@ def main():
     pages_per_seq = (plen + max_new) // 32 + 2
     if WORKLOAD["tool_loop"]:
         pages_per_seq += 12   # second LLM step: window + tool call + tool result
+    kv_pages = n_tasks * pages_per_seq * 2 + 8
+    if WORKLOAD.get("prompt_min"):
+        # mixed windows: size the pool from the very windows hostsim will build (dry run, no Task reconciled)
+        dry = host.hostsim_run({"tasks": n_tasks, "provider": "openai", "dry_run": True, **window_cfg(WORKLOAD)})
+        pages_per_seq = (dry["prompt_tokens_max"] + max_new) // 32 + 2
+        kv_pages = dry["prompt_tokens_total"] // 32 + n_tasks * (max_new // 32 + 3) + 64
+        WORKLOAD["name"] += f" [{dry['prompt_tokens_total']} window tokens per step, longest {dry['prompt_tokens_max']}]"
     ecfg = {"model": args.model, "device": local_rank, "max_batch": max(64, n_tasks), "max_tokens_per_step": args.max_tokens_per_step,
-            "kv_pages": n_tasks * pages_per_seq * 2 + 8, "max_pages_per_seq": max(32, pages_per_seq), "tp": WORKLOAD["tp"],
+            "kv_pages": kv_pages, "max_pages_per_seq": max(32, pages_per_seq), "tp": WORKLOAD["tp"],
             # config 1 measures cold Task steps: KV retention stays off so that no prefill work is skipped;
             # the tool loop of config 3 is exactly the case retention exists for (second turn of a Task)
             "prefix_cache": bool(WORKLOAD["tool_loop"])}
@@ -234,7 +276,8 @@ def main():
         ecfg["layers"] = args.layers
     eng = Engine(ecfg)
     sim = {"tasks": n_tasks, "workers": n_tasks, "provider": "local", "model": args.model, "max_tokens": max_new,
-           "prompt_tokens": plen, "tools": WORKLOAD["tools"], "tool_loop": WORKLOAD["tool_loop"]}
+           "tools": WORKLOAD["tools"], "tool_loop": WORKLOAD["tool_loop"],
+           **(window_cfg(WORKLOAD) if WORKLOAD.get("prompt_min") else {"prompt_tokens": plen})}
 
     def barrier():
         torch.cuda.synchronize(local_rank)
@@ -260,6 +303,27 @@ def main():
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
     s1 = eng.stats()
+    # extra key: BASELINE config 1 (64 Tasks x 512-token windows) on the same engine, outside the timed region
+    config1 = None
+    if args.config == 2 and rank == 0:
+        w1 = WORKLOADS[1]
+        sim1 = {"tasks": w1["tasks"], "workers": w1["tasks"], "provider": "local", "model": args.model,
+                "max_tokens": w1["max_tokens"], "prompt_tokens": w1["prompt_tokens"], "tools": 0, "tool_loop": False}
+        host.hostsim_run(dict(sim1, seed=2000), eng)
+        eng.stats_reset()
+        t1 = time.perf_counter()
+        n1 = sum(host.hostsim_run(dict(sim1, seed=2001 + i), eng)["reconciles"] for i in range(3))
+        w1_wall = time.perf_counter() - t1
+        c1 = eng.stats()
+        hbm_peak, _ = measured_peaks()
+        tf_peak, _ = measured_tensor_peak()
+        c1_dec_s, c1_pre_s = c1["decode_ms"] / 1e3, c1["prefill_ms"] / 1e3
+        config1 = {"workload": w1["name"], "steps": 3,
+                   "value": n1 / (c1_dec_s + c1_pre_s), "e2e": n1 / w1_wall, "unit": "reconciles/s",
+                   "decode_tokens_per_s": c1["decode_tokens"] / c1_dec_s, "p50_decode_step_ms": c1.get("decode_step_ms_p50"),
+                   "roofline_decode_frac": c1["decode_bytes_algorithmic"] / c1_dec_s / 1e9 / hbm_peak,
+                   "roofline_prefill_frac": c1["prefill_flops_algorithmic"] / c1_pre_s / 1e12 / tf_peak,
+                   "prefill_tokens_per_s": c1["prefill_tokens"] / c1_pre_s}
     dev_s = (s1["decode_ms"] + s1["prefill_ms"]) / 1e3
     from agentcontrolplane_b200.replicas import aggregate
     wall_max, dev_max, (total_reconciles, total_decode_tokens) = aggregate(
@@ -272,6 +336,9 @@ def main():
         # per GPU: a tensor-parallel engine streams 1/tp of the bytes on each GPU
         achieved = s1.get("decode_bytes_algorithmic_per_gpu", s1["decode_bytes_algorithmic"]) / dec_s / 1e9 if dec_s > 0 else 0.0
         launches = s1["kernel_launches"] - s0["kernel_launches"]
+        tf_peak, tf_src = measured_tensor_peak()
+        pre_s = s1["prefill_ms"] / 1e3
+        pre_tf = s1.get("prefill_flops_algorithmic", 0.0) / WORKLOAD["tp"] / pre_s / 1e12 if pre_s > 0 else 0.0
         line = {
             "metric": "task_reconciles_per_s", "value": total_reconciles / dev_max, "unit": "reconciles/s",
             "n_gpus": world * WORKLOAD["tp"], "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3,
@@ -290,6 +357,7 @@ def main():
             "decode_tokens_per_s_rank0": s1["decode_tokens"] / dec_s if dec_s > 0 else 0.0,
             "prefill_tokens_per_s_rank0": s1["prefill_tokens"] / (s1["prefill_ms"] / 1e3) if s1["prefill_ms"] else 0.0,
             "p50_decode_step_ms": s1.get("decode_step_ms_p50"),
+            "p99_decode_step_ms": s1.get("decode_step_ms_p99"),
             "p50_reconcile_ms": sorted(p50s)[len(p50s) // 2],
             "e2e": {"value": total_reconciles / wall_max, "unit": "reconciles/s",
                     "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) / args.steps,
@@ -298,16 +366,26 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # DRAM bytes of one decode step from the committed ncu --set full capture (config 1 only)
-                         "traffic": 20.00e9 if (args.config == 1 and not args.layers) else None,
-                         "traffic_source": "profiles/r1_v3_ncu_full_decode_kernels.md: 32 x (QKV 51.2 + attention 146.0 + O 34.1 "
-                                           "+ gate/up 238.4 + down 122.3 MB) + LM head 1054.4 MB, ctx 515",
+                         "traffic": NCU_TRAFFIC.get(args.config) if not args.layers else None,
+                         "traffic_source": NCU_TRAFFIC_SOURCE.get(args.config),
                          "peak_source": peak_src,
                          "kernel": "one decode step (all launches of the step, CUDA events on the engine stream)",
                          "bytes_per_decode_step": s1["decode_bytes_algorithmic"] / max(1, s1["decode_steps"]),
-                         "decode_steps_timed": s1["decode_steps"]},
+                         "decode_steps_timed": s1["decode_steps"],
+                         "share_of_device_time": dec_s / (dec_s + pre_s) if dec_s + pre_s > 0 else None},
+            # the other phase of the same timed region: prefill is dense contraction (tensor bound)
+            "roofline_prefill": {"bound": "tensor", "achieved": pre_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                                 "frac": pre_tf / tf_peak, "traffic": None, "peak_source": tf_src,
+                                 "kernel": "all prefill steps (QKV/O/gate-up/down GEMMs on tcgen05 + causal paged attention + LM head rows), "
+                                           "CUDA events on the engine stream; FLOPs = 2 per layer weight per token + 4*head_dim per (query head, visible key)",
+                                 "flops_per_prefill_token": s1.get("prefill_flops_algorithmic", 0.0) / max(1, s1["prefill_tokens"]),
+                                 "prefill_tokens_timed": s1["prefill_tokens"],
+                                 "share_of_device_time": pre_s / (dec_s + pre_s) if dec_s + pre_s > 0 else None},
             "clocks": clocks,
         }
-        if world == 1 and args.config == 1:
+        if config1 is not None:
+            line["config1"] = config1
+        if world == 1 and args.config != 3:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
     eng.close()

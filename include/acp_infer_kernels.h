@@ -26,6 +26,15 @@ int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int N, int K, i
                     int epi, int bn, void* out, float* amax_val, int* amax_idx, int iters,
                     float* elapsed_ms);
 
+/* Causal paged-KV GQA attention of ONE sequence's prefill chunk.  q: bf16 [q_len][heads][128] (already
+ * rotated), k, v: bf16 [ctx][kv_heads][128] — the whole context, the last q_len keys belong to the
+ * query tokens (query i sits at absolute position ctx - q_len + i and sees keys 0..that position).
+ * The hook scatters k/v into a paged cache with a shuffled page table, runs the kernel and returns
+ * out: bf16 [q_len][heads][128].  impl 1 = tcgen05 kernel (attention_prefill_tc.cu), 0 = round 1's
+ * mma.sync kernel.  iters > 0 also times the launch (mean ms, L2 flushed between launches). */
+int acp_kernel_attn_prefill(const uint16_t* q, const uint16_t* k, const uint16_t* v, int heads, int kv_heads,
+                            int q_len, int ctx, int impl, uint16_t* out, int iters, float* elapsed_ms);
+
 /* Number of visible CUDA devices (0 when none / no driver). */
 int acp_kernel_device_count(void);
 

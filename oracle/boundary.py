@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Every function cites the reference lines it
 follows (paths relative to /root/reference).  Pinned by the reference's own golden behaviours
-G1..G11 in tests/test_oracle_boundary.py.
+G1..G14 (G12-G14 added in round 2 for a5/a6/a8) in tests/test_oracle_boundary.py.
 
 Data model: plain dicts shaped like the CRD JSON (acp/api/v1alpha1/task_types.go:57-97):
     Message  = {"role", "content", "toolCalls": [{"id","type","function":{"name","arguments"}}],
@@ -344,6 +344,73 @@ def send_llm_request(task: dict, tools: list[dict], llm_client, recorder: Record
     except Exception as e:  # noqa: BLE001 — mirrors `if err != nil`
         return handle_llm_error(task, e, recorder)
     return process_llm_response(output, task, tools, recorder, toolcalls_out, id_gen), None
+
+
+def validate_task_and_agent(task: dict, agent: dict | None, recorder: Recorder) -> Result | None:
+    """validateTaskAndAgent (state_machine.go:379-424); `agent` is the Agent CR or None when the GET
+    returned NotFound.  Returns the (non-zero) Result when the Task has to wait, None when it may go on."""
+    st = task["status"]
+    if agent is None:
+        st.update(ready=False, status=STATUS_PENDING, phase=PHASE_PENDING,
+                  statusDetail="Waiting for Agent to exist", error="")
+        recorder.event("Normal", "Waiting", "Waiting for Agent to exist")
+        return Result(requeue_after=DEFAULT_REQUEUE_DELAY)
+    if not agent.get("status", {}).get("ready", False):
+        msg = f"Waiting for agent \"{agent['metadata']['name']}\" to become ready"
+        st.update(ready=False, status=STATUS_PENDING, phase=PHASE_PENDING, statusDetail=msg, error="")
+        recorder.event("Normal", "Waiting", msg)
+        return Result(requeue_after=DEFAULT_REQUEUE_DELAY)
+    return None
+
+
+def get_llm_and_credentials(task: dict, llm: dict | None, llm_name: str, secrets_by_name: dict,
+                            recorder: Recorder):
+    """getLLMAndCredentials (state_machine.go:480-538) -> (api_key, error string or None).
+    The reference dereferences llm.Spec.APIKeyFrom unconditionally (:504); with the `local`
+    provider and no apiKeyFrom that lookup is skipped and the key is ""."""
+    st = task["status"]
+
+    def fail(detail, error, reason):
+        st.update(ready=False, status=STATUS_ERROR, phase=PHASE_FAILED, statusDetail=detail, error=error)
+        recorder.event("Warning", reason, error)
+        return None, error
+
+    if llm is None:
+        e = f'llms.acp.humanlayer.dev "{llm_name}" not found'
+        return fail(f"Failed to get LLM: {e}", e, "LLMFetchFailed")
+    spec = llm.get("spec", {})
+    key_from = spec.get("apiKeyFrom")
+    if spec.get("provider") == "local" and not key_from:
+        return "", None
+    ref = (key_from or {}).get("secretKeyRef", {})
+    secret = secrets_by_name.get(ref.get("name", ""))
+    if secret is None:
+        e = f'secrets "{ref.get("name", "")}" not found'
+        return fail(f"Failed to get API key secret: {e}", e, "APIKeySecretFetchFailed")
+    api_key = secret.get("data", {}).get(ref.get("key", ""), "")
+    if api_key == "":
+        return fail("API key is empty", "API key is empty", "EmptyAPIKey")
+    return api_key, None
+
+
+def collect_tools(agent: dict, mcp_tools_by_server: dict, channels_by_name: dict, agents_by_name: dict) -> list[dict]:
+    """collectTools (state_machine.go:540-583): MCP server tools (in agent.spec.mcpServers order; servers
+    the manager does not know are skipped), then the agent's valid contact channels, then its sub-agents
+    (objects that cannot be fetched are skipped, like the `continue` at :563 / :576)."""
+    tools: list[dict] = []
+    for ref in agent.get("spec", {}).get("mcpServers", []):
+        if ref["name"] in mcp_tools_by_server:
+            tools += convert_mcp_tools(mcp_tools_by_server[ref["name"]], ref["name"])
+    for ref in agent.get("status", {}).get("validHumanContactChannels", []):
+        ch = channels_by_name.get(ref["name"])
+        if ch is not None:
+            tools.append(tool_from_contact_channel({"name": ch["metadata"]["name"], "spec": ch["spec"]}))
+    subs = []
+    for ref in agent.get("spec", {}).get("subAgents", []):
+        sub = agents_by_name.get(ref["name"])
+        if sub is not None:
+            subs.append({"name": sub["metadata"]["name"], "description": sub.get("spec", {}).get("description", "")})
+    return tools + convert_sub_agents(subs)
 
 
 def check_tool_calls(task: dict, toolcalls: list[dict], recorder: Recorder) -> Result:

@@ -276,3 +276,115 @@ def test_unimplemented_completion_parameters_are_refused_not_ignored():
                           ({"frequency_penalty": 0.5}, "frequency_penalty"), ({"presence_penalty": -1}, "presence_penalty")):
         r = host.render_prompt(dict(base, **extra))
         assert r.get("status") == 400 and needle in r["error"], (extra, r)
+
+
+# ------------------------------------------------------------------ a5 / a6 / a8: the cluster lookups of the LLM step
+def _agent(ready=True, **spec):
+    return {"metadata": {"name": FX["agent_name"], "namespace": "default"},
+            "spec": dict({"llmRef": {"name": "test-llm"}, "system": FX["system_prompt"]}, **spec),
+            "status": {"ready": ready, "validHumanContactChannels": spec.pop("_channels", [])}}
+
+
+def _llm(provider="mock", key_from=True, **params):
+    spec = {"provider": provider, "parameters": dict({"model": "m"}, **params)}
+    if key_from:
+        spec["apiKeyFrom"] = {"secretKeyRef": {"name": "test-secret", "key": "api-key"}}
+    return {"metadata": {"name": "test-llm"}, "spec": spec}
+
+
+SECRET = {"metadata": {"name": "test-secret"}, "data": {"api-key": "sk-test"}}
+
+
+def _cluster_step(objects, mcp=None, task=None):
+    return host.task_step({"op": "sendLLMRequestFromCluster", "task": task or _task(), "mcp": mcp or {},
+                           "objects": [{"kind": k, "object": o} for k, o in objects]})
+
+
+def test_G12_G13_validate_task_and_agent_host_matches_reference_and_oracle():
+    for gname, objects, agent in (("G12_agent_missing", [], None),
+                                  ("G13_agent_not_ready", [("Agent", _agent(ready=False))], _agent(ready=False))):
+        exp = G[gname]["expect"]
+        out = _cluster_step(objects)
+        st = out["task"]["status"]
+        assert st["phase"] == exp["phase"] and st["status"] == exp["status"]
+        assert exp["statusDetail_contains"] in st["statusDetail"] and st.get("error", "") == ""
+        assert out["result"]["requeueAfter"] == exp["requeue_after"] and out["error"] == ""
+        for frag in exp["events_containing"]:
+            assert any(frag in e["reason"] or frag in e["message"] for e in out["events"])
+        ot, rec = _task(), B.Recorder()
+        res = B.validate_task_and_agent(ot, agent, rec)
+        assert res.requeue_after == exp["requeue_after"]
+        for k in ("phase", "status", "statusDetail"):
+            assert st[k] == ot["status"][k]
+        assert [(e["type"], e["reason"], e["message"]) for e in out["events"]] == rec.events
+
+
+def test_get_llm_and_credentials_failures_match_oracle():
+    cases = [
+        ([("Agent", _agent())], None, {}, "LLMFetchFailed"),
+        ([("Agent", _agent()), ("LLM", _llm("openai"))], _llm("openai"), {}, "APIKeySecretFetchFailed"),
+        ([("Agent", _agent()), ("LLM", _llm("openai")), ("Secret", {"metadata": {"name": "test-secret"}, "data": {"api-key": ""}})],
+         _llm("openai"), {"test-secret": {"data": {"api-key": ""}}}, "EmptyAPIKey"),
+    ]
+    for objects, llm, secrets_by_name, reason in cases:
+        out = _cluster_step(objects)
+        st = out["task"]["status"]
+        ot, rec = _task(), B.Recorder()
+        key, err = B.get_llm_and_credentials(ot, llm, "test-llm", secrets_by_name, rec)
+        assert key is None and err
+        assert st["phase"] == "Failed" and st["status"] == "Error"
+        assert st["error"] == ot["status"]["error"] == err == out["error"]
+        assert st["statusDetail"] == ot["status"]["statusDetail"]
+        assert _reasons(out) == [reason] == [r for (_, r, _) in rec.events]
+        assert out["result"] == {"requeue": False, "requeueAfter": 0}
+
+
+def test_local_provider_needs_no_secret_and_other_providers_do():
+    """with provider `local` and no apiKeyFrom the reference would dereference a nil
+    pointer (state_machine.go:504); the mirror skips the Secret and goes on to CreateClient — which,
+    without an engine in this CPU test, fails with the typed client-creation error, proving the
+    credentials step was passed."""
+    out = _cluster_step([("Agent", _agent()), ("LLM", _llm("local", key_from=False))])
+    st = out["task"]["status"]
+    assert _reasons(out) == ["LLMClientCreationFailed"]
+    assert st["phase"] == "Failed" and "engine not initialised" in st["error"]
+    ot, rec = _task(), B.Recorder()
+    assert B.get_llm_and_credentials(ot, _llm("local", key_from=False), "test-llm", {}, rec) == ("", None)
+    # an unknown provider with valid credentials reaches the provider switch (langchaingo_client.go:71-72)
+    out = _cluster_step([("Agent", _agent()), ("LLM", _llm("cohere")), ("Secret", SECRET)])
+    assert "unsupported provider: cohere" in out["task"]["status"]["error"]
+
+
+def test_G14_contact_channel_tools_and_collect_tools_order():
+    g = G["G14_contact_channel_tools"]
+    for case in g["cases"]:
+        agent = _agent()
+        agent["status"]["validHumanContactChannels"] = [{"name": case["channel"]["metadata"]["name"]}]
+        out = host.task_step({"op": "collectTools", "task": _task(), "agent": agent, "mcp": {},
+                              "objects": [{"kind": "ContactChannel", "object": case["channel"]}]})
+        (tool,) = out["tools"]
+        assert tool["function"]["name"] == case["name"] and tool["function"]["description"] == case["description"]
+        assert tool["function"]["parameters"] == g["parameters"] and tool["acpToolType"] == g["acpToolType"]
+        assert tool == B.tool_from_contact_channel({"name": case["channel"]["metadata"]["name"], "spec": case["channel"]["spec"]})
+    # order: MCP servers (agent order, unknown servers skipped), contact channels, sub-agents (missing ones skipped)
+    agent = _agent(mcpServers=[{"name": "fetch"}, {"name": "ghost"}, {"name": "files"}], subAgents=[{"name": "sub-agent"}, {"name": "gone"}])
+    agent["status"]["validHumanContactChannels"] = [{"name": "ops"}]
+    mcp = {"files": [{"name": "read", "description": "Read a file", "inputSchema": {"type": "object", "properties": {"path": {"type": "string"}}}}],
+           "fetch": [{"name": "fetch", "description": "Fetch a URL"}]}
+    channel = G["G14_contact_channel_tools"]["cases"][0]["channel"]
+    sub = {"metadata": {"name": "sub-agent"}, "spec": {"description": G["G7_delegate_tool"]["agent"]["description"]}}
+    out = host.task_step({"op": "collectTools", "task": _task(), "agent": agent, "mcp": mcp,
+                          "objects": [{"kind": "ContactChannel", "object": channel}, {"kind": "Agent", "object": sub}]})
+    names = [t["function"]["name"] for t in out["tools"]]
+    assert names == ["fetch__fetch", "files__read", "ops__human_contact_email", "delegate_to_agent__sub-agent"]
+    want = B.collect_tools(agent, mcp, {"ops": channel}, {"sub-agent": sub})
+    assert out["tools"] == want
+    assert B.build_tool_type_map(want) == {"fetch__fetch": "MCP", "files__read": "MCP", "ops__human_contact_email": "HumanContact",
+                                           "delegate_to_agent__sub-agent": "DelegateToAgent"}
+
+
+def test_local_client_forwards_llm_parameters():
+    """a20: temperature / topP / topK / maxTokens of LLM.spec.parameters (llm_types.go:41-71) reach the
+    engine's request body; without them the body says temperature 0 like the reference's wire."""
+    body = host.build_chat_request("m", [{"role": "user", "content": "hi"}], [])
+    assert body["temperature"] == 0 and "top_p" not in body and "top_k" not in body and "max_tokens" not in body

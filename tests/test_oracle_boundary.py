@@ -181,3 +181,27 @@ def test_contact_channel_tools():
     s = B.tool_from_contact_channel({"name": "ops", "spec": {"type": "slack", "slack": {"contextAboutChannelOrUser": "the ops channel"}}})
     assert s["function"]["name"] == "ops__human_contact_slack" and s["function"]["description"] == "the ops channel"
     assert s["acpToolType"] == "HumanContact"
+
+
+def test_G12_G13_validate_task_and_agent():
+    for gname, agent in (("G12_agent_missing", None),
+                         ("G13_agent_not_ready", {"metadata": {"name": FX["agent_name"]}, "status": {"ready": False}})):
+        exp = G[gname]["expect"]
+        task = {"metadata": {"name": FX["task_name"]}, "status": {"phase": "Initializing", "status": "Pending", "error": "stale"}}
+        rec = B.Recorder()
+        res = B.validate_task_and_agent(task, agent, rec)
+        st = task["status"]
+        assert st["phase"] == exp["phase"] and st["status"] == exp["status"] and st["error"] == ""
+        assert exp["statusDetail_contains"] in st["statusDetail"] and res.requeue_after == exp["requeue_after"]
+        for frag in exp["events_containing"]:
+            assert any(frag in r or frag in m for (_, r, m) in rec.events)
+    ready = {"metadata": {"name": FX["agent_name"]}, "status": {"ready": True}}
+    assert B.validate_task_and_agent({"status": {}}, ready, B.Recorder()) is None
+
+
+def test_G14_contact_channel_goldens():
+    g = G["G14_contact_channel_tools"]
+    for case in g["cases"]:
+        t = B.tool_from_contact_channel({"name": case["channel"]["metadata"]["name"], "spec": case["channel"]["spec"]})
+        assert t["function"]["name"] == case["name"] and t["function"]["description"] == case["description"]
+        assert t["function"]["parameters"] == g["parameters"] and t["acpToolType"] == g["acpToolType"]
