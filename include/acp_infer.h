@@ -17,7 +17,9 @@
  * handleLLMError turns into phase Failed, controller/task/state_machine.go:733-790), 5xx =
  * transient (plain error => requeue after 5 s).
  *
- * Conventions: every function is thread-safe and callable from any OS thread (cgo); no function
+ * Conventions: every function except acp_infer_shutdown is thread-safe and callable from any OS
+ * thread (cgo); acp_infer_shutdown frees the handle and must not overlap any other call on it
+ * (stop the poller first: integration/go/inference Shutdown); no function
  * throws; return value 0 = success, negative = ACP_ERR_*; out-buffers are malloc'ed by the
  * library and released with acp_infer_free(); the library never keeps a caller pointer after
  * the call returns (cgo pointer-passing rule).  There is NO CPU fallback: without a usable CUDA
@@ -95,6 +97,9 @@ int acp_infer_stats(acp_engine* e, char** json);
 void acp_infer_stats_reset(acp_engine* e);
 
 void acp_infer_free(void* p);
+/* Ends every queued / running request with status 503 (each is reported once more through
+ * acp_infer_poll so that parked waiters wake), joins the scheduler, frees device memory and the
+ * handle.  Must not run concurrently with any other call on `e`. */
 void acp_infer_shutdown(acp_engine* e);
 
 /* Library build info: "acp_infer <version> sm_100a". */

@@ -22,6 +22,7 @@ import (
 	"context"
 	"fmt"
 	"sync"
+	"time"
 	"unsafe"
 )
 
@@ -32,6 +33,8 @@ type Engine struct {
 	mu      sync.Mutex
 	waiters map[uint64]chan struct{}
 	done    chan struct{}
+	wg      sync.WaitGroup // the poller; Shutdown waits for it before the handle is freed
+	closed  bool
 }
 
 var (
@@ -52,6 +55,7 @@ func Init(configJSON string) (*Engine, error) {
 			return
 		}
 		global = &Engine{h: h, waiters: map[uint64]chan struct{}{}, done: make(chan struct{})}
+		global.wg.Add(1)
 		go global.poller()
 	})
 	return global, globalErr
@@ -61,6 +65,7 @@ func Init(configJSON string) (*Engine, error) {
 func Get() *Engine { return global }
 
 func (e *Engine) poller() {
+	defer e.wg.Done()
 	var tickets [256]C.uint64_t
 	for {
 		select {
@@ -89,6 +94,10 @@ func (e *Engine) Complete(ctx context.Context, body []byte) (status int, resp []
 	var ticket C.uint64_t
 	ch := make(chan struct{})
 	e.mu.Lock() // register before submit so the poller cannot miss the completion
+	if e.closed {
+		e.mu.Unlock()
+		return 0, nil, fmt.Errorf("engine is shut down")
+	}
 	rc := C.acp_infer_submit(e.h, (*C.char)(unsafe.Pointer(&body[0])), C.size_t(len(body)), &ticket)
 	if rc != C.ACP_OK {
 		e.mu.Unlock()
@@ -113,8 +122,54 @@ func (e *Engine) Complete(ctx context.Context, body []byte) (status int, resp []
 	return int(st), C.GoBytes(unsafe.Pointer(out), C.int(n)), nil
 }
 
-// Shutdown stops the scheduler and frees device memory.
+// Shutdown stops the scheduler and frees device memory.  acp_infer_shutdown deletes the handle, so
+// nothing may be inside acp_infer_poll / acp_infer_result when it runs (include/acp_infer.h:
+// "shutdown must not overlap other calls"):
+//  1. refuse new submissions, cancel what is in flight (each ends with status 499 and is reported
+//     to the poller like any completion, so parked Complete() goroutines wake up);
+//  2. stop the poller and WAIT for it to leave acp_infer_poll;
+//  3. wake any goroutine still parked (its acp_infer_result then reports the engine's 503 / 499);
+//  4. free the handle.
 func (e *Engine) Shutdown() {
+	e.mu.Lock()
+	if e.closed {
+		e.mu.Unlock()
+		return
+	}
+	e.closed = true
+	for t := range e.waiters {
+		C.acp_infer_cancel(e.h, C.uint64_t(t))
+	}
+	e.mu.Unlock()
+	// give the scheduler one poll interval to report the cancellations through the poller
+	drained := make(chan struct{})
+	go func() {
+		for {
+			e.mu.Lock()
+			n := len(e.waiters)
+			e.mu.Unlock()
+			if n == 0 {
+				close(drained)
+				return
+			}
+			select {
+			case <-e.done:
+				return
+			case <-time.After(10 * time.Millisecond):
+			}
+		}
+	}()
+	select {
+	case <-drained:
+	case <-time.After(2 * time.Second):
+	}
 	close(e.done)
+	e.wg.Wait()
+	e.mu.Lock()
+	for t, ch := range e.waiters {
+		close(ch)
+		delete(e.waiters, t)
+	}
+	e.mu.Unlock()
 	C.acp_infer_shutdown(e.h)
 }

@@ -9,6 +9,7 @@ import (
 	"context"
 	"encoding/json"
 	"fmt"
+	"strconv"
 
 	acp "github.com/humanlayer/agentcontrolplane/acp/api/v1alpha1"
 	"github.com/humanlayer/agentcontrolplane/acp/internal/inference"
@@ -50,7 +51,9 @@ type wireMessage struct {
 type wireRequest struct {
 	Model       string        `json:"model"`
 	Messages    []wireMessage `json:"messages"`
-	Temperature float64       `json:"temperature"`
+	Temperature float64       `json:"temperature"` // no omitempty, like langchaingo's ChatRequest
+	TopP        *float64      `json:"top_p,omitempty"`
+	TopK        *int          `json:"top_k,omitempty"`
 	MaxTokens   int           `json:"max_tokens,omitempty"`
 	Tools       []Tool        `json:"tools,omitempty"` // ACPToolType is json:"-" (llm_client.go:38)
 }
@@ -69,7 +72,27 @@ type wireResponse struct {
 // SendRequest implements LLMClient.  Same conversions as convertToLangchainMessages /
 // convertFromLangchainResponse (langchaingo_client.go:118-185, 208-282).
 func (c *LocalClient) SendRequest(ctx context.Context, messages []acp.Message, tools []Tool) (*acp.Message, error) {
+	// LLM.spec.parameters (acp/api/v1alpha1/llm_types.go:41-71).  The reference's langchaingo path
+	// reads only Model and BaseURL and therefore always sends temperature 0; the local provider
+	// honours temperature / topP / topK / maxTokens when they are set (strings in the CRD).
 	req := wireRequest{Model: c.cfg.Model, Temperature: 0, Tools: tools}
+	if c.cfg.Temperature != "" {
+		t, err := strconv.ParseFloat(c.cfg.Temperature, 64)
+		if err != nil {
+			return nil, &LLMRequestError{StatusCode: 400, Message: "parameters.temperature: " + err.Error()}
+		}
+		req.Temperature = t
+	}
+	if c.cfg.TopP != "" {
+		p, err := strconv.ParseFloat(c.cfg.TopP, 64)
+		if err != nil {
+			return nil, &LLMRequestError{StatusCode: 400, Message: "parameters.topP: " + err.Error()}
+		}
+		req.TopP = &p
+	}
+	if c.cfg.TopK != nil {
+		req.TopK = c.cfg.TopK
+	}
 	if c.cfg.MaxTokens != nil {
 		req.MaxTokens = *c.cfg.MaxTokens
 	}
