@@ -208,43 +208,6 @@ ACP_DEVINL void produce_tiles(const CUtensorMap* tm_k, const CUtensorMap* tm_v, 
   }
 }
 
-// Experimental (ACP_ATTN_PT_PREFETCH=1, unmeasured — profiles/r1_v3_ncu_full_decode_kernels.md shows the
-// decode kernels latency bound with a page-table load in front of every TMA issue): ALL 32 lanes of
-// the producer warp read the CTA's page ids once (one coalesced load, <= 32 pages = 16 tiles) and
-// lane 0 gets them by shuffle, so no TMA issue waits on global memory any more.
-template <int NS = STAGES>
-ACP_DEVINL void produce_tiles_prefetched(const CUtensorMap* tm_k, const CUtensorMap* tm_v, uint8_t* stages,
-                                         uint64_t* full_bar, uint64_t* empty_bar, const int* pt_row, int kh,
-                                         int kv_heads, int tile_begin, int tile_end, int last_tok /*exclusive*/,
-                                         int lane) {
-  const int page0 = tile_begin * (TILE_TOK / KV_PAGE);
-  const int pages_here = (last_tok - tile_begin * TILE_TOK + KV_PAGE - 1) / KV_PAGE;
-  const int my_page = (lane < pages_here) ? pt_row[page0 + lane] : 0;
-  int it = 0;
-  for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
-    const int s = it % NS;
-    const uint32_t ph = (uint32_t)(it / NS) & 1u;
-    if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1u);
-    __syncwarp();
-    const int tok0 = tile * TILE_TOK;
-    const int n_pages = (last_tok - tok0 > KV_PAGE) ? 2 : 1;
-    const int rel = (tile - tile_begin) * (TILE_TOK / KV_PAGE);
-    const int pg0 = __shfl_sync(0xffffffffu, my_page, rel & 31);
-    const int pg1 = __shfl_sync(0xffffffffu, my_page, (rel + 1) & 31);
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(n_pages * 4 * BLOCK_BYTES));
-      uint8_t* kdst = stages + s * STAGE_BYTES;
-      uint8_t* vdst = kdst + K_TILE_BYTES;
-      for (int p = 0; p < n_pages; ++p) {
-        const int page = p ? pg1 : pg0;
-        const int row = (page * kv_heads + kh) * 2 * KV_PAGE;
-        tma_load_2d(kdst + p * 2 * BLOCK_BYTES, tm_k, &full_bar[s], 0, row, kEvictFirst);
-        tma_load_2d(vdst + p * 2 * BLOCK_BYTES, tm_v, &full_bar[s], 0, row, kEvictFirst);
-      }
-    }
-  }
-}
-
 struct SmemLayout {
   uint8_t* stages;
   uint64_t* full_bar;
@@ -387,7 +350,6 @@ ACP_DEVINL int find_seq(const int* cum, int n, long long f, int kvh) {  // cum[b
   return lo;
 }
 
-template <bool PT_PREFETCH>
 __global__ void __launch_bounds__(ATTN_THREADS, 2)
 attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                    AttnDecodeArgs a) {
@@ -423,13 +385,6 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   pdl_wait();  // K/V pages and q were written by the previous kernel (rope_kv)
 
   if (warp == CONSUMER_WARPS) {
-    if constexpr (PT_PREFETCH) {
-      if (tile_end - tile_begin <= 16) {
-        produce_tiles_prefetched(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
-                                 a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, tile_begin, tile_end, tok_end, lane);
-        return;
-      }
-    }
     if (lane == 0)
       produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
                     a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, tile_begin, tile_end, tok_end);
@@ -515,7 +470,6 @@ attn_merge_kernel(AttnDecodeArgs a) {
 // Per-item variant: CTA = (sequence, kv head), the whole context of the item, cross-warp merge in
 // shared memory, final bf16 output written directly (no workspace, no merge kernel).  Used when
 // there are enough items to fill the machine and every item is short (launch_attn_decode picks).
-template <bool PT_PREFETCH>
 __global__ void __launch_bounds__(ATTN_THREADS, 2)
 attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                         AttnDecodeArgs a) {
@@ -542,13 +496,6 @@ attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
   pdl_wait();
 
   if (warp == CONSUMER_WARPS) {
-    if constexpr (PT_PREFETCH) {
-      if (n_tiles <= 16) {
-        produce_tiles_prefetched(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
-                                 a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, cached, lane);
-        return;
-      }
-    }
     if (lane == 0)
       produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
                     a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, cached);
@@ -619,282 +566,12 @@ attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
 }
 
 // =================================================================================
-// Experimental (ACP_ATTN_HALF=1, unmeasured): decode kernels for G = heads / kv_heads <= 8.  The MMA
-// tile has 16 rows but only rows < G carry query heads; with G <= 8 the upper eight rows are never
-// used, so their accumulators (half of O, S, P), the upper A fragments of Q and P and the second
-// running max / sum are dropped from the register file (zero A/C operands, discarded D halves).
-// With a 2-stage ring (72 KiB) three CTAs share an SM instead of two: 12 consumer warps per SM and
-// six tiles in flight.  Same arithmetic, same order, same results as the full-tile kernels.
-// =================================================================================
-constexpr int STAGES_H = 2;
-constexpr int ATTN_SMEM_H = STAGES_H * STAGE_BYTES + 1024 + 2 * STAGES_H * 8 + 16 + NEWTOK_BYTES + 64;
-static_assert(SCRATCH_FLOATS * 4 <= STAGES_H * STAGE_BYTES, "scratch must fit in the 2-stage ring");
-
-struct WarpStateH {
-  float o[16][2];   // 16 dim-tiles of 8: c0,c1 of row lane/4
-  float m, l;
-};
-
-// rows 0..7 only: a1 = a3 = 0, c2 = c3 = 0, d2 / d3 discarded
-ACP_DEVINL void mma_bf16_16816_lo(float (&d)[2], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-  float j0 = 0.f, j1 = 0.f;   // discarded upper halves of D
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%10,%10};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(j0), "+f"(j1)
-      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1), "f"(0.f));
-}
-
-ACP_DEVINL void load_q_frags_half(uint32_t (&qf)[8][2], const __nv_bfloat16* q_lo, int lane) {
-  const int c = 2 * (lane & 3);
-#pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    qf[ks][0] = q_lo ? *reinterpret_cast<const uint32_t*>(q_lo + ks * 16 + c) : 0u;
-    qf[ks][1] = q_lo ? *reinterpret_cast<const uint32_t*>(q_lo + ks * 16 + 8 + c) : 0u;
-  }
-}
-
-// process_tile<NT> restricted to the lower eight rows (same order of operations)
-template <int NT>
-ACP_DEVINL void process_tile_half(WarpStateH& st, const uint32_t (&qf)[8][2], uint32_t k_base, uint32_t v_base,
-                                  int tile_tok0, int tok_off, int key_limit, float sl2e, int lane) {
-  float s[NT][2];
-#pragma unroll
-  for (int j = 0; j < NT; ++j) { s[j][0] = s[j][1] = 0.f; }
-  const int mi = lane >> 3, rr = lane & 7;
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-#pragma unroll
-    for (int kp = 0; kp < 4; ++kp) {
-      uint32_t b[4];
-      ldmatrix_x4(b, k_base + tile_off(tok_off + j * 8 + rr, kp * 32 + mi * 8));
-      mma_bf16_16816_lo(s[j], qf[kp * 2][0], qf[kp * 2][1], b[0], b[1]);
-      mma_bf16_16816_lo(s[j], qf[kp * 2 + 1][0], qf[kp * 2 + 1][1], b[2], b[3]);
-    }
-  }
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const int t0 = tile_tok0 + tok_off + j * 8 + 2 * (lane & 3);
-    if (t0 >= key_limit) s[j][0] = -INFINITY;
-    if (t0 + 1 >= key_limit) s[j][1] = -INFINITY;
-    mx = fmaxf(mx, fmaxf(s[j][0], s[j][1]));
-  }
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-  const float mn = fmaxf(st.m, mx);
-  const float base = (mn == -INFINITY) ? 0.f : mn * sl2e;
-  const float corr = (st.m == -INFINITY) ? 0.f : exp2f(st.m * sl2e - base);
-  st.m = mn;
-  st.l *= corr;
-#pragma unroll
-  for (int d = 0; d < 16; ++d) { st.o[d][0] *= corr; st.o[d][1] *= corr; }
-  uint32_t p_hi[NT / 2][2], p_lo[NT / 2][2];   // A fragments a0 (keys 0-7) and a2 (keys 8-15) of each 16-token k-step
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const float p0 = exp2f(s[j][0] * sl2e - base), p1 = exp2f(s[j][1] * sl2e - base);
-    st.l += p0 + p1;
-    const float h0 = bf16_round(p0), h1 = bf16_round(p1);
-    p_hi[j >> 1][j & 1] = pack_bf16x2(h0, h1);
-    p_lo[j >> 1][j & 1] = pack_bf16x2(p0 - h0, p1 - h1);
-  }
-#pragma unroll
-  for (int kt = 0; kt < NT / 2; ++kt) {
-#pragma unroll
-    for (int nd = 0; nd < 8; ++nd) {
-      uint32_t b[4];
-      ldmatrix_x4_trans(b, v_base + tile_off(tok_off + kt * 16 + (mi & 1) * 8 + rr, nd * 16 + (mi >> 1) * 8));
-      mma_bf16_16816_lo(st.o[nd * 2], p_hi[kt][0], p_hi[kt][1], b[0], b[1]);
-      mma_bf16_16816_lo(st.o[nd * 2], p_lo[kt][0], p_lo[kt][1], b[0], b[1]);
-      mma_bf16_16816_lo(st.o[nd * 2 + 1], p_hi[kt][0], p_hi[kt][1], b[2], b[3]);
-      mma_bf16_16816_lo(st.o[nd * 2 + 1], p_lo[kt][0], p_lo[kt][1], b[2], b[3]);
-    }
-  }
-}
-
-ACP_DEVINL void fold_new_token_half(WarpStateH& st, const SmemLayout& L, int G, float sl2e, int lane) {
-  const int row = lane >> 2;
-  if (row < G) {
-    const float s = L.ns[row];
-    const float mn = fmaxf(st.m, s);
-    const float corr = (st.m == -INFINITY) ? 0.f : exp2f((st.m - mn) * sl2e);
-    const float p = exp2f((s - mn) * sl2e);
-    st.m = mn;
-    st.l = st.l * corr + (((lane & 3) == 0) ? p : 0.f);
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const int dim = d * 8 + 2 * (lane & 3);
-      st.o[d][0] = st.o[d][0] * corr + p * L.nv[dim];
-      st.o[d][1] = st.o[d][1] * corr + p * L.nv[dim + 1];
-    }
-  }
-}
-
-ACP_DEVINL void attn_half_setup(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const SmemLayout& L) {
-  pdl_launch_dependents();
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm_k);
-    tma_prefetch_desc(&tm_v);
-    for (int s = 0; s < STAGES_H; ++s) {
-      mbar_init(&L.full_bar[s], 1);
-      mbar_init(&L.empty_bar[s], CONSUMER_WARPS);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-  pdl_wait();
-}
-
-__global__ void __launch_bounds__(ATTN_THREADS, 3)
-attn_decode_half_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                        AttnDecodeArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  SmemLayout L = carve<STAGES_H>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = a.heads / a.kv_heads;
-  const long long f = blockIdx.x;
-  const int b = find_seq(a.chunk_cum, a.num_seqs, f, a.kv_heads);
-  const int nc = a.chunk_cum[b + 1] - a.chunk_cum[b];
-  const long long r = f - (long long)a.chunk_cum[b] * a.kv_heads;
-  const int kh = (int)(r / nc), chunk = (int)(r % nc);
-  const int ctx = a.ctx_len[b];
-  const int tile_begin = chunk * ATTN_CHUNK_TILES;
-  const int tok_end = min(ctx - 1, (chunk + 1) * ATTN_CHUNK_TILES * TILE_TOK);
-  const int tile_end = max(tile_begin, (tok_end + TILE_TOK - 1) / TILE_TOK);
-  const int n_tiles = tile_end - tile_begin;
-  const bool last_chunk = (chunk == nc - 1);
-  attn_half_setup(tm_k, tm_v, L);
-  if (warp == CONSUMER_WARPS) {
-    produce_tiles_prefetched<STAGES_H>(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
-                                       a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, tile_begin, tile_end, tok_end, lane);
-    return;
-  }
-  const float sl2e = a.scale * 1.4426950408889634f;
-  const int r_lo = lane >> 2;
-  const int tok_off = warp * 16;
-  new_token_prologue(a, L, b, kh, ctx, last_chunk);
-  uint32_t qf[8][2];
-  load_q_frags_half(qf, r_lo < G ? L.nq + r_lo * HEAD_DIM : nullptr, lane);
-  WarpStateH st;
-#pragma unroll
-  for (int d = 0; d < 16; ++d) st.o[d][0] = st.o[d][1] = 0.f;
-  st.m = -INFINITY;
-  st.l = 0.f;
-  for (int it = 0; it < n_tiles; ++it) {
-    const int s = it % STAGES_H;
-    const uint32_t ph = (uint32_t)(it / STAGES_H) & 1u;
-    mbar_wait(&L.full_bar[s], ph);
-    uint8_t* kt = L.stages + s * STAGE_BYTES;
-    uint8_t* vt = kt + K_TILE_BYTES;
-    const int tile_tok0 = (tile_begin + it) * TILE_TOK;
-    const int valid = tok_end - tile_tok0;
-    if (valid > tok_off) {
-      if (valid < tok_off + 16) zero_v_tail(vt, valid, tok_off + 16, lane);
-      process_tile_half<2>(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_off, tok_end, sl2e, lane);
-    }
-    __syncwarp();
-    if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }
-  }
-  if (last_chunk && warp == 0) fold_new_token_half(st, L, G, sl2e, lane);
-  st.l += __shfl_xor_sync(0xffffffffu, st.l, 1);
-  st.l += __shfl_xor_sync(0xffffffffu, st.l, 2);
-  const size_t item = (size_t)b * a.kv_heads + kh;
-  float* base = a.ws + (((item * a.max_chunks + chunk) * CONSUMER_WARPS + warp) * G) * 130;
-  if (r_lo < G) {
-    float* dst = base + (size_t)r_lo * 130;
-    if ((lane & 3) == 0) { dst[128] = st.m; dst[129] = st.l; }
-#pragma unroll
-    for (int d = 0; d < 16; ++d)
-      *reinterpret_cast<float2*>(dst + d * 8 + 2 * (lane & 3)) = make_float2(st.o[d][0], st.o[d][1]);
-  }
-}
-
-__global__ void __launch_bounds__(ATTN_THREADS, 3)
-attn_decode_item_half_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                             AttnDecodeArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  SmemLayout L = carve<STAGES_H>(smem_raw);
-  const int b = blockIdx.x, kh = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = a.heads / a.kv_heads;
-  const int ctx = a.ctx_len[b];
-  const int cached = ctx - 1;
-  const int n_tiles = (cached + TILE_TOK - 1) / TILE_TOK;
-  attn_half_setup(tm_k, tm_v, L);
-  if (warp == CONSUMER_WARPS) {
-    if (n_tiles <= 16) {
-      produce_tiles_prefetched<STAGES_H>(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
-                                         a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, cached, lane);
-    } else if (lane == 0) {
-      produce_tiles<STAGES_H>(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
-                              a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, cached);
-    }
-    return;
-  }
-  const int r_lo = lane >> 2;
-  new_token_prologue(a, L, b, kh, ctx, true);
-  uint32_t qf[8][2];
-  load_q_frags_half(qf, r_lo < G ? L.nq + r_lo * HEAD_DIM : nullptr, lane);
-  WarpStateH st;
-#pragma unroll
-  for (int d = 0; d < 16; ++d) st.o[d][0] = st.o[d][1] = 0.f;
-  st.m = -INFINITY;
-  st.l = 0.f;
-  const float sl2e = a.scale * 1.4426950408889634f;
-  const int tok_off = warp * 16;
-  for (int it = 0; it < n_tiles; ++it) {
-    const int s = it % STAGES_H;
-    const uint32_t ph = (uint32_t)(it / STAGES_H) & 1u;
-    mbar_wait(&L.full_bar[s], ph);
-    uint8_t* kt = L.stages + s * STAGE_BYTES;
-    uint8_t* vt = kt + K_TILE_BYTES;
-    const int tile_tok0 = it * TILE_TOK;
-    const int valid = cached - tile_tok0;
-    if (valid > tok_off) {
-      if (valid < tok_off + 16) zero_v_tail(vt, valid, tok_off + 16, lane);
-      process_tile_half<2>(st, qf, smem_u32(kt), smem_u32(vt), tile_tok0, tok_off, cached, sl2e, lane);
-    }
-    __syncwarp();
-    if (lane == 0) { fence_proxy_async(); mbar_arrive(&L.empty_bar[s]); }
-  }
-  if (warp == 0) fold_new_token_half(st, L, G, sl2e, lane);
-  st.l += __shfl_xor_sync(0xffffffffu, st.l, 1);
-  st.l += __shfl_xor_sync(0xffffffffu, st.l, 2);
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  float* scratch = reinterpret_cast<float*>(L.stages);
-  float* my = scratch + warp * 16 * 130;
-  if (r_lo < G) {
-    if ((lane & 3) == 0) { my[r_lo * 130 + 128] = st.m; my[r_lo * 130 + 129] = st.l; }
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      my[r_lo * 130 + d * 8 + 2 * (lane & 3)] = st.o[d][0];
-      my[r_lo * 130 + d * 8 + 2 * (lane & 3) + 1] = st.o[d][1];
-    }
-  }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  const int d = threadIdx.x;
-  for (int r = 0; r < G; ++r) {
-    float M = -INFINITY;
-    for (int w = 0; w < CONSUMER_WARPS; ++w) M = fmaxf(M, scratch[(w * 16 + r) * 130 + 128]);
-    float num = 0.f, den = 0.f;
-    for (int w = 0; w < CONSUMER_WARPS; ++w) {
-      const float mw = scratch[(w * 16 + r) * 130 + 128];
-      const float wgt = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * sl2e);
-      num += wgt * scratch[(w * 16 + r) * 130 + d];
-      den += wgt * scratch[(w * 16 + r) * 130 + 129];
-    }
-    a.out[(size_t)b * a.heads * HEAD_DIM + (kh * G + r) * HEAD_DIM + d] = __float2bfloat16_rn(num / den);
-  }
-}
-
-// =================================================================================
 // prefill (causal, chunk-capable: queries may start at any position of the sequence)
 // =================================================================================
-// <NS, MINB>: ring depth and CTAs per SM.  <3, 2> is the measured default; <2, 3> (ACP_ATTN_PREFILL_3CTA=1,
-// experimental, unmeasured) trades a stage and ~32 registers (spilled) for a third CTA per SM — the kernel is
-// latency bound at 2 warps per scheduler (profiles/r1_v2_ncu_prefill_kernels.md).
-template <int NS, int MINB>
-__global__ void __launch_bounds__(ATTN_THREADS, MINB)
+// Round 1's mma.sync prefill kernel: kept ONLY as the A/B baseline of the tcgen05 kernel
+// (attention_prefill_tc.cu; ACP_ATTN_PREFILL_TC=0 and tests/test_attention_gpu.py impl 0).
+constexpr int NS = STAGES;
+__global__ void __launch_bounds__(ATTN_THREADS, 2)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                     AttnPrefillArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -988,21 +665,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
 }  // namespace
 
 int attn_setup_attributes() {
-  cudaError_t e0 = cudaFuncSetAttribute(attn_decode_item_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
-  if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_item_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
-  if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
-  if (e0 != cudaSuccess) { fprintf(stderr, "[acp_infer] attention cudaFuncSetAttribute failed\n"); return -5; }
-  if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_item_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_H);
-  if (e0 == cudaSuccess) e0 = cudaFuncSetAttribute(attn_decode_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_H);
-  if (attn_prefill_tc_setup() != 0) return -5;
-  cudaError_t e1 = cudaFuncSetAttribute(attn_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
-  cudaError_t e2 = cudaFuncSetAttribute(attn_prefill_kernel<STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
-  if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(attn_prefill_kernel<STAGES_H, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_H);
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+  if (cudaFuncSetAttribute(attn_decode_item_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM) != cudaSuccess) {
     fprintf(stderr, "[acp_infer] attention cudaFuncSetAttribute failed\n");
     return -5;
   }
-  return 0;
+  return attn_prefill_tc_setup();
 }
 
 int attn_make_kv_map(CUtensorMap* out, const void* base, uint64_t num_pages, int kv_heads) {
@@ -1019,40 +688,17 @@ size_t attn_decode_ws_floats(int max_batch, int heads, int kv_heads, int max_chu
   return (size_t)max_batch * kv_heads * max_chunks * CONSUMER_WARPS * (heads / kv_heads) * 130;
 }
 
-// ACP_ATTN_PT_PREFETCH=1: decode kernels with the page ids of a CTA loaded once by the producer warp
-static bool pt_prefetch_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ACP_ATTN_PT_PREFETCH"); v = (e && *e == '1') ? 1 : 0; }
-  return v == 1;
-}
-
-// ACP_ATTN_HALF=1: half-tile decode kernels (G <= 8), 2-stage ring, 3 CTAs per SM
-static bool half_tile_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ACP_ATTN_HALF"); v = (e && *e == '1') ? 1 : 0; }
-  return v == 1;
-}
-
 int launch_attn_decode(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnDecodeArgs& a,
                        cudaStream_t s) {
   if (a.num_seqs <= 0) return 0;
   if (a.heads % a.kv_heads != 0 || a.heads / a.kv_heads > 16) return -1;
-  const bool half = half_tile_enabled() && a.heads / a.kv_heads <= 8;
   if (a.per_item) {
-    cudaError_t e = half ? acp_launch(attn_decode_item_half_kernel, dim3(a.num_seqs, a.kv_heads), dim3(ATTN_THREADS), ATTN_SMEM_H, s, tm_k, tm_v, a)
-                    : pt_prefetch_enabled()
-                        ? acp_launch(attn_decode_item_kernel<true>, dim3(a.num_seqs, a.kv_heads), dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a)
-                        : acp_launch(attn_decode_item_kernel<false>, dim3(a.num_seqs, a.kv_heads), dim3(ATTN_THREADS), ATTN_SMEM,
-                                     s, tm_k, tm_v, a);
+    cudaError_t e = acp_launch(attn_decode_item_kernel, dim3(a.num_seqs, a.kv_heads), dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
     if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode_item launch: %s\n", cudaGetErrorString(e)); return -5; }
     return 0;
   }
   if (a.total_chunks <= 0) return -1;
-  cudaError_t e = half ? acp_launch(attn_decode_half_kernel, dim3((unsigned)(a.total_chunks * a.kv_heads)), dim3(ATTN_THREADS), ATTN_SMEM_H, s, tm_k, tm_v, a)
-                  : pt_prefetch_enabled()
-                      ? acp_launch(attn_decode_kernel<true>, dim3((unsigned)(a.total_chunks * a.kv_heads)), dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a)
-                      : acp_launch(attn_decode_kernel<false>, dim3((unsigned)(a.total_chunks * a.kv_heads)), dim3(ATTN_THREADS),
-                                   ATTN_SMEM, s, tm_k, tm_v, a);
+  cudaError_t e = acp_launch(attn_decode_kernel, dim3((unsigned)(a.total_chunks * a.kv_heads)), dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_decode launch: %s\n", cudaGetErrorString(e)); return -5; }
   e = acp_launch(attn_merge_kernel, dim3(a.num_seqs, a.heads), dim3(128), 0, s, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_merge launch: %s\n", cudaGetErrorString(e)); return -5; }
@@ -1074,9 +720,7 @@ int launch_attn_prefill(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const 
   const int G = a.heads / a.kv_heads;
   if (a.heads % a.kv_heads != 0 || G > 16 || (16 % G) != 0) return -1;
   dim3 grid(num_blocks, a.kv_heads);
-  static const bool three = [] { const char* e = getenv("ACP_ATTN_PREFILL_3CTA"); return e && *e == '1'; }();
-  cudaError_t e = three ? acp_launch(attn_prefill_kernel<STAGES_H, 3>, grid, dim3(ATTN_THREADS), ATTN_SMEM_H, s, tm_k, tm_v, a)
-                        : acp_launch(attn_prefill_kernel<STAGES, 2>, grid, dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
+  cudaError_t e = acp_launch(attn_prefill_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, s, tm_k, tm_v, a);
   if (e != cudaSuccess) { fprintf(stderr, "[acp_infer] attn_prefill launch: %s\n", cudaGetErrorString(e)); return -5; }
   return 0;
 }

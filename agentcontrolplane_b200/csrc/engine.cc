@@ -69,6 +69,11 @@ int Engine::init(const char* config_json) {
   }
   if (cfg.find("seed")) mc.seed = (uint64_t)cfg.get("seed").as_int((long long)mc.seed);
   if (cfg.find("layers")) mc.layers = (int)cfg.get("layers").as_int(mc.layers);  // truncated-depth runs
+  // std of the seeded synthetic matrices (oracle/synth.py); the default 0.02 makes every layer's
+  // update ~85x the embedding's scale, a chaotic regime in which bf16 rounding noise grows layer by
+  // layer — tests/test_fulldepth_gpu.py also runs a damped setting where it does not
+  if (cfg.find("w_std") && !ckpt_) mc.w_std = cfg.get("w_std").as_double(mc.w_std);
+  if (!(mc.w_std > 0.0 && mc.w_std < 1.0)) { fprintf(stderr, "[acp_infer] w_std out of range\n"); return -1; }
   if (mc.layers < 1 || mc.layers > 1024 || mc.hidden < 128 || mc.ffn < 64 || mc.vocab < 128 || mc.heads < 1 || mc.kv_heads < 1) {
     fprintf(stderr, "[acp_infer] invalid model dimensions (layers=%d hidden=%d ffn=%d vocab=%d heads=%d kv_heads=%d)\n",
             mc.layers, mc.hidden, mc.ffn, mc.vocab, mc.heads, mc.kv_heads);

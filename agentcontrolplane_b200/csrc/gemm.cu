@@ -147,30 +147,6 @@ static bool persistent_enabled() {
   return v == 1;
 }
 
-// experimental (next round's first A/B): split-K decode steps of more than 256 sequences on the
-// persistent kernel; off unless ACP_GEMM_PERSISTENT_DECODE=1
-static bool persistent_decode_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ACP_GEMM_PERSISTENT_DECODE"); v = (e && *e == '1') ? 1 : 0; }
-  return v == 1;
-}
-
-static int launch_persistent_splitk(const GemmLaunch& g, cudaStream_t stream) {
-  GemmArgs a;
-  a.M = g.M; a.N = g.N; a.K = g.K; a.splits = g.splits; a.ld = g.ld; a.n_cap = g.n_cap;
-  a.out = g.out; a.amax_val = nullptr; a.amax_idx = nullptr; a.n_dev = g.n_dev;
-  const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (g.N + PGEMM_BN - 1) / PGEMM_BN;
-  int grid = m_tiles * n_tiles * g.splits;
-  if (grid > 148) grid = 148;
-  cudaError_t e = acp_launch(gemm_wx_persistent_kernel<EPI_F32, true>, dim3(grid), dim3(GEMM_THREADS), PGEMM_SMEM, stream,
-                             *g.w, g.x->x[4], a, m_tiles, n_tiles);
-  if (e != cudaSuccess) {
-    fprintf(stderr, "[acp_infer] persistent split-K gemm launch failed: %s\n", cudaGetErrorString(e));
-    return -5;
-  }
-  return 0;
-}
-
 template <int EPI>
 static int launch_persistent(const GemmLaunch& g, cudaStream_t stream) {
   GemmArgs a;
@@ -195,7 +171,6 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   if (g.N > 256 && g.bn_override == 0 && persistent_enabled()) {
     if (g.epi == EPI_BF16) return launch_persistent<EPI_BF16>(g, stream);
     if (g.epi == EPI_SWIGLU) return launch_persistent<EPI_SWIGLU>(g, stream);
-    if (g.epi == EPI_F32 && persistent_decode_enabled()) return launch_persistent_splitk(g, stream);
   }
   const int bn = g.bn_override ? g.bn_override : gemm_pick_bn(g.N);
   switch (bn) {
@@ -228,8 +203,7 @@ int gemm_setup_attributes() {
   int rc = set_attr_bn<16>() | set_attr_bn<32>() | set_attr_bn<64>() | set_attr_bn<128>() |
            set_attr_bn<256>();
   if (cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_F32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess)
+      cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess)
     rc = -5;
   if (rc != 0) fprintf(stderr, "[acp_infer] cudaFuncSetAttribute(max dyn smem) failed\n");
   return rc;

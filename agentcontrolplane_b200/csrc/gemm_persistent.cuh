@@ -19,27 +19,14 @@ constexpr int PGEMM_STAGES = 4;
 constexpr int PGEMM_STAGE_BYTES = GEMM_BM * GEMM_BK * 2 + PGEMM_BN * GEMM_BK * 2;  // 48 KiB
 constexpr int PGEMM_SMEM = PGEMM_STAGES * PGEMM_STAGE_BYTES + 1024 + 256;
 
-// SPLITK (experimental, ACP_GEMM_PERSISTENT_DECODE=1, not yet measured): the same loop over
-// (m-tile, split, n-tile) work items with fp32 partial planes out, for DECODE steps of more than
-// 256 sequences — the split ranges are the non-persistent kernel's, so the planes are identical.
-struct PTile { int m_tile, n0, split, kb_begin, kb_end; };
-template <bool SPLITK>
-__device__ __forceinline__ PTile ptile_decode(int t, int n_tiles, int splits, int nkb) {
+struct PTile { int m_tile, n0; };
+__device__ __forceinline__ PTile ptile_decode(int t, int n_tiles) {
   PTile p;
-  if constexpr (SPLITK) {
-    const int r = t / n_tiles;
-    p.n0 = (t % n_tiles) * 256;
-    p.split = r % splits;
-    p.m_tile = r / splits;
-    p.kb_begin = (int)(((long long)nkb * p.split) / splits);
-    p.kb_end = (int)(((long long)nkb * (p.split + 1)) / splits);
-  } else {
-    p.m_tile = t / n_tiles; p.n0 = (t % n_tiles) * 256; p.split = 0; p.kb_begin = 0; p.kb_end = nkb;
-  }
+  p.m_tile = t / n_tiles; p.n0 = (t % n_tiles) * 256;
   return p;
 }
 
-template <int EPI, bool SPLITK = false>
+template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_wx_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                           GemmArgs args, int m_tiles, int n_tiles) {
@@ -56,7 +43,7 @@ gemm_wx_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gr
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nkb = (args.K + GEMM_BK - 1) / GEMM_BK;
-  const int num_tiles = SPLITK ? m_tiles * n_tiles * args.splits : m_tiles * n_tiles;
+  const int num_tiles = m_tiles * n_tiles;
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -79,9 +66,9 @@ gemm_wx_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gr
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const PTile pt = ptile_decode<SPLITK>(t, n_tiles, args.splits, nkb);
+        const PTile pt = ptile_decode(t, n_tiles);
         const int m_tile = pt.m_tile, n0 = pt.n0;
-        for (int kb = pt.kb_begin; kb < pt.kb_end; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* a_dst = smem + s * PGEMM_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], PGEMM_STAGE_BYTES);
@@ -103,9 +90,8 @@ gemm_wx_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gr
         mbar_wait(&tmem_empty[buf], (uint32_t)((i >> 1) & 1) ^ 1u);  // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * PGEMM_BN);
-        const PTile pt = ptile_decode<SPLITK>(t, n_tiles, args.splits, nkb);
-        const int kb0 = pt.kb_begin;
-        for (int kb = pt.kb_begin; kb < pt.kb_end; ++kb) {
+        const PTile pt = ptile_decode(t, n_tiles);
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * PGEMM_STAGE_BYTES);
@@ -113,7 +99,7 @@ gemm_wx_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gr
           const uint64_t b_desc = umma_desc_k_sw128(a_addr + ABYTES);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16(acc, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16(acc, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -128,7 +114,7 @@ gemm_wx_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gr
     int i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
-      const PTile pt = ptile_decode<SPLITK>(t, n_tiles, args.splits, nkb);
+      const PTile pt = ptile_decode(t, n_tiles);
       const int m_tile = pt.m_tile, n0 = pt.n0;
       const int m = m_tile * GEMM_BM + q * 32 + lane;
       mbar_wait(&tmem_full[buf], (uint32_t)((i >> 1) & 1));
@@ -146,14 +132,6 @@ gemm_wx_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gr
             const int n = n0 + c + j;
             if (n < n_valid && m < args.M)
               out[(size_t)n * args.ld + m] = __float2bfloat16_rn(__uint_as_float(r[j]));
-          }
-        } else if constexpr (EPI == EPI_F32) {  // split-K partial plane (SPLITK instantiation only)
-          float* outf = (float*)args.out;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c + j;
-            if (n < n_valid && m < args.M)
-              outf[((size_t)pt.split * args.n_cap + n) * args.ld + m] = __uint_as_float(r[j]);
           }
         } else {  // EPI_SWIGLU
           swiglu_store16(out, r, n0 + c, n_valid, m, args.M, args.ld, lane);

@@ -125,9 +125,6 @@ def test_checkpoint_with_its_own_tokenizer_json(tmp_path):
         Engine(dict(BASE, weights=small))
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("ACP_UNVALIDATED_TESTS"),
-                    reason="written after the round's GPU budget was spent: enable with ACP_UNVALIDATED_TESTS=1, "
-                           "then drop this guard once it has passed on a B200")
 def test_llama31_rope_scaling_checkpoint_matches_oracle(tmp_path):
     """config.json rope_scaling {"rope_type": "llama3"}: the engine's scaled RoPE table is bit-identical
     to the oracle's (tests/test_checkpoint_cpu.py), so greedy tokens must match the bf16 oracle."""
