@@ -755,23 +755,6 @@ bool Engine::step() {
   in.want_logits = want_logits;
   in.max_ctx = max_ctx;
 
-  if (tp_ > 1 && (!all_greedy || want_logits)) {
-    // vocab-parallel LM head: sampling / logits need an all-gather of logits (not built yet)
-    std::lock_guard<std::mutex> lk(mu_);
-    for (int i = 0; i < ns; ++i) {
-      Sequence& s = *part[sample_seq[i]];
-      if (s.sampling.temperature > 0.f || s.return_logits > 0)
-        for (auto it = running_.begin(); it != running_.end(); ++it)
-          if (it->get() == &s) {
-            auto sp = *it;
-            running_.erase(it);
-            finish(sp, 400, "invalid_request_error", "temperature > 0 and return_logits are not supported by a tensor-parallel engine", "");
-            break;
-          }
-    }
-    cv_done_.notify_all();
-    return true;
-  }
   int rc = run_forward(in);
   if (rc != 0) { fail_all_running("CUDA step failed (see stderr)"); return true; }
   float step_ms = 0.f;

@@ -585,4 +585,24 @@ int launch_argmax_ranks(const int* gathered, int P, int B, int* token_out, cudaS
   return 0;
 }
 
+// [P][n][rows_per_rank] padded logit shards (rank r holds vocabulary rows r*rows_per_rank ...) -> [n][vocab]
+__global__ void __launch_bounds__(256)
+repack_logits_kernel(const float* __restrict__ gathered, int n, int rows_per_rank, int vocab, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * vocab) return;
+  const int row = (int)(i / vocab), v = (int)(i % vocab);
+  const int r = v / rows_per_rank, c = v % rows_per_rank;
+  out[i] = gathered[((size_t)r * n + row) * rows_per_rank + c];
+}
+int launch_repack_logits(const float* gathered, int P, int n, int rows_per_rank, int vocab, float* out, cudaStream_t s) {
+  (void)P;
+  if (n <= 0) return 0;
+  const size_t total = (size_t)n * vocab;
+  ACP_LAUNCH("repack_logits", acp_launch(repack_logits_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s,
+                                         gathered, n, rows_per_rank, vocab, out));
+  return 0;
+}
+
 }  // namespace acp

@@ -90,6 +90,7 @@ int launch_reduce_planes(const float* planes, int splits, size_t plane_elems, fl
 
 // Tensor-parallel arg-max: gathered[P][2][B] (per rank: B fp32 maxima then B int32 global ids)
 // -> token[B], lowest id wins ties.
+int launch_repack_logits(const float* gathered, int P, int n, int rows_per_rank, int vocab, float* out, cudaStream_t s);
 int launch_argmax_ranks(const int* gathered, int P, int B, int* token_out, cudaStream_t s);
 // packs (val[B], idx[B] + idx_offset) into out[2][B] words
 int launch_pack_candidates(const float* val, const int* idx, int idx_offset, int B, int* out, cudaStream_t s);

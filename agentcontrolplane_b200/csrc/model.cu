@@ -174,6 +174,7 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int 
     const int t1 = per * (tp_rank + 1) < tiles ? per * (tp_rank + 1) : tiles;
     lm_row0_ = t0 * GEMM_BM;
     lm_rows_l_ = (t1 - t0) * GEMM_BM;
+    lm_rows_per_rank_ = per * GEMM_BM;
     if (lm_rows_l_ <= 0) { fprintf(stderr, "[acp_infer] tp too large for the vocabulary\n"); return -1; }
   }
   const char* env = getenv("ACP_SPLITK_TARGET");
@@ -267,7 +268,11 @@ int Model::alloc_all() {
   const int m_tiles_lm = (lm_rows_l_ + GEMM_BM - 1) / GEMM_BM;
   ACP_TRY(dmalloc_t(allocs_, &amax_val_, (size_t)Bp * m_tiles_lm));
   ACP_TRY(dmalloc_t(allocs_, &amax_idx_, (size_t)Bp * m_tiles_lm));
-  ACP_TRY(dmalloc_t(allocs_, &logits_, (size_t)lim_.max_batch * lm_rows_l_));
+  ACP_TRY(dmalloc_t(allocs_, &logits_, (size_t)lim_.max_batch * lm_rows_per_rank_));
+  if (tp_size_ > 1) {
+    ACP_TRY(dmalloc_t(allocs_, &logits_gather_, (size_t)tp_size_ * lim_.max_batch * lm_rows_per_rank_));
+    ACP_TRY(dmalloc_t(allocs_, &logits_full_, (size_t)lim_.max_batch * cfg_.vocab));
+  }
   attn_max_chunks_ = attn_decode_chunks(lim_.max_pages_per_seq * KV_PAGE);
   ACP_TRY(dmalloc_t(allocs_, &attn_ws_, attn_decode_ws_floats(lim_.max_batch, heads_l_, kvh_l_, attn_max_chunks_)));
   // step staging
@@ -279,7 +284,7 @@ int Model::alloc_all() {
   ACP_CUDA_CHECK(cudaMallocHost((void**)&h_sparams_, lim_.max_batch * sizeof(SampleParams)));
   ACP_TRY(dmalloc_t(allocs_, &d_tokens_, (size_t)lim_.max_batch));
   ACP_CUDA_CHECK(cudaMallocHost((void**)&h_tokens_, lim_.max_batch * sizeof(int)));
-  ACP_CUDA_CHECK(cudaMallocHost((void**)&h_logits_, (size_t)lim_.max_batch * lm_rows_l_ * sizeof(float)));
+  ACP_CUDA_CHECK(cudaMallocHost((void**)&h_logits_, (size_t)lim_.max_batch * (tp_rank_ == 0 ? cfg_.vocab : GEMM_BM) * sizeof(float)));
   return 0;
 }
 
@@ -736,13 +741,10 @@ int Model::forward(const StepInput& in) {
     const int m_tiles = (lm_rows_l_ + GEMM_BM - 1) / GEMM_BM;
     GemmLaunch g;
     g.w = &m_lm_.w; g.x = &m_xs_; g.M = lm_rows_l_; g.N = in.n_sample; g.K = c.hidden; g.splits = 1;
-    g.epi = EPI_ARGMAX; g.ld = lm_rows_l_; g.n_cap = in.n_sample;
+    g.epi = EPI_ARGMAX; g.ld = lm_rows_per_rank_; g.n_cap = in.n_sample;   // == lm_rows_l_ when tp == 1
     const bool logits = in.want_logits || !in.all_greedy;
-    if (logits && tp_size_ > 1) {
-      fprintf(stderr, "[acp_infer] logits / sampling are not available on a tensor-parallel engine yet\n");
-      return -1;
-    }
     g.out = logits ? logits_ : nullptr;
+    const float* full_logits = logits_;
     g.amax_val = amax_val_; g.amax_idx = amax_idx_;
     PROF("gemm_lm_head_argmax", gemm_launch(g, stream_));
     ++launches_;
@@ -755,6 +757,22 @@ int Model::forward(const StepInput& in) {
       if (rc != 0) { fprintf(stderr, "[acp_infer] ncclAllGather: %s\n", nc.GetErrorString(rc)); return -5; }
       ACP_TRY(launch_argmax_ranks(cand_all_, tp_size_, in.n_sample, d_tokens_, stream_));
       launches_ += 4;
+      if (logits) {
+        // sampling / return_logits under a vocab-parallel LM head: all-gather the padded logit
+        // shards ([n][rows per rank] per rank) and re-pack them as [n][vocab]; every rank then runs
+        // the same sampler on the same bits (only rank 0's tokens / logits leave the device)
+        rc = nc.AllGather(logits_, logits_gather_, (size_t)in.n_sample * lm_rows_per_rank_ * sizeof(float), kNcclInt8, comm_, stream_);
+        if (rc != 0) { fprintf(stderr, "[acp_infer] ncclAllGather(logits): %s\n", nc.GetErrorString(rc)); return -5; }
+        ACP_TRY(launch_repack_logits(logits_gather_, tp_size_, in.n_sample, lm_rows_per_rank_, c.vocab, logits_full_, stream_));
+        launches_ += 2;
+        full_logits = logits_full_;
+        if (!in.all_greedy) {
+          ACP_CUDA_CHECK(cudaMemcpyAsync(d_sparams_, lead_ ? lead_->h_sparams_ : h_sparams_, in.n_sample * sizeof(SampleParams),
+                                         cudaMemcpyHostToDevice, stream_));
+          h2d_bytes_ += (long long)(in.n_sample * sizeof(SampleParams));
+          ACP_TRY(launch_sample(full_logits, c.vocab, in.n_sample, d_sparams_, d_tokens_, stream_));   // greedy rows: same arg-max, lowest id
+        }
+      }
     } else if (in.all_greedy) {
       PROF("argmax_finish", launch_argmax_finish(amax_val_, amax_idx_, m_tiles, in.n_sample, d_tokens_, nullptr, stream_));
     } else {
@@ -769,7 +787,7 @@ int Model::forward(const StepInput& in) {
       d2h_bytes_ += (long long)(in.n_sample * sizeof(int));
       if (in.want_logits) {
         d2h_bytes_ += (long long)in.n_sample * c.vocab * (long long)sizeof(float);
-        ACP_CUDA_CHECK(cudaMemcpyAsync(h_logits_, logits_, (size_t)in.n_sample * c.vocab * sizeof(float),
+        ACP_CUDA_CHECK(cudaMemcpyAsync(h_logits_, full_logits, (size_t)in.n_sample * c.vocab * sizeof(float),
                                        cudaMemcpyDeviceToHost, stream_));
       }
     }

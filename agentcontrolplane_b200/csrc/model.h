@@ -146,6 +146,9 @@ class Model {
   Model* lead_ = nullptr;
   int heads_l_ = 0, kvh_l_ = 0, qdim_l_ = 0, kvdim_l_ = 0, qkv_l_ = 0, ffn_l_ = 0;
   int lm_rows_l_ = 0, lm_row0_ = 0;
+  int lm_rows_per_rank_ = 0;       // rows of the widest vocabulary shard (logits rows are padded to it)
+  float* logits_gather_ = nullptr; // [P][max_batch][lm_rows_per_rank_] all-gathered logits (sampling / return_logits under TP)
+  float* logits_full_ = nullptr;   // [max_batch][vocab] re-packed on every rank (rank 0 samples / copies out)
   float* ar_buf_ = nullptr;      // [T][hidden] fp32 all-reduce buffer
   int* cand_local_ = nullptr;    // [2][B] packed (max, id)
   int* cand_all_ = nullptr;      // [P][2][B]

@@ -43,11 +43,25 @@ def test_tp_matches_tp1_and_oracle(tp, comm):
         got_tp = _gen(e, model, prompts, n_new)
         s = e.stats()
         assert s["tp"] == tp
-        # sampling is rejected (vocab-parallel LM head), greedy requests are unaffected
-        st, body = e.complete({"model": model, "max_tokens": 2, "temperature": 0.7, "acp": {"prompt_token_ids": prompts[0]}})
-        assert st == 400
+        # sampling / return_logits under the vocab-parallel LM head: logits are all-gathered, the sampler
+        # then sees exactly the TP=1 logits layout (checked against the sampling oracle on those logits)
+        t = e.submit({"model": model, "max_tokens": 3, "temperature": 0.7, "top_k": 20, "seed": 77,
+                      "acp": {"prompt_token_ids": prompts[1], "return_logits": 3}})
+        assert e.wait(t, 120000)
+        lg_tp = e.logits(t, 3, 128256)
+        st, body = e.result(t)
+        assert st == 200, body
+        from oracle import sampling_oracle as S
+        for step, tok in enumerate(body["acp"]["token_ids"]):
+            assert tok in S.candidates(lg_tp[step], 0.7, 20, 1.0, 77, step), (step, tok)
     with Engine(base) as e:
         got_1 = _gen(e, model, prompts, n_new)
+        t = e.submit({"model": model, "max_tokens": 1, "acp": {"prompt_token_ids": prompts[1], "return_logits": 1}})
+        assert e.wait(t, 120000)
+        lg_1 = e.logits(t, 1, 128256)
+        e.result(t)
+    # first-position logits: TP shards sum partial products in a different order (one rounding after the exchange)
+    assert np.max(np.abs(lg_tp[0] - lg_1[0])) < 3e-2
     for p, a, b in zip(prompts, got_tp, got_1):
         want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(p, n_new, eos=(128001, 128008, 128009))
         for i, (x, y, w) in enumerate(zip(a, b, want)):
