@@ -17,7 +17,7 @@
 #include <chrono>
 #include <thread>
 #include "../chat.h"
-#include "../model.h"
+#include "../model_config.h"
 #include "../safetensors.h"
 #include "task.h"
 
@@ -33,6 +33,8 @@ static char* dup_out(const std::string& s, size_t* len = nullptr) {
   if (len) *len = s.size();
   return p;
 }
+extern "C" void acp_host_free(void* p) { free(p); }
+
 static int ret_json(const Json& j, char** out) {
   *out = dup_out(j.dump());
   return *out ? ACP_OK : ACP_ERR_NOMEM;

@@ -1,5 +1,7 @@
 // host/llmclient.cc — see llmclient.h.
 #include "llmclient.h"
+#include <dlfcn.h>
+#include <mutex>
 #include <arpa/inet.h>
 #include <netdb.h>
 #include <netinet/in.h>
@@ -169,6 +171,34 @@ bool convert_from_response_json(const std::string& body, Message* out, std::stri
 // ---------------------------------------------------------------------------------
 // provider: local
 // ---------------------------------------------------------------------------------
+// libacp_host.so has NO link-time dependency on the product library: the engine's C ABI
+// (include/acp_infer.h) is looked up in the process image the first time provider "local" is used —
+// libacp_infer.so must have been loaded with RTLD_GLOBAL (agentcontrolplane_b200/_lib.py), or, in the
+// sanitizer harnesses, the stand-in engine is linked into the executable (-rdynamic).
+namespace {
+struct InferApi {
+  int (*submit)(acp_engine*, const char*, size_t, uint64_t*) = nullptr;
+  int (*wait)(acp_engine*, uint64_t, int) = nullptr;
+  int (*result)(acp_engine*, uint64_t, char**, size_t*, int*) = nullptr;
+  void (*cancel)(acp_engine*, uint64_t) = nullptr;
+  void (*free_)(void*) = nullptr;
+  bool ok() const { return submit && wait && result && cancel && free_; }
+};
+const InferApi* infer_api() {
+  static std::mutex mu;
+  static InferApi api;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!api.ok()) {   // only success is cached: the product may be loaded after the first (failed) look-up
+    api.submit = (decltype(api.submit))dlsym(RTLD_DEFAULT, "acp_infer_submit");
+    api.wait = (decltype(api.wait))dlsym(RTLD_DEFAULT, "acp_infer_wait");
+    api.result = (decltype(api.result))dlsym(RTLD_DEFAULT, "acp_infer_result");
+    api.cancel = (decltype(api.cancel))dlsym(RTLD_DEFAULT, "acp_infer_cancel");
+    api.free_ = (decltype(api.free_))dlsym(RTLD_DEFAULT, "acp_infer_free");
+  }
+  return api.ok() ? &api : nullptr;
+}
+}  // namespace
+
 bool LocalClient::SendRequest(const Context& ctx, const std::vector<Message>& messages,
                               const std::vector<Tool>& tools, Message* out, Error* err) {
   if (!engine_) {
@@ -177,32 +207,37 @@ bool LocalClient::SendRequest(const Context& ctx, const std::vector<Message>& me
   }
   const std::string body = build_chat_request_json(cfg_.Model, messages, tools, cfg_.MaxTokens,
                                                    has_ext_ ? &ext_ : nullptr, &cfg_);
+  const InferApi* api = infer_api();
+  if (!api) {
+    err->Message = "model API call failed: provider local: libacp_infer.so is not loaded in this process";
+    return false;
+  }
   uint64_t ticket = 0;
-  int rc = acp_infer_submit(engine_, body.data(), body.size(), &ticket);
+  int rc = api->submit(engine_, body.data(), body.size(), &ticket);
   if (rc != ACP_OK) {
     err->Message = "model API call failed: acp_infer_submit error " + std::to_string(rc);
     return false;
   }
   // Blocking wait that honours ctx.Done() (manager shutdown): poll the flag every 50 ms.
   while (true) {
-    rc = acp_infer_wait(engine_, ticket, 50);
+    rc = api->wait(engine_, ticket, 50);
     if (rc == ACP_OK) break;
     if (rc != ACP_ERR_TIMEOUT) {
       err->Message = "model API call failed: acp_infer_wait error " + std::to_string(rc);
       return false;
     }
-    if (ctx.done()) acp_infer_cancel(engine_, ticket);
+    if (ctx.done()) api->cancel(engine_, ticket);
   }
   char* resp = nullptr;
   size_t len = 0;
   int status = 0;
-  rc = acp_infer_result(engine_, ticket, &resp, &len, &status);
+  rc = api->result(engine_, ticket, &resp, &len, &status);
   if (rc != ACP_OK) {
     err->Message = "model API call failed: acp_infer_result error " + std::to_string(rc);
     return false;
   }
   last_response_.assign(resp, len);
-  acp_infer_free(resp);
+  api->free_(resp);
   if (status != 200) {
     Json e;
     std::string perr;

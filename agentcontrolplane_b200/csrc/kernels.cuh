@@ -3,6 +3,7 @@
 // or as `splits` fp32 partial planes [splits][n_cap][M] which it sums in index order before the
 // bf16 rounding — the deterministic split-K reduction (see gemm_tcgen05.cuh).
 #pragma once
+#include "model_config.h"
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -95,7 +96,5 @@ int launch_argmax_ranks(const int* gathered, int P, int B, int* token_out, cudaS
 // packs (val[B], idx[B] + idx_offset) into out[2][B] words
 int launch_pack_candidates(const float* val, const int* idx, int idx_offset, int B, int* out, cudaStream_t s);
 
-constexpr int KV_PAGE = 32;   // tokens per KV page
-constexpr int HEAD_DIM = 128;
 
 }  // namespace acp

@@ -1,0 +1,54 @@
+// model_config.h — the architecture description of the served model (pure C++, no CUDA): shared by
+// the engine (libacp_infer.so) and by the host-side mirror of the reference (libacp_host.so), which
+// only needs it to inspect checkpoints.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include "json.h"
+
+namespace acp {
+
+constexpr int KV_PAGE = 32;   // tokens per KV page
+constexpr int HEAD_DIM = 128;
+
+struct ModelConfig {
+  std::string name = "tiny";
+  int hidden = 512, layers = 2, heads = 4, kv_heads = 1, ffn = 1024, vocab = 128256;
+  double rope_theta = 500000.0;
+  float eps = 1e-5f;
+  double w_std = 0.02;
+  int max_pos = 8192;
+  uint64_t seed = 0xACB200ull;
+  bool tied_embeddings = false;   // checkpoint without lm_head.weight: LM head = embedding matrix
+  // Llama-3.1 "llama3" RoPE frequency scaling (config.json rope_scaling); factor 0 = none
+  double rope_factor = 0.0, rope_low_freq = 1.0, rope_high_freq = 4.0;
+  int rope_orig_max_pos = 8192;
+  int q_dim() const { return heads * HEAD_DIM; }
+  int kv_dim() const { return kv_heads * HEAD_DIM; }
+  int qkv_dim() const { return q_dim() + 2 * kv_dim(); }
+  // bytes of weights streamed by one decode step (SURVEY.md §8d "W")
+  double weight_bytes() const {
+    double per_layer = (double)qkv_dim() * hidden + (double)hidden * q_dim() +
+                       2.0 * ffn * hidden + (double)hidden * ffn + 2.0 * hidden;
+    return 2.0 * (per_layer * layers + (double)vocab * hidden + hidden);
+  }
+  double kv_bytes_per_token() const { return 2.0 * kv_dim() * 2.0 * layers; }
+  // algorithmic FLOPs of one step: 2 per weight per token row for the layer matrices,
+  // 2 per LM-head weight per SAMPLED row, and QK^T + PV = 4 * head_dim per (query head, visible key)
+  double layer_params() const {
+    return ((double)qkv_dim() * hidden + (double)hidden * q_dim() + 3.0 * ffn * hidden) * layers;
+  }
+  double step_flops(double token_rows, double sampled_rows, double query_key_pairs) const {
+    return 2.0 * layer_params() * token_rows + 2.0 * (double)vocab * hidden * sampled_rows +
+           4.0 * q_dim() * query_key_pairs * layers;
+  }
+};
+bool model_preset(const std::string& name, ModelConfig* out);
+class Checkpoint;
+// ModelConfig from a HuggingFace Llama config.json; false + *err when the architecture is not one
+// this engine runs (head_dim must be 128, vocab a multiple of 128, ...).
+bool model_config_from_hf(const Json& hf, ModelConfig* out, std::string* err);
+// inverse RoPE frequencies [64] as the engine and oracle/llama_oracle.py rope_tables() build them
+void rope_inv_freq(const ModelConfig& c, float* inv64);
+
+}  // namespace acp

@@ -1,4 +1,4 @@
-"""ctypes binding of include/acp_host.h — the C++ host mirror of the reference's Go code on the
+"""ctypes binding of include/acp_host.h (libacp_host.so) — the C++ host mirror of the reference's Go code on the
 path (llmclient + Task LLM step) and the reconcile-loop simulator.  JSON in, JSON out."""
 from __future__ import annotations
 
@@ -14,7 +14,7 @@ _bound = None
 def lib():
     global _bound
     if _bound is None:
-        l = _lib.load()
+        l = _lib.load_host()
         cp, vp = ctypes.c_char_p, ctypes.c_void_p
         out = ctypes.POINTER(ctypes.c_void_p)
         l.acp_host_render_prompt.argtypes = [cp, ctypes.c_size_t, out]
@@ -29,8 +29,8 @@ def lib():
         l.acp_host_stub_server_stop.restype = None
         l.acp_hostsim_run.argtypes = [vp, cp, out]
         l.acp_host_checkpoint_index.argtypes = [cp, out]
-        l.acp_infer_free.argtypes = [vp]
-        l.acp_infer_free.restype = None
+        l.acp_host_free.argtypes = [vp]
+        l.acp_host_free.restype = None
         _bound = l
     return _bound
 
@@ -39,7 +39,7 @@ def _take(buf, length=None) -> bytes:
     try:
         return ctypes.string_at(buf) if length is None else ctypes.string_at(buf, length)
     finally:
-        lib().acp_infer_free(buf)
+        lib().acp_host_free(buf)
 
 
 def _check(rc, what):

@@ -29,7 +29,9 @@ path — DESIGN.md §6); weak scaling: every rank runs its own 64 Tasks; time = 
 --impl reference: the reference's own path for this metric is a CPU reconcile loop doing HTTP to
 a provider; it cannot be built here (Go, no toolchain), so the arm runs the C++ restatement
 (agentcontrolplane_b200/csrc/host, provider "openai" over loopback to the stub server returning
-the reference's fixture body) on all host cores, on rank 0 only.
+the reference's fixture body) on all host cores, on rank 0 only.  That restatement lives in its own
+library, libacp_host.so (pure C++, not linked against the product): the reference arm never maps
+libacp_infer.so.
 """
 from __future__ import annotations
 
@@ -234,6 +236,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    dry = None
+    if WORKLOAD.get("prompt_min"):
+        # mixed windows: the very windows hostsim will build (dry run, no Task reconciled); both arms
+        # describe — and run — the same window distribution
+        from agentcontrolplane_b200 import host as _host
+        dry = _host.hostsim_run({"tasks": WORKLOAD["tasks"], "provider": "openai", "dry_run": True, **window_cfg(WORKLOAD)})
+        WORKLOAD["name"] += f" [{dry['prompt_tokens_total']} window tokens per step, longest {dry['prompt_tokens_max']}]"
+
     if args.impl == "reference":
         if rank == 0:
             print(json.dumps(run_reference(args)), flush=True)
@@ -261,12 +271,9 @@ def main():
     if WORKLOAD["tool_loop"]:
         pages_per_seq += 12   # second LLM step: window + tool call + tool result
     kv_pages = n_tasks * pages_per_seq * 2 + 8
-    if WORKLOAD.get("prompt_min"):
-        # mixed windows: size the pool from the very windows hostsim will build (dry run, no Task reconciled)
-        dry = host.hostsim_run({"tasks": n_tasks, "provider": "openai", "dry_run": True, **window_cfg(WORKLOAD)})
+    if dry is not None:   # mixed windows: size the KV pool from the dry run
         pages_per_seq = (dry["prompt_tokens_max"] + max_new) // 32 + 2
         kv_pages = dry["prompt_tokens_total"] // 32 + n_tasks * (max_new // 32 + 3) + 64
-        WORKLOAD["name"] += f" [{dry['prompt_tokens_total']} window tokens per step, longest {dry['prompt_tokens_max']}]"
     ecfg = {"model": args.model, "device": local_rank, "max_batch": max(64, n_tasks), "max_tokens_per_step": args.max_tokens_per_step,
             "kv_pages": kv_pages, "max_pages_per_seq": max(32, pages_per_seq), "tp": WORKLOAD["tp"],
             # config 1 measures cold Task steps: KV retention stays off so that no prefill work is skipped;

@@ -1,6 +1,10 @@
 /* acp_host.h — C entry points of the HOST-side mirror of the reference's Go code on this path
  * (agentcontrolplane_b200/csrc/host/: llmclient + Task LLM step), plus the reconcile-loop
- * simulator used by bench.py.  JSON in, malloc'ed JSON out (release with acp_infer_free).
+ * simulator used by bench.py.  JSON in, malloc'ed JSON out (release with acp_host_free).
+ *
+ * These live in their OWN shared library, libacp_host.so (pure C++, no CUDA, not linked against
+ * libacp_infer.so): the reference arm of bench.py and the cpu_baseline load it alone.  Only provider
+ * "local" reaches the engine, through the acp_infer_* C ABI looked up with dlsym at first use.
  *
  * Why this exists: the reference's host language is Go and this image has no Go toolchain, so
  * the caller side of the boundary (what acp/internal/llmclient and
@@ -15,6 +19,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* Releases any buffer returned by the functions below. */
+void acp_host_free(void* p);
 
 /* Chat template + tokenizer: {"text": <prompt with specials spelled out>, "token_ids": [...]}
  * for an OpenAI chat-completions body, or {"status": 4xx, "error": "..."} . */
@@ -38,7 +45,10 @@ int acp_host_build_chat_request(const char* model, const char* messages_crd_json
 int acp_host_convert_response(const char* response_json, char** out_message_crd_json);
 
 /* One Task state-machine operation against an in-memory object store.  input_json:
- *   {"op": "sendLLMRequest" | "checkToolCalls",
+ *   {"op": "sendLLMRequest" | "checkToolCalls" | "sendLLMRequestFromCluster" (validateTaskAndAgent +
+ *          getLLMAndCredentials + CreateClient from the LLM CR + collectTools + the LLM step; needs
+ *          "objects": [{"kind": "Agent"|"LLM"|"Secret"|"ContactChannel", "object": <CR JSON>}] and
+ *          "mcp": {<server>: [<MCP tool>...]}) | "collectTools" ("agent": <Agent CR JSON>),
  *    "task": <Task CR JSON>, "tools": [<llmclient.Tool + "acpToolType">...],
  *    "toolcalls": [<ToolCall CR JSON>...]            (pre-existing objects for checkToolCalls)
  *    "llm": {"provider": "mock" | "local" | "openai" | <anything: unsupported>,

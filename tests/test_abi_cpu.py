@@ -20,7 +20,7 @@ def _declared(header):
 
 @pytest.mark.parametrize("header", ["acp_infer.h", "acp_infer_kernels.h", "acp_host.h"])
 def test_every_declared_symbol_is_exported(header):
-    lib = _lib.load()
+    lib = _lib.load_host() if header == "acp_host.h" else _lib.load()
     names = _declared(header)
     assert names, header
     for n in names:
@@ -50,3 +50,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cc", ".cu", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_host_library_is_independent_of_the_product():
+    """libacp_host.so (the reference-side mirror + CPU baseline) neither links nor needs libacp_infer.so
+    or CUDA: bench.py --impl reference maps it alone."""
+    import subprocess
+    out = subprocess.run(["ldd", _lib.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "libacp_infer" not in out and "libcuda" not in out and "libcudart" not in out, out
+    nm = subprocess.run(["nm", "-D", "--undefined-only", _lib.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "acp_infer_" not in nm and "cuda" not in nm.lower(), nm
+    code = ("import ctypes, json, sys; sys.path.insert(0, %r)\n"
+            "from agentcontrolplane_b200 import host\n"
+            "with host.StubServer() as srv:\n"
+            "    r = host.hostsim_run({'tasks': 20, 'workers': 2, 'provider': 'openai', 'model': 'gpt-4o', 'baseURL': srv.base_url})\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libacp_host.so' in maps and 'libacp_infer' not in maps and 'libcuda' not in maps, maps\n"
+            "print(r['reconciles'])") % ROOT
+    res = subprocess.run([__import__("sys").executable, "-c", code], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip() == "20", res.stderr

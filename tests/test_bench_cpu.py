@@ -23,7 +23,17 @@ def test_reference_arm_contract():
     cb = j["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "sample" in cb
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "64 concurrent Task CRs" in j["config"]["workload"]
+    assert "512 concurrent Task CRs" in j["config"]["workload"] and "window tokens per step" in j["config"]["workload"]
+
+
+def test_reference_arm_never_maps_the_product_library():
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--config', '1']\n"
+            "runpy.run_path(%r, run_name='__main__')\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libacp_host.so' in maps and 'libacp_infer' not in maps, 'product library mapped by the reference arm'\n"
+            % os.path.join(ROOT, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
 
 
 def test_reference_arm_follows_the_config_flag():

@@ -12,22 +12,22 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "agentcontrolplane_b200", "csrc")
 SOURCES = [os.path.join(ROOT, "tests", "sanitizers", "main.cc"), os.path.join(ROOT, "tests", "sanitizers", "engine_stub.cc")] + [
-    os.path.join(CSRC, f) for f in ("host/hostsim.cc", "host/llmclient.cc", "host/task.cc", "chat.cc", "tokenizer.cc", "safetensors.cc")]
+    os.path.join(CSRC, f) for f in ("host/hostsim.cc", "host/llmclient.cc", "host/task.cc", "chat.cc", "tokenizer.cc", "safetensors.cc", "model_config.cc")]
 
 
 SAN = os.path.join(ROOT, "tests", "sanitizers")
 INC = ["-I" + SAN, "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-I/usr/local/cuda/include"]
 BUILDS = {
-    "host_tsan": (["-fsanitize=thread"], SOURCES, ["-lpthread"]),
+    "host_tsan": (["-fsanitize=thread"], SOURCES, ["-lpthread", "-ldl", "-rdynamic"]),
     "engine_sim": (["-fsanitize=thread"], [os.path.join(SAN, "engine_sim_main.cc"), os.path.join(SAN, "fake_model.cc")] + [
-        os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc")], ["-lpthread"]),
+        os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc", "model_config.cc")], ["-lpthread"]),
     "edge_sim": (["-fsanitize=thread"], [os.path.join(SAN, "edge_sim_main.cc"), os.path.join(SAN, "fake_model.cc")] + [
-        os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc")], ["-lpthread"]),
+        os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc", "model_config.cc")], ["-lpthread"]),
     "stack_sim": (["-fsanitize=thread"], [os.path.join(SAN, "stack_sim_main.cc"), os.path.join(SAN, "fake_model.cc")] + [
-        os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc", "host/hostsim.cc",
-                                        "host/llmclient.cc", "host/task.cc")], ["-lpthread"]),
+        os.path.join(CSRC, f) for f in ("engine.cc", "c_api.cc", "chat.cc", "tokenizer.cc", "safetensors.cc", "model_config.cc", "host/hostsim.cc",
+                                        "host/llmclient.cc", "host/task.cc")], ["-lpthread", "-ldl", "-rdynamic"]),
     "fuzz": (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"], [os.path.join(SAN, "fuzz_main.cc")] + [
-        os.path.join(CSRC, f) for f in ("chat.cc", "tokenizer.cc", "safetensors.cc")], []),
+        os.path.join(CSRC, f) for f in ("chat.cc", "tokenizer.cc", "safetensors.cc", "model_config.cc")], []),
 }
 
 
