@@ -73,6 +73,24 @@ ACP_DEVINL void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
 }
 ACP_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// two fp32 -> packed bf16x2 (round to nearest even) in ONE conversion instruction; `lo` lands in bits 0..15
+ACP_DEVINL uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 2^x on the SFU without the denormal fix-up sequence (inputs here are <= 8 and -inf maps to +0)
+ACP_DEVINL float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// P = hi + lo with hi = bf16(p), lo = bf16(p - hi): two PV MMAs carry ~16 mantissa bits of P
+ACP_DEVINL void split_hi_lo(float p0, float p1, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_bf16x2(p0, p1);
+  lo = cvt_bf16x2(p0 - __uint_as_float(hi << 16), p1 - __uint_as_float(hi & 0xffff0000u));
+}
+
 // D[tmem] (+)= A[tmem, bf16 pairs per 32-bit column] * B[smem desc]
 ACP_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -286,8 +304,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           if (tile0 + 32 + c >= limit) sr1[c] = 0xff800000u;
         }
       }
+      {  // four independent max chains (a single one is 32 dependent FMNMX)
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(sr0[c]), __uint_as_float(sr1[c])));
+        for (int c = 0; c < 32; c += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(sr0[c]), __uint_as_float(sr1[c])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(sr0[c + 1]), __uint_as_float(sr1[c + 1])));
+          m2 = fmaxf(m2, fmaxf(__uint_as_float(sr0[c + 2]), __uint_as_float(sr1[c + 2])));
+          m3 = fmaxf(m3, fmaxf(__uint_as_float(sr0[c + 3]), __uint_as_float(sr1[c + 3])));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
       const float cand = mx * sl2e;
       // lazy rescale: keep the old base unless the max grew by more than 2^8 (or there was none)
       float corr = 1.0f;
@@ -295,14 +322,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       if (m_run == -INFINITY) {
         m_run = cand;                        // first visible key of this row (O and l are still 0)
       } else if (cand > m_run + PF_RESCALE_LOG2) {
-        corr = exp2f(m_run - cand);
+        corr = ex2_ftz(m_run - cand);
         m_run = cand;
         need = true;
       }
-      if (j > 0) {
-        mbar_wait(&bars->pv_done, ((uint32_t)(j - 1)) & 1u);   // O is stable: PV_{j-1} has completed
+      // O is only touched when some row of this warp rescales: only then wait for PV_{j-1}.  (Every
+      // phase <= j-2 of pv_done is complete once S_j is full — QK_j was issued after PV_{j-2} — so the
+      // parity of phase j-1 is unambiguous even though earlier phases were never waited for.)
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        mbar_wait(&bars->pv_done, ((uint32_t)(j - 1)) & 1u);
         tcgen05_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
+        {
           l_run *= corr;
 #pragma unroll 1
           for (int c0 = 0; c0 < HEAD_DIM; c0 += 32) {
@@ -318,26 +348,23 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       }
       const float base = (m_run == -INFINITY) ? 0.f : m_run;
       uint32_t ph[32], pl[32];   // columns 0..31 = P hi (keys 2c, 2c+1), columns 32..63 = P lo
-      float lsum = 0.f;
+      float ls0 = 0.f, ls1 = 0.f;
+      const float nbase = -base;
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
-        const float p0 = exp2f(__uint_as_float(sr0[c]) * sl2e - base);
-        const float p1 = exp2f(__uint_as_float(sr0[c + 1]) * sl2e - base);
-        lsum += p0 + p1;
-        const float h0 = bf16_round(p0), h1 = bf16_round(p1);
-        ph[c >> 1] = pack_bf16x2(h0, h1);
-        pl[c >> 1] = pack_bf16x2(p0 - h0, p1 - h1);
+        const float p0 = ex2_ftz(fmaf(__uint_as_float(sr0[c]), sl2e, nbase));
+        const float p1 = ex2_ftz(fmaf(__uint_as_float(sr0[c + 1]), sl2e, nbase));
+        ls0 += p0; ls1 += p1;
+        split_hi_lo(p0, p1, ph[c >> 1], pl[c >> 1]);
       }
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
-        const float p0 = exp2f(__uint_as_float(sr1[c]) * sl2e - base);
-        const float p1 = exp2f(__uint_as_float(sr1[c + 1]) * sl2e - base);
-        lsum += p0 + p1;
-        const float h0 = bf16_round(p0), h1 = bf16_round(p1);
-        ph[16 + (c >> 1)] = pack_bf16x2(h0, h1);
-        pl[16 + (c >> 1)] = pack_bf16x2(p0 - h0, p1 - h1);
+        const float p0 = ex2_ftz(fmaf(__uint_as_float(sr1[c]), sl2e, nbase));
+        const float p1 = ex2_ftz(fmaf(__uint_as_float(sr1[c + 1]), sl2e, nbase));
+        ls0 += p0; ls1 += p1;
+        split_hi_lo(p0, p1, ph[16 + (c >> 1)], pl[16 + (c >> 1)]);
       }
-      l_run += lsum;
+      l_run += ls0 + ls1;
       tmem_st_x32(s_addr, ph);
       tmem_st_x32(s_addr + 32, pl);
       tmem_st_wait();
