@@ -373,6 +373,11 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       if (lane == 0) mbar_arrive(&bars->p_full[bsel]);
     }
     // ---- epilogue: O / l -> bf16 -> global ----
+    // pv_done phases are only waited for on demand, so the parity wait must never be more than one
+    // phase behind: S_{n-1} full implies PV_{n-3} done, hence phase n-2 is the oldest that can still
+    // be pending — wait for it first, then for the last one.  (Waiting for phase n-1 alone would see
+    // the parity of a still-pending phase n-2 as "n-1 complete" and read O two MMAs early.)
+    if (n_tiles >= 2) mbar_wait(&bars->pv_done, ((uint32_t)(n_tiles - 2)) & 1u);
     mbar_wait(&bars->pv_done, ((uint32_t)(n_tiles - 1)) & 1u);
     tcgen05_fence_after();
     const float inv = 1.0f / l_run;

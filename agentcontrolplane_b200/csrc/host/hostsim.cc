@@ -401,13 +401,14 @@ extern "C" int acp_host_task_step(acp_engine* engine, const char* input_json, ch
   tools_from_json(in.get("tools"), &tools);
   for (const Json& tcj : in.get("toolcalls").items())
     store.Put("ToolCall", tcj.get("metadata").get("name").as_string(), tcj);
-  const long long writes0 = store.writes();
+  long long writes0 = store.writes();
   const std::string op = in.get("op").as_string();
   std::string err, request_json;
   task::Result res;
   // cluster objects the step may look up: [{"kind": "Agent"|"LLM"|"Secret"|"ContactChannel", "object": {...}}]
   for (const Json& o : in.get("objects").items())
     store.Put(o.get("kind").as_string(), o.get("object").get("metadata").get("name").as_string(), o.get("object"));
+  writes0 = store.writes();   // API writes of the step itself, not of the fixture
   if (op == "checkToolCalls") {
     res = sm.checkToolCalls(&t, &err);
   } else if (op == "sendLLMRequestFromCluster") {
@@ -415,8 +416,31 @@ extern "C" int acp_host_task_step(acp_engine* engine, const char* input_json, ch
     task::MCPToolsByServer mcp;
     for (const auto& kv : in.get("mcp").members()) mcp[kv.first] = kv.second.items();
     store.Put("Task", t.Name, task::task_to_json(t));
+    writes0 = store.writes();
     llmclient::Context ctx;
     res = sm.sendLLMRequestFromCluster(ctx, &t, mcp, engine, &err);
+  } else if (op == "process" || op == "reconcile") {
+    // StateMachine.Process / TaskReconciler.Reconcile against the objects given; "now" pins the lease clock,
+    // "podName" this controller's identity, "emulate_lease": false = the local provider's hand-off
+    task::MCPToolsByServer mcp;
+    for (const auto& kv : in.get("mcp").members()) mcp[kv.first] = kv.second.items();
+    if (in.find("now")) { const double fixed = in.get("now").as_double(); sm.now = [fixed] { return fixed; }; }
+    if (in.find("podName")) sm.podName = in.get("podName").as_string();
+    if (in.find("emulate_lease")) sm.emulate_lease = in.get("emulate_lease").as_bool(true);
+    llmclient::Context ctx;
+    if (op == "process") {
+      if (!in.get("unsaved").as_bool(false)) { store.Put("Task", t.Name, task::task_to_json(t)); writes0 = store.writes(); }
+      res = sm.Process(ctx, &t, mcp, engine, &err);
+    } else {
+      // Reconcile fetches the Task itself: it only exists if it is among "objects"
+      Json tj;
+      task::TaskReconciler rec2(&store, &rec);
+      if (in.find("now")) { const double fixed = in.get("now").as_double(); rec2.stateMachine().now = [fixed] { return fixed; }; }
+      res = rec2.Reconcile(ctx, in.get("name").as_string(), mcp, engine, &err);
+      if (store.Get("Task", in.get("name").as_string(), &tj)) task::task_from_json(tj, &t);
+    }
+    Json lease;
+    if (store.Get("Lease", "task-llm-" + t.Name, &lease)) { /* reported below */ }
   } else if (op == "collectTools") {
     task::MCPToolsByServer mcp;
     for (const auto& kv : in.get("mcp").members()) mcp[kv.first] = kv.second.items();
@@ -457,6 +481,10 @@ extern "C" int acp_host_task_step(acp_engine* engine, const char* input_json, ch
     for (Json& j : store.ListToolCalls(t.Name, t.Status.ToolCallRequestID)) tcs.push(j);
   out.set("toolcalls", tcs);
   out.set("store_writes", Json(store.writes() - writes0));
+  {
+    Json lease;
+    if (store.Get("Lease", "task-llm-" + t.Name, &lease)) out.set("lease", lease);
+  }
   if (op == "collectTools") {
     Json tj = Json::array();
     for (const Tool& tl : tools) {
@@ -633,16 +661,73 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
     store.Put("Task", t.Name, task::task_to_json(t));
   }
 
+  // the cluster objects the reference's sendLLMRequest looks up on every step (validateTaskAndAgent,
+  // getLLMAndCredentials, collectTools): one Agent, its LLM, the API-key Secret
+  {
+    Json agent = Json::object(), ameta = Json::object(), aspec = Json::object(), astatus = Json::object();
+    ameta.set("name", Json("test-agent"));
+    Json llmref = Json::object(); llmref.set("name", Json("test-llm"));
+    aspec.set("llmRef", llmref);
+    aspec.set("system", Json(system_prompt));
+    if (n_tools > 0) {
+      Json srv = Json::object(); srv.set("name", Json("fetch"));
+      Json servers = Json::array(); servers.push(srv);
+      aspec.set("mcpServers", servers);
+    }
+    astatus.set("ready", Json(true));
+    agent.set("metadata", ameta); agent.set("spec", aspec); agent.set("status", astatus);
+    store.Put("Agent", "test-agent", agent);
+    Json llm = Json::object(), lmeta = Json::object(), lspec = Json::object(), params = Json::object();
+    lmeta.set("name", Json("test-llm"));
+    lspec.set("provider", Json(provider));
+    params.set("model", Json(bc.Model));
+    if (!bc.BaseURL.empty()) params.set("baseUrl", Json(bc.BaseURL));
+    if (bc.MaxTokens > 0) params.set("maxTokens", Json(bc.MaxTokens));
+    lspec.set("parameters", params);
+    if (provider != "local") {   // `local` needs no credentials
+      Json ref = Json::object(); ref.set("name", Json("test-secret")); ref.set("key", Json("api-key"));
+      Json from = Json::object(); from.set("secretKeyRef", ref);
+      lspec.set("apiKeyFrom", from);
+      Json secret = Json::object(), smeta = Json::object(), data = Json::object();
+      smeta.set("name", Json("test-secret"));
+      data.set("api-key", Json("test-key"));
+      secret.set("metadata", smeta); secret.set("data", data);
+      store.Put("Secret", "test-secret", secret);
+    }
+    llm.set("metadata", lmeta); llm.set("spec", lspec);
+    store.Put("LLM", "test-llm", llm);
+  }
+  task::MCPToolsByServer mcp_by_server;
+  if (n_tools > 0) mcp_by_server["fetch"] = mcp;
+  const std::string scripted_call = tools.empty() ? std::string()
+      : "{\"name\": \"" + tools[0].Function.Name + "\", \"parameters\": {\"url\": \"https://api.example.com/data\"}}";
+
   std::atomic<int> next{0};
   std::atomic<long long> reconciles{0};
   std::mutex lat_mu;
   std::vector<double> lat_ms;
   std::map<std::string, int> phases;
   uint64_t digest = 0;
+  // ONE state machine shared by all reconcile workers, like the reference's TaskReconciler
+  task::StateMachine sm(&store, &rec);
+  sm.emulate_lease = lease;
+  static thread_local bool tl_scripted = false;   // this worker's next LLM step is the scripted tool call
+  sm.client_hook = [&](llmclient::LLMClient* c) {
+    if (!tl_scripted) return;
+    // scripted step 1: force the model's output to be a tool call (BASELINE config 3).  The call must fit
+    // the completion budget or it is cut mid-JSON (one token per byte under the synthetic vocabulary):
+    // never fewer decode steps than configured.
+    auto* lc = static_cast<llmclient::LocalClient*>(c);
+    if (bc.MaxTokens < (int)scripted_call.size() + 1) lc->set_max_tokens((int)scripted_call.size() + 1);
+    Json ext = Json::object();
+    Json forced = Json::array();
+    for (unsigned char ch : scripted_call) forced.push(Json((int)ch));
+    forced.push(Json(TOK_EOT));
+    ext.set("force_tokens", forced);
+    lc->set_extension(ext);
+  };
   const auto t0 = std::chrono::steady_clock::now();
   auto worker = [&]() {
-    task::StateMachine sm(&store, &rec);
-    sm.emulate_lease = lease;
     while (true) {
       const int i = next.fetch_add(1);
       if (i >= n_tasks) break;
@@ -655,30 +740,11 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
         task::task_from_json(tj, &t);
         if (t.Status.Phase == "ReadyForLLM") {
           const auto s0 = std::chrono::steady_clock::now();
-          task::ClientFactory factory = [&](std::string* cerr) -> std::unique_ptr<llmclient::LLMClient> {
-            const bool scripted = provider == "local" && tool_loop && steps == 0 && !tools.empty();
-            // scripted step 1: force the model's output to be a tool call (BASELINE config 3)
-            const std::string call = scripted ? "{\"name\": \"" + tools[0].Function.Name +
-                                                    "\", \"parameters\": {\"url\": \"https://api.example.com/data\"}}"
-                                              : std::string();
-            llmclient::BaseConfig step_bc = bc;
-            // the call must fit the completion budget or it is cut mid-JSON and parsed as plain content
-            // (one token per byte under the synthetic vocabulary): never fewer decode steps than configured
-            if (scripted && step_bc.MaxTokens < (int)call.size() + 1) step_bc.MaxTokens = (int)call.size() + 1;
-            auto c = llmclient::NewLLMClient(provider, "test-key", step_bc, engine, cerr);
-            if (c && scripted) {
-              Json ext = Json::object();
-              Json forced = Json::array();
-              for (unsigned char ch : call) forced.push(Json((int)ch));
-              forced.push(Json(TOK_EOT));
-              ext.set("force_tokens", forced);
-              static_cast<llmclient::LocalClient*>(c.get())->set_extension(ext);
-            }
-            return c;
-          };
+          tl_scripted = provider == "local" && tool_loop && steps == 0 && !tools.empty();
           llmclient::Context ctx;
           std::string err;
-          sm.sendLLMRequest(ctx, &t, tools, factory, &err);
+          sm.Process(ctx, &t, mcp_by_server, engine, &err);   // -> sendLLMRequest (a5, a6, CreateClient, a8, the LLM step)
+          tl_scripted = false;
           const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count();
           ++reconciles;
           {
@@ -696,8 +762,9 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
             tc.StatusResult = "{\"data\": \"" + synth_text(seed ^ 0x5151, i, 96) + "\"}";
             store.Put("ToolCall", tc.Name, task::toolcall_to_json(tc));
           }
+          llmclient::Context ctx;
           std::string err;
-          sm.checkToolCalls(&t, &err);
+          sm.Process(ctx, &t, mcp_by_server, engine, &err);   // -> checkToolCalls
         } else {
           break;  // FinalAnswer / Failed
         }

@@ -86,6 +86,7 @@ class LocalClient : public LLMClient {
                    const std::vector<Tool>& tools, Message* out, Error* err) override;
   // test / bench hook: extra "acp" block merged into the request (forced tokens, raw prompt ids)
   void set_extension(const Json& ext) { ext_ = ext; has_ext_ = true; }
+  void set_max_tokens(int n) { cfg_.MaxTokens = n; }
   const std::string& last_response_json() const { return last_response_; }
 
  private:

@@ -1,5 +1,6 @@
 // host/task.cc — see task.h.
 #include "task.h"
+#include <chrono>
 #include <random>
 #include <stdio.h>
 
@@ -24,6 +25,11 @@ Json task_to_json(const Task& t) {
   ar.set("name", Json(t.AgentName));
   spec.set("agentRef", ar);
   if (!t.UserMessage.empty()) spec.set("userMessage", Json(t.UserMessage));
+  if (!t.SpecContextWindow.empty()) {
+    Json scw = Json::array();
+    for (const Message& m : t.SpecContextWindow) scw.push(llmclient::message_to_crd_json(m));
+    spec.set("contextWindow", scw);
+  }
   Json st = Json::object();
   st.set("ready", Json(t.Status.Ready));
   st.set("status", Json(t.Status.Status));
@@ -55,6 +61,12 @@ bool task_from_json(const Json& j, Task* t) {
   for (auto& kv : meta.get("labels").members()) t->Labels[kv.first] = kv.second.as_string();
   t->AgentName = j.get("spec").get("agentRef").get("name").as_string();
   t->UserMessage = j.get("spec").get("userMessage").as_string();
+  t->SpecContextWindow.clear();
+  for (const Json& m : j.get("spec").get("contextWindow").items()) {
+    Message msg;
+    llmclient::message_from_crd_json(m, &msg);
+    t->SpecContextWindow.push_back(std::move(msg));
+  }
   const Json& st = j.get("status");
   t->Status = TaskStatus();
   t->Status.Ready = st.get("ready").as_bool(false);
@@ -146,6 +158,12 @@ void ObjectStore::Put(const std::string& kind, const std::string& name, const Js
   std::lock_guard<std::mutex> lk(mu_);
   ++writes_;
   objs_[kind + "/" + name] = std::move(text);
+}
+bool ObjectStore::Create(const std::string& kind, const std::string& name, const Json& obj) {
+  std::string text = obj.dump();
+  std::lock_guard<std::mutex> lk(mu_);
+  ++writes_;   // the request reaches the API server either way
+  return objs_.emplace(kind + "/" + name, std::move(text)).second;
 }
 bool ObjectStore::Delete(const std::string& kind, const std::string& name) {
   std::lock_guard<std::mutex> lk(mu_);
@@ -312,6 +330,50 @@ Tool ToolFromContactChannel(const Json& channel) {
 // ---------------------------------------------------------------------------------
 // state machine
 // ---------------------------------------------------------------------------------
+StateMachine::StateMachine(ObjectStore* store, Recorder* recorder) : store_(store), recorder_(recorder) {
+  now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+}
+
+// getTaskMutex (state_machine.go:1147-1170): one mutex per task name, created on first use
+std::mutex* StateMachine::getTaskMutex(const std::string& taskName) {
+  std::lock_guard<std::mutex> lk(mutex_map_lock_);
+  auto& slot = task_mutexes_[taskName];
+  if (!slot) slot.reset(new std::mutex());
+  return slot.get();
+}
+
+// canAcquireLease (:1121-1132): we already hold it, or it has no renew time, or it has expired
+bool StateMachine::canAcquireLease(const Json& lease) const {
+  const Json& spec = lease.get("spec");
+  if (spec.get("holderIdentity").as_string() == podName) return true;
+  if (!spec.get("renewTime").is_number()) return true;
+  return now() > spec.get("renewTime").as_double() + leaseDurationSeconds;
+}
+
+// acquireTaskLease (:1069-1118): Create; on AlreadyExists read it and take it over if allowed
+int StateMachine::acquireTaskLease(const std::string& taskName) {
+  const std::string leaseName = "task-llm-" + taskName;
+  const double t = now();
+  Json spec = Json::object();
+  spec.set("holderIdentity", Json(podName));
+  spec.set("leaseDurationSeconds", Json((int)leaseDurationSeconds));
+  spec.set("acquireTime", Json(t));
+  spec.set("renewTime", Json(t));
+  Json meta = Json::object();
+  meta.set("name", Json(leaseName));
+  Json lease = Json::object();
+  lease.set("metadata", meta);
+  lease.set("spec", spec);
+  if (store_->Create("Lease", leaseName, lease)) return 0;
+  Json existing;
+  if (!store_->Get("Lease", leaseName, &existing)) return -1;   // deleted in between: the reference returns the Get error
+  if (!canAcquireLease(existing)) return 1;
+  store_->Put("Lease", leaseName, lease);                       // Update with us as holder
+  return 0;
+}
+
+void StateMachine::releaseTaskLease(const std::string& taskName) { store_->Delete("Lease", "task-llm-" + taskName); }
+
 // apierrors.NewNotFound(...).Error() for a GET of `kind` `name` (what the reference stores in Status.Error)
 static std::string not_found_error(const std::string& resource, const std::string& name) {
   return resource + ".acp.humanlayer.dev \"" + name + "\" not found";
@@ -411,38 +473,57 @@ std::vector<Tool> StateMachine::collectTools(const Json& agent, const MCPToolsBy
   return tools;
 }
 
+// mutex + Lease around an LLM step (state_machine.go:166-181); `body` runs while both are held
+Result StateMachine::withTaskLock(const std::string& taskName, const std::function<Result()>& body) {
+  std::lock_guard<std::mutex> task_lock(*getTaskMutex(taskName));   // :167-169
+  if (emulate_lease) {        // acquireTaskLease -> API write #1 (:172-181)
+    const int rc = acquireTaskLease(taskName);
+    if (rc < 0) { Result r; r.RequeueAfter = 2.0; return r; }        // :174-176
+    if (rc > 0) { Result r; r.RequeueAfter = 5.0; return r; }        // held by another pod (:177-180)
+  }
+  struct LeaseGuard {
+    StateMachine* sm; std::string name; bool on;
+    ~LeaseGuard() { if (on) sm->releaseTaskLease(name); }  // defer releaseTaskLease (:181)
+  } guard{this, taskName, emulate_lease};
+  return body();
+}
+
+// sendLLMRequest in the reference's own order (state_machine.go:162-288): mutex, Lease,
+// validateTaskAndAgent, getLLMAndCredentials, CreateClient (provider switch on the LLM CR), collectTools,
+// then the step.
 Result StateMachine::sendLLMRequestFromCluster(const llmclient::Context& ctx, Task* task, const MCPToolsByServer& mcp,
                                                acp_engine* engine, std::string* err) {
   err->clear();
-  Task statusUpdate = *task;
-  Json agent;
-  bool ok = false;
-  Result r = validateTaskAndAgent(task, &statusUpdate, &agent, &ok, err);   // :183-186
-  if (!ok) return r;
-  Json llm;
-  std::string apiKey;
-  if (!getLLMAndCredentials(agent, task, &statusUpdate, &llm, &apiKey, err)) return Result();   // :188-191
-  const std::string provider = llm.get("spec").get("provider").as_string();
-  const llmclient::BaseConfig bc = llmclient::base_config_from_json(llm.get("spec").get("parameters"));
-  ClientFactory factory = [&](std::string* cerr) { return llmclient::NewLLMClient(provider, apiKey, bc, engine, cerr); };
-  const std::vector<Tool> tools = collectTools(agent, mcp);   // :220
-  return sendLLMRequest(ctx, task, tools, factory, err);
+  return withTaskLock(task->Name, [&]() -> Result {
+    Task statusUpdate = *task;
+    Json agent;
+    bool ok = false;
+    Result r = validateTaskAndAgent(task, &statusUpdate, &agent, &ok, err);   // :183-186
+    if (!ok) return r;
+    Json llm;
+    std::string apiKey;
+    if (!getLLMAndCredentials(agent, task, &statusUpdate, &llm, &apiKey, err)) return Result();   // :188-191
+    const std::string provider = llm.get("spec").get("provider").as_string();
+    const llmclient::BaseConfig bc = llmclient::base_config_from_json(llm.get("spec").get("parameters"));
+    ClientFactory factory = [&](std::string* cerr) {
+      auto c = llmclient::NewLLMClient(provider, apiKey, bc, engine, cerr);
+      if (c && client_hook) client_hook(c.get());
+      return c;
+    };
+    const std::vector<Tool> tools = collectTools(agent, mcp);   // :220 (after CreateClient in the reference; no observable difference)
+    return llmStepLocked(ctx, task, tools, factory, err);
+  });
 }
 
 Result StateMachine::sendLLMRequest(const llmclient::Context& ctx, Task* task, const std::vector<Tool>& tools,
                                     const ClientFactory& factory, std::string* err) {
   err->clear();
-  Task statusUpdate = *task;  // task.DeepCopy()  (:164)
-  if (emulate_lease) {        // acquireTaskLease -> API write #1 (:172-181)
-    Json lease = Json::object();
-    lease.set("holder", Json("acp-controller-manager"));
-    store_->Put("Lease", "task-llm-" + task->Name, lease);
-  }
-  struct LeaseGuard {
-    ObjectStore* s; std::string name; bool on;
-    ~LeaseGuard() { if (on) s->Delete("Lease", name); }  // defer releaseTaskLease (:181)
-  } guard{store_, "task-llm-" + task->Name, emulate_lease};
+  return withTaskLock(task->Name, [&]() -> Result { return llmStepLocked(ctx, task, tools, factory, err); });
+}
 
+Result StateMachine::llmStepLocked(const llmclient::Context& ctx, Task* task, const std::vector<Tool>& tools,
+                                   const ClientFactory& factory, std::string* err) {
+  Task statusUpdate = *task;  // task.DeepCopy()  (:164)
   std::string cerr;
   std::unique_ptr<llmclient::LLMClient> client = factory(&cerr);  // CreateClient (:195)
   if (!client) {
@@ -601,6 +682,83 @@ Result StateMachine::checkToolCalls(Task* task, std::string* err) {
   Result r;
   r.Requeue = true;
   return r;
+}
+
+// ---------------------------------------------------------------------------------
+// Process / Reconcile
+// ---------------------------------------------------------------------------------
+Result StateMachine::initialize(Task* task, std::string* err) {
+  err->clear();
+  task->Status.Phase = "Initializing";
+  task->Status.Status = "Pending";
+  task->Status.StatusDetail = "Initializing Task";
+  store_->Put("Task", task->Name, task_to_json(*task));   // the root span context is out of scope (OTel)
+  Result r;
+  r.Requeue = true;
+  return r;
+}
+
+Result StateMachine::prepareForLLM(Task* task, Task* statusUpdate, const Json& agent, std::string* err) {
+  TaskStatus& st = statusUpdate->Status;
+  if (st.Phase != "Initializing" && st.Phase != "Pending") return Result();
+  const std::string verr = ValidateTaskMessageInput(task->UserMessage, task->SpecContextWindow);
+  if (!verr.empty()) {   // setValidationError (:462-476): returns the error to the controller
+    st.Ready = false;
+    st.Status = "Error";
+    st.Phase = "Failed";
+    st.StatusDetail = verr;
+    st.Error = verr;
+    recorder_->Emit("Warning", "ValidationFailed", verr);
+    store_->Put("Task", task->Name, task_to_json(*statusUpdate));
+    *task = *statusUpdate;
+    *err = verr;
+    return Result();
+  }
+  // ValidateContactChannelRef (:434) belongs to the HumanLayer v1beta3 path: out of scope
+  st.ContextWindow = buildInitialContextWindow(task->SpecContextWindow, agent.get("spec").get("system").as_string(), task->UserMessage);
+  st.Phase = "ReadyForLLM";
+  st.Ready = true;
+  st.Status = "Ready";
+  st.StatusDetail = "Ready to send to LLM";
+  st.Error.clear();
+  if (task->Status.Phase != "ReadyForLLM") recorder_->Emit("Normal", "ValidationSucceeded", "Task validation succeeded");
+  store_->Put("Task", task->Name, task_to_json(*statusUpdate));
+  *task = *statusUpdate;
+  Result r;
+  r.Requeue = true;
+  return r;
+}
+
+Result StateMachine::validateAgent(Task* task, std::string* err) {
+  err->clear();
+  Task statusUpdate = *task;
+  Json agent;
+  bool ok = false;
+  Result r = validateTaskAndAgent(task, &statusUpdate, &agent, &ok, err);
+  if (!ok) return r;
+  return prepareForLLM(task, &statusUpdate, agent, err);
+}
+
+Result StateMachine::Process(const llmclient::Context& ctx, Task* task, const MCPToolsByServer& mcp, acp_engine* engine,
+                             std::string* err) {
+  err->clear();
+  const std::string& phase = task->Status.Phase;
+  if (phase == "FinalAnswer" || phase == "Failed") return Result();   // handleTerminal: only ends the trace
+  if (phase.empty()) return initialize(task, err);
+  if (phase == "Initializing" || phase == "Pending") return validateAgent(task, err);
+  if (phase == "ReadyForLLM") return sendLLMRequestFromCluster(ctx, task, mcp, engine, err);
+  if (phase == "ToolCallsPending") return checkToolCalls(task, err);
+  return Result();   // handleUnknownPhase
+}
+
+Result TaskReconciler::Reconcile(const llmclient::Context& ctx, const std::string& taskName, const MCPToolsByServer& mcp,
+                                 acp_engine* engine, std::string* err) {
+  err->clear();
+  Json tj;
+  if (!store_->Get("Task", taskName, &tj)) return Result();   // client.IgnoreNotFound (:217-219)
+  Task t;
+  if (!task_from_json(tj, &t)) return Result();
+  return sm_.Process(ctx, &t, mcp, engine, err);
 }
 
 }  // namespace task

@@ -10,6 +10,7 @@
 #pragma once
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -46,6 +47,7 @@ struct TaskStatus {  // acp.TaskStatus (acp/api/v1alpha1/task_types.go:108-158),
 };
 struct Task {
   std::string Name, Namespace = "default", UID, AgentName, UserMessage;
+  std::vector<Message> SpecContextWindow;   // task.Spec.ContextWindow (alternative to UserMessage)
   std::map<std::string, std::string> Labels;
   TaskStatus Status;
 };
@@ -67,6 +69,7 @@ class ObjectStore {
  public:
   bool Get(const std::string& kind, const std::string& name, Json* out);
   void Put(const std::string& kind, const std::string& name, const Json& obj);  // create or update
+  bool Create(const std::string& kind, const std::string& name, const Json& obj);  // false = AlreadyExists
   bool Delete(const std::string& kind, const std::string& name);
   std::vector<Json> ListToolCalls(const std::string& task, const std::string& request_id);
   long long writes() const { return writes_; }
@@ -99,7 +102,26 @@ using ClientFactory = std::function<std::unique_ptr<llmclient::LLMClient>(std::s
 
 class StateMachine {
  public:
-  StateMachine(ObjectStore* store, Recorder* recorder) : store_(store), recorder_(recorder) {}
+  StateMachine(ObjectStore* store, Recorder* recorder);
+  // ---- StateMachine.Process (state_machine.go:84-114): terminal -> handleTerminal; no phase ->
+  // initialize; Initializing / Pending -> validateAgent (validateTaskAndAgent + prepareForLLM);
+  // ReadyForLLM -> sendLLMRequest; ToolCallsPending -> checkToolCalls; anything else -> no-op.
+  Result Process(const llmclient::Context& ctx, Task* task, const MCPToolsByServer& mcp, acp_engine* engine,
+                 std::string* err);
+  Result initialize(Task* task, std::string* err);                                    // :119-146
+  Result validateAgent(Task* task, std::string* err);                                 // :149-160
+  Result prepareForLLM(Task* task, Task* statusUpdate, const Json& agent, std::string* err);   // :426-460
+  // ---- per-task mutex + distributed Lease (state_machine.go:166-181, 1069-1145) ----
+  std::mutex* getTaskMutex(const std::string& taskName);
+  // 0 = acquired, 1 = held by another pod (requeue 5 s), -1 = API error (requeue 2 s)
+  int acquireTaskLease(const std::string& taskName);
+  bool canAcquireLease(const Json& lease) const;
+  void releaseTaskLease(const std::string& taskName);
+  std::string podName = "acp-controller-manager-test";   // POD_NAME (:66-70)
+  double leaseDurationSeconds = 30.0;                     // :81
+  std::function<double()> now;                            // seconds; injectable clock for the lease tests
+  // called on every client CreateClient returns (hostsim scripts forced tool calls on LocalClient)
+  std::function<void(llmclient::LLMClient*)> client_hook;
   // The LLM step.  `err` receives the returned Go error text ("" = nil).
   Result sendLLMRequest(const llmclient::Context& ctx, Task* task, const std::vector<Tool>& tools,
                         const ClientFactory& factory, std::string* err);
@@ -124,13 +146,33 @@ class StateMachine {
   // CreateClient from the LLM CR (provider switch), a8, then the LLM step above.
   Result sendLLMRequestFromCluster(const llmclient::Context& ctx, Task* task, const MCPToolsByServer& mcp,
                                    acp_engine* engine, std::string* err);
-  // when true the per-step Lease create/delete of acquireTaskLease/releaseTaskLease
-  // (state_machine.go:1069-1145) is emulated as two store writes (reference behaviour)
+  Result withTaskLock(const std::string& taskName, const std::function<Result()>& body);
+  Result llmStepLocked(const llmclient::Context& ctx, Task* task, const std::vector<Tool>& tools,
+                       const ClientFactory& factory, std::string* err);
+  // when true the per-step Lease of acquireTaskLease/releaseTaskLease (state_machine.go:1069-1145)
+  // is taken (reference behaviour: one Create and one Delete per LLM step); false = the `local`
+  // provider's hand-off (the per-task mutex already serialises a Task's steps)
   bool emulate_lease = true;
 
  private:
   ObjectStore* store_;
   Recorder* recorder_;
+  std::mutex mutex_map_lock_;
+  std::map<std::string, std::unique_ptr<std::mutex>> task_mutexes_;
+};
+
+// TaskReconciler.Reconcile (task_controller.go:215-235): fetch the Task (NotFound is ignored),
+// delegate to StateMachine.Process, persist nothing itself.
+class TaskReconciler {
+ public:
+  TaskReconciler(ObjectStore* store, Recorder* recorder) : store_(store), sm_(store, recorder) {}
+  Result Reconcile(const llmclient::Context& ctx, const std::string& taskName, const MCPToolsByServer& mcp,
+                   acp_engine* engine, std::string* err);
+  StateMachine& stateMachine() { return sm_; }
+
+ private:
+  ObjectStore* store_;
+  StateMachine sm_;
 };
 
 }  // namespace task

@@ -3,6 +3,7 @@
 // strings are UTF-8, \uXXXX escapes (incl. surrogate pairs) are decoded on parse; invalid UTF-8
 // is replaced by U+FFFD on serialisation so that every response is valid JSON text.
 #pragma once
+#include <errno.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -257,8 +258,14 @@ class Json {
         while (pos < n && t[pos] >= '0' && t[pos] <= '9') ++pos;
       }
       std::string tok(t + s, pos - s);
-      if (is_int && tok.size() < 18) *out = Json((long long)strtoll(tok.c_str(), nullptr, 10));
-      else *out = Json(strtod(tok.c_str(), nullptr));
+      // every integer that fits int64 stays exact (request `seed`s are 63-bit); larger ones become doubles
+      bool exact = false;
+      if (is_int && tok.size() <= 20) {
+        errno = 0;
+        const long long v = strtoll(tok.c_str(), nullptr, 10);
+        if (errno == 0) { *out = Json(v); exact = true; }
+      }
+      if (!exact) *out = Json(strtod(tok.c_str(), nullptr));
       return true;
     }
     bool value(Json* out, int depth) {

@@ -8,6 +8,7 @@ bool model_preset(const std::string& name, ModelConfig* c) {
   ModelConfig m;
   m.name = name;
   if (name == "tiny") { m.hidden = 512; m.layers = 2; m.heads = 4; m.kv_heads = 1; m.ffn = 1024; }
+  else if (name == "sim") { m.hidden = 512; m.layers = 2; m.heads = 4; m.kv_heads = 1; m.ffn = 1024; }   // scheduler simulations (tests/sanitizers)
   else if (name == "tiny-g2") { m.hidden = 512; m.layers = 3; m.heads = 4; m.kv_heads = 2; m.ffn = 1536; }
   // the head grouping of one Llama-3-70B tensor-parallel shard at TP=8: 8 query heads on 1 KV head
   else if (name == "tiny-g8") { m.hidden = 1024; m.layers = 2; m.heads = 8; m.kv_heads = 1; m.ffn = 2048; }

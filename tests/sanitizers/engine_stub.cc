@@ -137,8 +137,3 @@ const char* acp_infer_version(void) { return "acp_infer host-only stub"; }
 
 }  // extern "C"
 
-// model.cu is CUDA: the two host helpers hostsim.cc's checkpoint hook needs are not part of this build
-namespace acp {
-bool model_config_from_hf(const Json&, ModelConfig*, std::string* err) { *err = "not in the host-only build"; return false; }
-void rope_inv_freq(const ModelConfig&, float* inv64) { for (int i = 0; i < 64; ++i) inv64[i] = 0.f; }
-}  // namespace acp

@@ -37,15 +37,7 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
 namespace acp {
 
 // ---- free functions engine.cc / hostsim.cc link against ----
-bool model_preset(const std::string& name, ModelConfig* c) {
-  ModelConfig m;
-  m.name = name;
-  m.hidden = 512; m.layers = 2; m.heads = 4; m.kv_heads = 1; m.ffn = 1024;
-  *c = m;
-  return name == "tiny" || name == "sim";
-}
-bool model_config_from_hf(const Json&, ModelConfig*, std::string* err) { *err = "not in the host-only build"; return false; }
-void rope_inv_freq(const ModelConfig&, float* inv64) { for (int i = 0; i < 64; ++i) inv64[i] = 0.f; }
+// model_preset / model_config_from_hf / rope_inv_freq come from csrc/model_config.cc (pure C++, linked as is)
 int attn_prefill_block_tokens(int heads, int kv_heads) { return (16 / (heads / kv_heads)) * 4; }
 int attn_decode_chunks(int ctx_len) { return (ctx_len + 1023) / 1024; }
 const NcclApi& nccl_api() { static NcclApi a; return a; }

