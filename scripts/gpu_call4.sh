@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+echo "=================== attention unit + sampling + engine + fullsize parity"
+( time timeout 1500 python -m pytest tests/test_attention_gpu.py tests/test_sampling_gpu.py tests/test_engine_gpu.py tests/test_fullsize_gpu.py tests/test_llmclient_gpu.py tests/test_checkpoint_gpu.py tests/test_gemm_gpu.py -m gpu -q 2>&1 | grep -E "^E  |passed|failed|Error" | cut -c1-500 | head -40 ) 2>&1
+echo "=================== timings (decode attention K/V prefetch before the grid-dependency wait is in this build)"
+REPS=3 timeout 300 python scripts/engine_probe.py llama-3-8b 64 512 64 2>&1 | grep '"rep": [12]' | cut -c1-420
+REPS=2 timeout 300 python scripts/engine_probe.py llama-3-8b 256 512 24 2>&1 | grep '"rep": 1' | cut -c1-420
+REPS=2 timeout 400 python scripts/config2_probe.py 2>&1 | tail -1 | cut -c1-420
+echo "=================== launch list of one config-1 bench step (ncu, gpu__time_duration)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r2.csv python scripts/engine_probe.py llama-3-8b 64 512 3 > gpurun_out/launches_r2.log 2>&1; tail -1 gpurun_out/launches_r2.log | cut -c1-200
