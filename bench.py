@@ -337,6 +337,41 @@ def main():
         dist, f"cuda:{local_rank}", wall, dev_s, [float(reconciles), float(s1["decode_tokens"])])
     _, dec_max, _ = aggregate(dist, f"cuda:{local_rank}", 0.0, s1["decode_ms"] / 1e3, [0.0])
 
+    # N = 8 only: BASELINE config 3 (Llama-3-70B, tensor parallel over the 8 GPUs of ONE process, 256 Tasks
+    # with the tool-call loop) measured right after the data-parallel line, so that the driver's scaling run
+    # records it.  Every rank frees its GPU first; rank 0 runs `bench.py --config 3` as a SUBPROCESS (a crash
+    # there costs the extra key, never the headline line); the other ranks wait on the rendezvous store
+    # (host-side, no NCCL kernel spinning on their GPUs).
+    tp8 = None
+    # dev: ACP_BENCH_TP_WORLD=2 ACP_BENCH_TP_ARGS="--model llama-3-8b --tp 2" exercises the same flow on a 2-GPU box
+    tp_world = int(os.environ.get("ACP_BENCH_TP_WORLD", "8"))
+    if world == tp_world and world > 1 and args.config == 2 and not args.layers and os.environ.get("ACP_BENCH_TP8", "1") != "0":
+        eng.close()
+        eng = None
+        barrier()
+        store = torch.distributed.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                env = {k: v for k, v in os.environ.items()
+                       if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "MASTER_ADDR", "MASTER_PORT",
+                                    "TORCHELASTIC_RUN_ID", "CUDA_VISIBLE_DEVICES")}
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "3", "--steps", "2", "--warmup", "1",
+                                      *os.environ.get("ACP_BENCH_TP_ARGS", "").split()],
+                                     capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+                j = json.loads(out.stdout.strip().splitlines()[-1])
+                tp8 = {"workload": j["config"]["workload"], "parallelism": j["config"]["parallelism"], "n_gpus": j["n_gpus"],
+                       "value": j["value"], "e2e": j["e2e"]["value"], "unit": j["unit"], "steps": j["steps"],
+                       "decode_tokens_per_s": j["decode_tokens_per_s"], "p50_decode_step_ms": j["p50_decode_step_ms"],
+                       "p99_decode_step_ms": j.get("p99_decode_step_ms"), "roofline_decode_frac_per_gpu": j["roofline"]["frac"],
+                       "roofline_prefill_frac_per_gpu": j["roofline_prefill"]["frac"], "gpu_launches": j["gpu_launches"],
+                       "llm_steps_per_task": j["config"]["llm_steps_per_task"], "prefix_tokens_reused": j["config"]["prefix_tokens_reused"]}
+            except Exception as e:  # noqa: BLE001
+                tp8 = {"unavailable": f"{type(e).__name__}: {e}"[:400]}
+            store.set("acp_bench_tp8_done", "1")
+        else:
+            import datetime
+            store.wait(["acp_bench_tp8_done"], datetime.timedelta(seconds=1500))
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         dec_s = s1["decode_ms"] / 1e3
@@ -392,10 +427,13 @@ def main():
         }
         if config1 is not None:
             line["config1"] = config1
+        if tp8 is not None:
+            line["tp8_70b"] = tp8
         if world == 1 and args.config != 3:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
