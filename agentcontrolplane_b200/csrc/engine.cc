@@ -102,6 +102,17 @@ int Engine::init(const char* config_json) {
     fprintf(stderr, "[acp_infer] max_tokens_per_step %d < max_batch %d: raised to %d\n", lim.max_tokens, lim.max_batch, lim.max_batch);
     lim.max_tokens = lim.max_batch;
   }
+  // Scheduling policy when prompts are pending AND sequences are decoding:
+  //   0 (default)  prefill first — best throughput for a burst of Tasks (bench.py): decoding sequences wait
+  //                until every pending prompt token is cached;
+  //   k > 0        latency bound — after every k prefill steps (each <= max_tokens_per_step rows) ONE decode
+  //                step runs for the sequences that are already generating, so a decoding Task never waits
+  //                longer than k prefill chunks for its next token.
+  // Prompt tokens still take the prefill arithmetic and generated tokens the decode arithmetic (a mixed
+  // step would put decode rows through the non-split GEMM path and change their fp32 summation order),
+  // so results are bit-identical under either policy.
+  decode_interleave_ = (int)cfg.get("decode_interleave").as_int(0);
+  if (decode_interleave_ < 0) decode_interleave_ = 0;
   default_max_tokens_ = (int)cfg.get("default_max_tokens").as_int(default_max_tokens_);
   if (default_max_tokens_ < 1) default_max_tokens_ = 1;
   const int device = (int)cfg.get("device").as_int(0);
@@ -685,8 +696,14 @@ bool Engine::step() {
   // A sequence is in prefill while prompt tokens remain un-cached (even a single one): prompt
   // tokens always take the prefill arithmetic path, generated tokens always the decode path, so a
   // sequence's result never depends on batch composition or chunk boundaries.
-  for (auto& s : running_)
-    if (s->n_cached < s->prompt_len) { prefill = true; break; }
+  bool any_decoding = false;
+  for (auto& s : running_) {
+    if (s->n_cached < s->prompt_len) prefill = true;
+    else any_decoding = true;
+  }
+  if (prefill && any_decoding && decode_interleave_ > 0 && prefill_steps_since_decode_ >= decode_interleave_)
+    prefill = false;   // latency bound: the decoding sequences get a step now, the pending prompts right after
+  prefill_steps_since_decode_ = prefill ? prefill_steps_since_decode_ + 1 : 0;
   int T = 0, n_blocks = 0;
   const int blk_tokens = attn_prefill_block_tokens(model_.config().heads, model_.config().kv_heads);
   if (prefill) {
@@ -703,7 +720,11 @@ bool Engine::step() {
       n_blocks += (t + blk_tokens - 1) / blk_tokens;
     }
   } else {
-    for (auto& s : running_) { part.push_back(s.get()); take.push_back(1); }
+    for (auto& s : running_) {
+      if (s->n_cached < s->prompt_len) continue;   // still prefilling (only possible under decode_interleave)
+      part.push_back(s.get());
+      take.push_back(1);
+    }
     T = (int)part.size();
   }
   if (part.empty()) return false;

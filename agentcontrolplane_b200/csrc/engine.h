@@ -135,6 +135,7 @@ class Engine {
   EngineStats stats_;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   int max_ctx_tokens_ = 0;
+  int decode_interleave_ = 0, prefill_steps_since_decode_ = 0;   // scheduling policy, see Engine::init
   int default_max_tokens_ = 1024;  // completion budget of a request that sets no max_tokens ("default_max_tokens")
 };
 

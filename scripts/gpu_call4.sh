@@ -10,3 +10,5 @@ REPS=2 timeout 300 python scripts/engine_probe.py llama-3-8b 256 512 24 2>&1 | g
 REPS=2 timeout 400 python scripts/config2_probe.py 2>&1 | tail -1 | cut -c1-420
 echo "=================== launch list of one config-1 bench step (ncu, gpu__time_duration)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r2.csv python scripts/engine_probe.py llama-3-8b 64 512 3 > gpurun_out/launches_r2.log 2>&1; tail -1 gpurun_out/launches_r2.log | cut -c1-200
+echo "=================== open-loop arrivals: prefill-first vs latency-bound scheduling"
+timeout 600 python scripts/arrivals_probe.py 30 15 0 1 2>&1 | grep decode_interleave | cut -c1-700

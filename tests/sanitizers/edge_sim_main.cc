@@ -25,7 +25,7 @@ static std::vector<int> prompt_of(int n, uint64_t seed) {
 int main() {
   acp_engine* e = nullptr;
   if (acp_infer_init("{\"model\": \"sim\", \"max_batch\": 6, \"kv_pages\": 64, \"max_tokens_per_step\": 48, "
-                     "\"max_pages_per_seq\": 12, \"prefix_cache\": true}", &e) != 0) return 1;
+                     "\"max_pages_per_seq\": 12, \"prefix_cache\": true, \"decode_interleave\": 1}", &e) != 0) return 1;
   struct Case { std::vector<int> prompt; int max_tokens; int want_status; };
   std::vector<Case> cases;
   const int lens[] = {1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 128, 129, 200, 255, 256, 257, 300};

@@ -37,7 +37,7 @@ int main() {
   const char* cfg = replicas ? "{\"model\": \"sim\", \"replicas\": 4, \"max_batch\": 8, \"kv_pages\": 120, \"max_tokens_per_step\": 512, "
                                "\"max_pages_per_seq\": 16, \"prefix_cache\": true}"
                     : no_cache ? "{\"model\": \"sim\", \"max_batch\": 24, \"kv_pages\": 300, \"max_tokens_per_step\": 512, "
-                               "\"max_pages_per_seq\": 16, \"prefix_cache\": false}"
+                               "\"max_pages_per_seq\": 16, \"prefix_cache\": false, \"decode_interleave\": 2}"
                              : "{\"model\": \"sim\", \"max_batch\": 24, \"kv_pages\": 300, \"max_tokens_per_step\": 512, "
                                "\"max_pages_per_seq\": 16, \"prefix_cache\": true}";
   if (acp_infer_init(cfg, &e) != 0) { fprintf(stderr, "init failed\n"); return 1; }
