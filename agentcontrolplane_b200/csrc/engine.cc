@@ -88,6 +88,7 @@ int Engine::init(const char* config_json) {
     const std::string am = cfg.get("attn_decode_mode").as_string();
     lim.attn_decode_mode = am == "item" ? 1 : (am == "chunked" || am == "flat") ? 2 : 0;
   }
+  lim.strict_batch_invariance = cfg.get("strict_batch_invariance").as_bool(false);
   if (cfg.find("prefix_cache")) prefix_cache_on_ = cfg.get("prefix_cache").as_bool(true);
   request_timeout_ms_ = (double)cfg.get("request_timeout_ms").as_int(0);
   if (cfg.find("splitk_target_ctas")) lim.splitk_target_ctas = (int)cfg.get("splitk_target_ctas").as_int(lim.splitk_target_ctas);

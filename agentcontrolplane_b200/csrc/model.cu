@@ -120,16 +120,28 @@ static int dmalloc_t(std::vector<void*>& allocs, T** p, size_t count, bool zero 
   return dmalloc(allocs, (void**)p, count * sizeof(T), zero);
 }
 
-// Split-K factor of a DECODE-step GEMM.  It depends only on (M, K), never on the batch size, so
-// a sequence's arithmetic does not change with what it happens to be batched with (prefill steps
-// never split: see gemm()).
+// Split-K factor of a DECODE-step GEMM.
+//   N <= 256 rows (one N tile): depends only on (M, K), never on the batch size, so a sequence's
+//   arithmetic does not change with what it happens to be batched with (prefill steps never split:
+//   see gemm()) — the batch-invariance the tests check.
+//   N > 256 rows (BASELINE config 2, B = 512): the GEMMs are tensor-bound and 5-7 fp32 planes of
+//   512 rows cost more than the MMAs (r1: QKV 0.5, O 0.4 PFLOP/s); there the split only has to give
+//   every SM a tile: the smallest S with m_tiles * n_tiles * S >= 148.  Still a fixed function of
+//   (M, K, number of N tiles) — deterministic run to run — but a sequence decoded inside a batch of
+//   more than 256 sums its K range in different pieces than inside a smaller batch
+//   ("strict_batch_invariance": true keeps the one-tile splits everywhere).
 int Model::choose_splits(int M, int K, int N) const {
-  (void)N;
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int nkb = (K + GEMM_BK - 1) / GEMM_BK;
-  int s = (lim_.splitk_target_ctas + m_tiles / 2) / m_tiles;
-  if (s < 1) s = 1;
   const int max_s = nkb / 4 > 0 ? nkb / 4 : 1;  // at least 4 k-blocks per split
+  int s;
+  if (N > 256 && !lim_.strict_batch_invariance) {
+    const int tiles = m_tiles * ((N + 255) / 256);
+    s = (148 + tiles - 1) / tiles;
+  } else {
+    s = (lim_.splitk_target_ctas + m_tiles / 2) / m_tiles;
+  }
+  if (s < 1) s = 1;
   if (s > max_s) s = max_s;
   if (s > 16) s = 16;
   return s;

@@ -23,6 +23,7 @@ struct ModelLimits {
   int num_pages = 2048;      // KV pages (32 tokens each) in the pool, page 0 is reserved
   int max_pages_per_seq = 256;
   int splitk_target_ctas = 222;
+  bool strict_batch_invariance = false;   // true: decode steps of > 256 rows keep the one-tile split-K factors
   int attn_decode_mode = 0;  // 0 = auto, 1 = one CTA per (sequence, kv head) when possible, 2 = always chunked + merge
 };
 
