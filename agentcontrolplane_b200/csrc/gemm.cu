@@ -113,7 +113,8 @@ static int launch_one(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t s
   GemmArgs a;
   a.M = g.M; a.N = g.N; a.K = g.K; a.splits = g.splits; a.ld = g.ld; a.n_cap = g.n_cap;
   a.out = g.out; a.amax_val = g.amax_val; a.amax_idx = g.amax_idx; a.n_dev = g.n_dev;
-  dim3 grid((g.N + BN - 1) / BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.splits);
+  a.group_ranges = g.groups > 0 ? g.group_ranges : nullptr;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.groups > 0 ? g.groups : g.splits);
   cudaError_t e;
   constexpr int kShallow = GemmCfg<BN>::kShallowStages;
   if (kShallow != GemmCfg<BN>::kStages && shallow_enabled())
@@ -152,6 +153,7 @@ static int launch_persistent(const GemmLaunch& g, cudaStream_t stream) {
   GemmArgs a;
   a.M = g.M; a.N = g.N; a.K = g.K; a.splits = 1; a.ld = g.ld; a.n_cap = g.n_cap;
   a.out = g.out; a.amax_val = nullptr; a.amax_idx = nullptr; a.n_dev = g.n_dev;
+  a.group_ranges = nullptr;
   const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (g.N + PGEMM_BN - 1) / PGEMM_BN;
   int grid = m_tiles * n_tiles;
   if (grid > 148) grid = 148;  // one persistent CTA per SM
@@ -167,8 +169,9 @@ static int launch_persistent(const GemmLaunch& g, cudaStream_t stream) {
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   if (g.N <= 0 || g.M <= 0) return 0;
   if (g.epi != EPI_F32 && g.splits != 1) return -1;
+  if (g.groups > 0 && (g.splits != 1 || g.group_ranges == nullptr || (g.epi != EPI_BF16 && g.epi != EPI_SWIGLU))) return -1;
   // prefill-sized problems: persistent kernel with double-buffered TMEM accumulators
-  if (g.N > 256 && g.bn_override == 0 && persistent_enabled()) {
+  if (g.N > 256 && g.bn_override == 0 && g.groups == 0 && persistent_enabled()) {
     if (g.epi == EPI_BF16) return launch_persistent<EPI_BF16>(g, stream);
     if (g.epi == EPI_SWIGLU) return launch_persistent<EPI_SWIGLU>(g, stream);
   }

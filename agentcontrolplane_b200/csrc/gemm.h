@@ -36,6 +36,11 @@ struct GemmLaunch {
   int* amax_idx = nullptr;
   const int* n_dev = nullptr;
   int bn_override = 0;  // 0 = pick from N
+  // grouped mode (mixture of experts): `groups` weight tensors of M rows each, concatenated in `w`;
+  // group g works on rows [ranges[2g], ranges[2g] + ranges[2g+1]) of x / out (device array).  N = the
+  // largest row count any group can have (grid sizing; CTAs past a group's rows exit at once).
+  int groups = 0;
+  const int* group_ranges = nullptr;
 };
 int gemm_pick_bn(int N);
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);

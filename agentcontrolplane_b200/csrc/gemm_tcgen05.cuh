@@ -51,6 +51,10 @@ struct GemmArgs {
   float* amax_val;   // EPI_ARGMAX: [N][m_tiles]
   int* amax_idx;     // EPI_ARGMAX: [N][m_tiles]
   const int* n_dev;  // optional device scalar overriding N (CUDA-graph replay with varying batch)
+  // GROUPED mode (mixture of experts): blockIdx.z = group g, its weights are m-tiles [g*gridDim.y, (g+1)*gridDim.y)
+  // of the (concatenated) weight tensor, its activation / output rows are [ranges[2g], ranges[2g] + ranges[2g+1])
+  // — written on the device by the dispatch kernel, so the row counts never visit the host.  splits must be 1.
+  const int* group_ranges;
 };
 
 template <int BN>
@@ -110,14 +114,25 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   // activation rows, so W streams from HBM once and X (<= 67 MB at 8192 x 4096) is served by L2.
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * GEMM_BM;
-  const int m_tile = blockIdx.y, m_tiles = gridDim.y;
-  const int split = blockIdx.z;
+  const int m_tiles = gridDim.y;
+  const bool grouped = args.group_ranges != nullptr;
+  int m_tile = blockIdx.y;            // weight m-tile (global index over all groups)
+  int split = blockIdx.z;
+  int row_off = 0, group_rows = 0;
+  pdl_launch_dependents();
+  if (grouped) {
+    pdl_wait();                        // the ranges come from the previous kernel (moe_dispatch)
+    row_off = args.group_ranges[2 * blockIdx.z];
+    group_rows = args.group_ranges[2 * blockIdx.z + 1];
+    if (n0 >= group_rows) return;      // whole CTA, before any barrier / TMEM allocation
+    m_tile = (int)blockIdx.z * m_tiles + (int)blockIdx.y;
+    split = 0;
+  }
   const int nkb_total = (args.K + GEMM_BK - 1) / GEMM_BK;
   const int kb_begin = (int)(((long long)nkb_total * split) / args.splits);
   const int kb_end = (int)(((long long)nkb_total * (split + 1)) / args.splits);
   const int nkb = kb_end - kb_begin;
 
-  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
@@ -148,7 +163,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       pdl_wait();  // activations come from the previous kernel
       for (int kb = 0; kb < pre; ++kb)
         tma_load_2d(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tmap_x, &full_bar[kb],
-                    (kb_begin + kb) * GEMM_BK, n0, kEvictLast);
+                    (kb_begin + kb) * GEMM_BK, row_off + n0, kEvictLast);
       int s = pre % STAGES;
       uint32_t ph = (pre == STAGES) ? 1u : 0u;
       for (int kb = pre; kb < nkb; ++kb) {
@@ -159,7 +174,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const int kcoord = (kb_begin + kb) * GEMM_BK;
         // weights are read once per step: evict-first; activations are re-read by every m-tile
         tma_load_2d(a_dst, &tmap_w, &full_bar[s], 0, (m_tile * nkb_total + kb_begin + kb) * GEMM_BM, kEvictFirst);
-        tma_load_2d(b_dst, &tmap_x, &full_bar[s], kcoord, n0, kEvictLast);
+        tma_load_2d(b_dst, &tmap_x, &full_bar[s], kcoord, row_off + n0, kEvictLast);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -194,7 +209,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int m = m0 + q * 32 + lane;
     pdl_wait();  // outputs may still be read by the previous kernels until they complete
-    int n_valid = args.n_dev ? *args.n_dev : args.N;
+    int n_valid = grouped ? group_rows : (args.n_dev ? *args.n_dev : args.N);
     if (nkb > 0) {
       mbar_wait(accum_bar, 0);
       tcgen05_fence_after();
@@ -215,7 +230,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         for (int j = 0; j < 16; ++j) {
           const int n = n0 + c + j;
           if (n < n_valid && m < args.M)
-            out[(size_t)n * args.ld + m] = __float2bfloat16_rn(__uint_as_float(r[j]));
+            out[(size_t)(row_off + n) * args.ld + m] = __float2bfloat16_rn(__uint_as_float(r[j]));
         }
       } else if constexpr (EPI == EPI_F32) {
         float* out = (float*)args.out;
@@ -228,7 +243,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       } else if constexpr (EPI == EPI_SWIGLU) {
         // W rows are stored interleaved: even row = gate_j, odd row = up_j (j = row / 2), so the
         // pair sits in adjacent TMEM lanes = adjacent threads of this warp.
-        swiglu_store16((__nv_bfloat16*)args.out, r, n0 + c, n_valid, m, args.M, args.ld, lane);
+        swiglu_store16((__nv_bfloat16*)args.out + (size_t)row_off * args.ld, r, n0 + c, n_valid, m, args.M, args.ld, lane);
       } else {  // EPI_ARGMAX
         float* out = (float*)args.out;
         float* red_v = (float*)(smem);  // ring buffers are idle now: reuse [4][16] floats + ints

@@ -165,6 +165,15 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int 
   heads_l_ = cfg.heads / tp_size; kvh_l_ = cfg.kv_heads / tp_size;
   qdim_l_ = heads_l_ * HEAD_DIM; kvdim_l_ = kvh_l_ * HEAD_DIM; qkv_l_ = qdim_l_ + 2 * kvdim_l_;
   ffn_l_ = cfg.ffn / tp_size;
+  if (cfg.experts > 0) {
+    // expert parallel: the experts are spread over the tensor-parallel ranks (whole experts, full ffn width each);
+    // attention stays head-parallel.  Tokens are replicated across the ranks (every rank holds xn after the
+    // fused exchange), so "dispatch" is a local gather and "combine" is the row-parallel all-reduce.
+    if (cfg.experts % tp_size) { fprintf(stderr, "[acp_infer] tp=%d does not divide experts=%d\n", tp_size, cfg.experts); return -1; }
+    experts_l_ = cfg.experts / tp_size;
+    expert0_ = tp_rank * experts_l_;
+    ffn_l_ = cfg.ffn;
+  }
   {  // vocab-parallel LM head: whole 128-row tiles per rank
     const int tiles = cfg.vocab / GEMM_BM, per = (tiles + tp_size - 1) / tp_size;
     const int t0 = per * tp_rank < tiles ? per * tp_rank : tiles;
@@ -207,16 +216,27 @@ int Model::alloc_all() {
     Layer& L = layers_[l];
     ACP_TRY(dmalloc_t(allocs_, &L.wqkv, (size_t)qkv_l_ * H));
     ACP_TRY(dmalloc_t(allocs_, &L.wo, H * qdim_l_));
-    ACP_TRY(dmalloc_t(allocs_, &L.wgu, (size_t)2 * ffn_l_ * H));
-    ACP_TRY(dmalloc_t(allocs_, &L.wdown, H * ffn_l_));
+    if (c.experts > 0) {
+      ACP_TRY(dmalloc_t(allocs_, &L.router, (size_t)c.experts * H));
+      ACP_TRY(dmalloc_t(allocs_, &L.wgu_e, (size_t)experts_l_ * 2 * c.ffn * H));
+      ACP_TRY(dmalloc_t(allocs_, &L.wdown_e, (size_t)experts_l_ * H * c.ffn));
+      ACP_TRY(tma_make_weight(&L.m_gu_e, L.wgu_e, (uint64_t)experts_l_ * 2 * c.ffn, H));
+      ACP_TRY(tma_make_weight(&L.m_down_e, L.wdown_e, (uint64_t)experts_l_ * H, c.ffn));
+      L.wgu = L.wdown = nullptr;
+    } else {
+      ACP_TRY(dmalloc_t(allocs_, &L.wgu, (size_t)2 * ffn_l_ * H));
+      ACP_TRY(dmalloc_t(allocs_, &L.wdown, H * ffn_l_));
+    }
     ACP_TRY(dmalloc_t(allocs_, &L.attn_norm, H));
     ACP_TRY(dmalloc_t(allocs_, &L.ffn_norm, H));
     ACP_TRY(dmalloc_t(allocs_, &L.k_cache, kv_elems, true));
     ACP_TRY(dmalloc_t(allocs_, &L.v_cache, kv_elems, true));
     ACP_TRY(tma_make_weight(&L.m_qkv, L.wqkv, qkv_l_, H));
     ACP_TRY(tma_make_weight(&L.m_o, L.wo, H, qdim_l_));
-    ACP_TRY(tma_make_weight(&L.m_gu, L.wgu, 2 * ffn_l_, H));
-    ACP_TRY(tma_make_weight(&L.m_down, L.wdown, H, ffn_l_));
+    if (c.experts == 0) {
+      ACP_TRY(tma_make_weight(&L.m_gu, L.wgu, 2 * ffn_l_, H));
+      ACP_TRY(tma_make_weight(&L.m_down, L.wdown, H, ffn_l_));
+    }
     ACP_TRY(attn_make_kv_map(&L.tm_k, L.k_cache, lim_.num_pages, kvh_l_));
     ACP_TRY(attn_make_kv_map(&L.tm_v, L.v_cache, lim_.num_pages, kvh_l_));
     ACP_TRY(attn_make_kv_half_map(&L.tm_k32, L.k_cache, lim_.num_pages, kvh_l_));
@@ -233,7 +253,19 @@ int Model::alloc_all() {
   ACP_TRY(dmalloc_t(allocs_, &xn_, (size_t)T * H, true));
   ACP_TRY(dmalloc_t(allocs_, &qbuf_, (size_t)T * qdim_l_, true));
   ACP_TRY(dmalloc_t(allocs_, &attn_, (size_t)T * qdim_l_, true));
-  ACP_TRY(dmalloc_t(allocs_, &h_, (size_t)T * ffn_l_, true));
+  ACP_TRY(dmalloc_t(allocs_, &h_, (size_t)T * (c.experts > 0 ? 8 : ffn_l_), true));
+  if (c.experts > 0) {
+    const size_t rows = (size_t)2 * T + 256;   // 2 assignments per token, + one N tile of slack for the last group's TMA box
+    ACP_TRY(dmalloc_t(allocs_, &xe_, rows * H, true));
+    ACP_TRY(dmalloc_t(allocs_, &he_, rows * c.ffn, true));
+    ACP_TRY(dmalloc_t(allocs_, &ye_, rows * H, true));
+    ACP_TRY(tma_make_act(&m_xe_, xe_, rows, H));
+    ACP_TRY(tma_make_act(&m_he_, he_, rows, c.ffn));
+    ACP_TRY(dmalloc_t(allocs_, &moe_topk_idx_, (size_t)2 * T));
+    ACP_TRY(dmalloc_t(allocs_, &moe_topk_w_, (size_t)2 * T));
+    ACP_TRY(dmalloc_t(allocs_, &moe_row_of_, (size_t)2 * T));
+    ACP_TRY(dmalloc_t(allocs_, &moe_ranges_, (size_t)2 * 16));
+  }
   ACP_TRY(dmalloc_t(allocs_, &xs_, (size_t)Bp * H, true));
   int max_m = qkv_l_;
   if (2 * ffn_l_ > max_m) max_m = 2 * ffn_l_;
@@ -242,12 +274,13 @@ int Model::alloc_all() {
   ACP_TRY(attn_make_q_map(&tm_q_, qbuf_, (uint64_t)T, heads_l_, kvh_l_));
   ACP_TRY(tma_make_act(&m_xn_, xn_, T, H));
   ACP_TRY(tma_make_act(&m_attn_, attn_, T, qdim_l_));
-  ACP_TRY(tma_make_act(&m_h_, h_, T, ffn_l_));
+  if (c.experts == 0) ACP_TRY(tma_make_act(&m_h_, h_, T, ffn_l_));
   ACP_TRY(tma_make_act(&m_xs_, xs_, Bp, H));
   // split-K workspace: worst case over the four GEMMs of a decode step with max_batch rows
   size_t ws = 0;
   const int shapes[4][2] = {{qkv_l_, c.hidden}, {c.hidden, qdim_l_}, {2 * ffn_l_, c.hidden}, {c.hidden, ffn_l_}};
   for (auto& s : shapes) {
+    if (c.experts > 0 && (&s - shapes) >= 2) continue;   // the expert GEMMs are grouped, never split-K
     size_t b = (size_t)choose_splits(s[0], s[1], 0) * lim_.max_batch * s[0] * sizeof(float);
     if (b > ws) ws = b;
   }
@@ -314,14 +347,28 @@ int Model::gen_weights() {
       ACP_TRY(launch_synth(L.wqkv, (size_t)qkv_l_ * H, c.seed, base + 0, c.w_std, 0, stream_, m));
     }
     ACP_TRY(launch_synth(L.wo, H * qdim_l_, c.seed, base + 1, c.w_std, 0, stream_, tiled(qdim_l_, c.q_dim(), r * qdim_l_)));
-    {  // gate/up rows interleaved (2j = gate_j, 2j+1 = up_j); values = oracle's [gate; up] tensor
-      SynthMap m = tiled((int)H, (int)H, 0);
-      m.interleave_half = ffn_l_;
-      m.seg_global[0] = r * ffn_l_;
-      m.seg_global[1] = c.ffn + r * ffn_l_;
-      ACP_TRY(launch_synth(L.wgu, (size_t)2 * ffn_l_ * H, c.seed, base + 2, c.w_std, 0, stream_, m));
+    if (c.experts > 0) {
+      // tensor ids of oracle/synth.py: router = layer_tid(l, 6); expert e: expert_tid(l, e, 0 = [gate; up] | 1 = down)
+      ACP_TRY(launch_synth(L.router, (size_t)c.experts * H, c.seed, base + 6, c.w_std, 0, stream_));
+      for (int j = 0; j < experts_l_; ++j) {
+        const uint32_t etid = (1u << 20) + (uint32_t)l * 256u + (uint32_t)(expert0_ + j) * 2u;
+        SynthMap m = tiled((int)H, (int)H, 0);
+        m.interleave_half = c.ffn;
+        m.seg_global[0] = 0;
+        m.seg_global[1] = c.ffn;
+        ACP_TRY(launch_synth(L.wgu_e + (size_t)j * 2 * c.ffn * H, (size_t)2 * c.ffn * H, c.seed, etid, c.w_std, 0, stream_, m));
+        ACP_TRY(launch_synth(L.wdown_e + (size_t)j * H * c.ffn, H * c.ffn, c.seed, etid + 1, c.w_std, 0, stream_, tiled(c.ffn, c.ffn, 0)));
+      }
+    } else {
+      {  // gate/up rows interleaved (2j = gate_j, 2j+1 = up_j); values = oracle's [gate; up] tensor
+        SynthMap m = tiled((int)H, (int)H, 0);
+        m.interleave_half = ffn_l_;
+        m.seg_global[0] = r * ffn_l_;
+        m.seg_global[1] = c.ffn + r * ffn_l_;
+        ACP_TRY(launch_synth(L.wgu, (size_t)2 * ffn_l_ * H, c.seed, base + 2, c.w_std, 0, stream_, m));
+      }
+      ACP_TRY(launch_synth(L.wdown, H * ffn_l_, c.seed, base + 3, c.w_std, 0, stream_, tiled(ffn_l_, c.ffn, r * ffn_l_)));
     }
-    ACP_TRY(launch_synth(L.wdown, H * ffn_l_, c.seed, base + 3, c.w_std, 0, stream_, tiled(ffn_l_, c.ffn, r * ffn_l_)));
     ACP_TRY(launch_synth(L.attn_norm, H, c.seed, base + 4, 0.1, 1, stream_));
     ACP_TRY(launch_synth(L.ffn_norm, H, c.seed, base + 5, 0.1, 1, stream_));
   }
@@ -351,6 +398,10 @@ int Model::build_rope_tables() {
 // placed by gather_weight_kernel through the SAME SynthMap the synthetic generator uses.
 int Model::load_weights(const Checkpoint& ck) {
   const ModelConfig& c = cfg_;
+  if (c.experts > 0) {
+    fprintf(stderr, "[acp_infer] mixture-of-experts checkpoints are not loadable yet (synthetic weights only)\n");
+    return -1;
+  }
   const size_t H = c.hidden;
   const int r = tp_rank_;
   size_t stage_elems = (size_t)c.qkv_dim() * H;
@@ -632,6 +683,17 @@ int Model::forward(const StepInput& in) {
       PROF("add_rmsnorm_o", launch_add_rmsnorm(x_, o, L.ffn_norm, xn_, nullptr, T, c.hidden, c.eps, stream_));
       ++launches_;
     }
+    if (c.experts > 0) {
+      const __nv_bfloat16* gain = (l + 1 < c.layers) ? layers_[l + 1].attn_norm : final_norm_;
+      ACP_TRY(moe_mlp(L, T, gain, l + 1 == c.layers));
+      if (l + 1 == c.layers) {
+        // moe_mlp left the residual added in x_ on this rank: normalise the sampled rows into xs_
+        GemmOut nothing;
+        PROF("add_rmsnorm_final", launch_add_rmsnorm(x_, nothing, final_norm_, xs_, d_srows, in.n_sample, c.hidden, c.eps, stream_));
+        ++launches_;
+      }
+      continue;
+    }
     if (fuse_swiglu_ || (!in.decode && T > 256 && fuse_swiglu_prefill_)) {
       // SwiGLU in the GEMM epilogue.  Decode (non-persistent kernel, epilogue exposed at the end of
       // every CTA) measured no gain, so it stays a separate kernel there unless ACP_FUSE_SWIGLU=1.
@@ -722,6 +784,51 @@ int Model::forward(const StepInput& in) {
       }
     }
   }
+  return 0;
+}
+
+// Sparse MoE MLP of one layer (Mixtral; oracle/llama_oracle.py _moe): router -> dispatch -> gather ->
+// grouped gate/up GEMM with fused SwiGLU -> grouped down GEMM -> weighted combine -> residual + next norm.
+// The expert GEMMs never split K (prefill and decode share one arithmetic path).
+int Model::moe_mlp(Layer& L, int T, const __nv_bfloat16* gain, bool last_layer) {
+  const ModelConfig& c = cfg_;
+  PROF("moe_router", launch_moe_router(xn_, L.router, c.hidden, c.experts, T, moe_topk_idx_, moe_topk_w_, stream_));
+  PROF("moe_dispatch", launch_moe_dispatch(moe_topk_idx_, T, expert0_, experts_l_, moe_ranges_, moe_row_of_, stream_));
+  PROF("moe_gather", launch_moe_gather(xn_, moe_row_of_, c.hidden, T, xe_, stream_));
+  GemmLaunch g;
+  g.groups = experts_l_; g.group_ranges = moe_ranges_; g.splits = 1;
+  g.N = T;   // a token picks an expert at most once: no group has more than T rows
+  g.w = &L.m_gu_e.w; g.x = &m_xe_; g.M = 2 * c.ffn; g.K = c.hidden; g.epi = EPI_SWIGLU; g.out = he_; g.ld = c.ffn; g.n_cap = T;
+  PROF("gemm_experts_gateup_swiglu", gemm_launch(g, stream_));
+  g.w = &L.m_down_e.w; g.x = &m_he_; g.M = c.hidden; g.K = c.ffn; g.epi = EPI_BF16; g.out = ye_; g.ld = c.hidden;
+  PROF("gemm_experts_down", gemm_launch(g, stream_));
+  launches_ += 5;
+  if (tp_size_ > 1) {
+    // expert parallel: fp32 sum over THIS rank's experts, then the row-parallel exchange sums the ranks,
+    // rounds once, adds the residual and normalises (same contract as the dense down projection)
+    PROF("moe_combine", launch_moe_combine(ye_, moe_row_of_, moe_topk_w_, c.hidden, T, ar_buf_, true, stream_));
+    ++launches_;
+    if (have_peers_) {
+      const int epoch = tp_epoch_ + 1;
+      tp_epoch_ += 2;
+      PROF("moe_p2p_allreduce_norm", launch_tp_reduce_norm(peers_, T, c.hidden, gain, c.eps, epoch, tp_flags_ + TP_MAX, last_layer, stream_));
+      ++launches_;
+    } else {
+      const NcclApi& nc = nccl_api();
+      int rc = nc.AllReduce(ar_buf_, ar_buf_, (size_t)T * c.hidden, kNcclFloat32, kNcclSum, comm_, stream_);
+      if (rc != 0) { fprintf(stderr, "[acp_infer] ncclAllReduce: %s\n", nc.GetErrorString(rc)); return -5; }
+      GemmOut o;
+      o.ptr = ar_buf_; o.splits = 1; o.n_cap = T; o.ld = c.hidden;
+      PROF("add_rmsnorm_moe", launch_add_rmsnorm(x_, o, gain, xn_, nullptr, T, c.hidden, c.eps, stream_));
+      launches_ += 2;
+    }
+    return 0;
+  }
+  PROF("moe_combine", launch_moe_combine(ye_, moe_row_of_, moe_topk_w_, c.hidden, T, gemm_bf16_, false, stream_));
+  GemmOut o;
+  o.ptr = gemm_bf16_; o.splits = 0; o.n_cap = T; o.ld = c.hidden;
+  PROF("add_rmsnorm_moe", launch_add_rmsnorm(x_, o, gain, xn_, nullptr, T, c.hidden, c.eps, stream_));
+  launches_ += 2;
   return 0;
 }
 

@@ -12,6 +12,7 @@
 #include "json.h"
 #include "model_config.h"
 #include "kernels.cuh"
+#include "moe.h"
 #include "nccl_dyn.h"
 #include "tp_comm.h"
 
@@ -124,6 +125,10 @@ class Model {
 
   struct Layer {
     __nv_bfloat16 *wqkv, *wo, *wgu, *wdown, *attn_norm, *ffn_norm;
+    // mixture of experts (cfg.experts > 0): router [E][hidden] row-major; this rank's experts concatenated,
+    // each tiled like the dense matrices: wgu_e [E_l][2 ffn][hidden] (gate/up rows interleaved), wdown_e [E_l][hidden][ffn]
+    __nv_bfloat16 *router = nullptr, *wgu_e = nullptr, *wdown_e = nullptr;
+    TmaMaps m_gu_e, m_down_e;
     __nv_bfloat16 *k_cache, *v_cache;
     TmaMaps m_qkv, m_o, m_gu, m_down;
     CUtensorMap tm_k, tm_v;       // box = one (page, kv head) block, both dim halves (decode kernels)
@@ -142,6 +147,13 @@ class Model {
   size_t ws_bytes_ = 0;
   float *amax_val_ = nullptr, *logits_ = nullptr;
   int* amax_idx_ = nullptr;
+  // mixture-of-experts scratch: expert-sorted activations and the routing tables of the current layer
+  int experts_l_ = 0, expert0_ = 0;   // experts on this rank (expert parallel = one slice per tensor-parallel rank)
+  __nv_bfloat16 *xe_ = nullptr, *he_ = nullptr, *ye_ = nullptr;   // [T][hidden], [T][ffn], [T][hidden] x 2 assignments
+  TmaMaps m_xe_, m_he_;
+  int *moe_topk_idx_ = nullptr, *moe_row_of_ = nullptr, *moe_ranges_ = nullptr;
+  float* moe_topk_w_ = nullptr;
+  int moe_mlp(Layer& L, int T, const __nv_bfloat16* gain, bool last_layer);
   float* attn_ws_ = nullptr;
   int attn_max_chunks_ = 1;
   int* d_ints_ = nullptr;     // packed step ints

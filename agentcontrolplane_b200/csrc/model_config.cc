@@ -14,6 +14,11 @@ bool model_preset(const std::string& name, ModelConfig* c) {
   else if (name == "tiny-g8") { m.hidden = 1024; m.layers = 2; m.heads = 8; m.kv_heads = 1; m.ffn = 2048; }
   else if (name == "llama-3-8b-l2") { m.hidden = 4096; m.layers = 2; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; }
   else if (name == "llama-3-8b") { m.hidden = 4096; m.layers = 32; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; }
+  // Mixtral-8x7B architecture (BASELINE config 4).  Synthetic presets keep the 128256-entry vocabulary of
+  // the synthetic tokenizer; a real checkpoint brings its own 32000 entries + tokenizer.json.
+  else if (name == "tiny-moe") { m.hidden = 512; m.layers = 2; m.heads = 4; m.kv_heads = 1; m.ffn = 768; m.experts = 8; m.rope_theta = 1000000.0; }
+  else if (name == "mixtral-8x7b-l2") { m.hidden = 4096; m.layers = 2; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; m.experts = 8; m.rope_theta = 1000000.0; }
+  else if (name == "mixtral-8x7b") { m.hidden = 4096; m.layers = 32; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; m.experts = 8; m.rope_theta = 1000000.0; }
   else if (name == "llama-3-70b") { m.hidden = 8192; m.layers = 80; m.heads = 64; m.kv_heads = 8; m.ffn = 28672; }
   else return false;
   *c = m;
@@ -48,7 +53,12 @@ bool model_config_from_hf(const Json& hf, ModelConfig* out, std::string* err) {
     return true;
   };
   const std::string mt = hf.get("model_type").as_string();
-  if (!mt.empty() && mt != "llama") { *err = "config.json: model_type \"" + mt + "\" is not supported (llama only)"; return false; }
+  if (!mt.empty() && mt != "llama" && mt != "mixtral") { *err = "config.json: model_type \"" + mt + "\" is not supported (llama, mixtral)"; return false; }
+  if (mt == "mixtral") {
+    m.experts = (int)hf.get("num_local_experts").as_int(8);
+    if (hf.get("num_experts_per_tok").as_int(2) != 2 || m.experts < 2 || m.experts > 16) { *err = "config.json: mixtral needs top-2 routing over 2..16 experts"; return false; }
+    if (!hf.get("sliding_window").is_null() && hf.get("sliding_window").as_int(0) > 0) { *err = "config.json: sliding-window attention is not supported"; return false; }
+  }
   if (!need("hidden_size", &m.hidden) || !need("num_hidden_layers", &m.layers) ||
       !need("num_attention_heads", &m.heads) || !need("intermediate_size", &m.ffn) || !need("vocab_size", &m.vocab))
     return false;

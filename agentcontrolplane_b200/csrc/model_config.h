@@ -19,6 +19,7 @@ struct ModelConfig {
   double w_std = 0.02;
   int max_pos = 8192;
   uint64_t seed = 0xACB200ull;
+  int experts = 0;                // Mixtral-style sparse MoE: experts per layer (top-2 routing); 0 = dense MLP
   bool tied_embeddings = false;   // checkpoint without lm_head.weight: LM head = embedding matrix
   // Llama-3.1 "llama3" RoPE frequency scaling (config.json rope_scaling); factor 0 = none
   double rope_factor = 0.0, rope_low_freq = 1.0, rope_high_freq = 4.0;
@@ -27,16 +28,19 @@ struct ModelConfig {
   int kv_dim() const { return kv_heads * HEAD_DIM; }
   int qkv_dim() const { return q_dim() + 2 * kv_dim(); }
   // bytes of weights streamed by one decode step (SURVEY.md §8d "W")
+  // (a mixture-of-experts step streams every expert that has a token; with >= 32 sequences and 8 experts
+  // that is all of them, so all experts are counted)
   double weight_bytes() const {
-    double per_layer = (double)qkv_dim() * hidden + (double)hidden * q_dim() +
-                       2.0 * ffn * hidden + (double)hidden * ffn + 2.0 * hidden;
+    const double mlp = 3.0 * ffn * hidden * (experts > 0 ? experts : 1) + (experts > 0 ? (double)experts * hidden : 0.0);
+    double per_layer = (double)qkv_dim() * hidden + (double)hidden * q_dim() + mlp + 2.0 * hidden;
     return 2.0 * (per_layer * layers + (double)vocab * hidden + hidden);
   }
   double kv_bytes_per_token() const { return 2.0 * kv_dim() * 2.0 * layers; }
   // algorithmic FLOPs of one step: 2 per weight per token row for the layer matrices,
   // 2 per LM-head weight per SAMPLED row, and QK^T + PV = 4 * head_dim per (query head, visible key)
-  double layer_params() const {
-    return ((double)qkv_dim() * hidden + (double)hidden * q_dim() + 3.0 * ffn * hidden) * layers;
+  double layer_params() const {   // weights a token row is multiplied with (top-2 of the experts + the router)
+    const double mlp = experts > 0 ? 2.0 * 3.0 * ffn * hidden + (double)experts * hidden : 3.0 * ffn * hidden;
+    return ((double)qkv_dim() * hidden + (double)hidden * q_dim() + mlp) * layers;
   }
   double step_flops(double token_rows, double sampled_rows, double query_key_pairs) const {
     return 2.0 * layer_params() * token_rows + 2.0 * (double)vocab * hidden * sampled_rows +

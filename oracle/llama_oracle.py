@@ -51,6 +51,9 @@ class LlamaConfig:
     # Llama-3.1 "llama3" RoPE frequency scaling: (factor, low_freq_factor, high_freq_factor,
     # original_max_position_embeddings) or None; same formula as csrc/model.cu rope_inv_freq()
     rope_scaling: tuple | None = None
+    # Mixtral-style sparse mixture of experts: `experts` SwiGLU MLPs of width `ffn` per layer, top-2 routing
+    # (0 = dense Llama MLP)
+    experts: int = 0
 
     @property
     def q_dim(self):
@@ -71,6 +74,14 @@ PRESETS = {
     "llama-3-8b": LlamaConfig("llama-3-8b", hidden=4096, layers=32, heads=32, kv_heads=8, ffn=14336),
     "llama-3-70b": LlamaConfig("llama-3-70b", hidden=8192, layers=80, heads=64, kv_heads=8,
                                ffn=28672),
+    # Mixtral-8x7B architecture (BASELINE config 4): 8 experts, top-2, rope theta 1e6.  The synthetic
+    # presets keep the 128256-entry vocabulary of the synthetic tokenizer (a real checkpoint has 32000).
+    "tiny-moe": LlamaConfig("tiny-moe", hidden=512, layers=2, heads=4, kv_heads=1, ffn=768, experts=8,
+                            rope_theta=1000000.0),
+    "mixtral-8x7b-l2": LlamaConfig("mixtral-8x7b-l2", hidden=4096, layers=2, heads=32, kv_heads=8, ffn=14336,
+                                   experts=8, rope_theta=1000000.0),
+    "mixtral-8x7b": LlamaConfig("mixtral-8x7b", hidden=4096, layers=32, heads=32, kv_heads=8, ffn=14336,
+                                experts=8, rope_theta=1000000.0),
 }
 
 
@@ -99,6 +110,22 @@ def rope_tables(cfg: LlamaConfig, max_pos: int):
     ang = (np.arange(max_pos, dtype=np.float32)[:, None] * inv[None, :]).astype(np.float32)
     return np.cos(ang.astype(np.float64)).astype(np.float32), np.sin(ang.astype(np.float64)).astype(
         np.float32)
+
+
+def router_logits(x: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """fp32 router logits x[T][H] . w[E][H] in the ENGINE's summation order (csrc/moe.cu
+    moe_router_kernel): 32 lanes, lane j accumulates the products of elements j, j+32, j+64, ... in
+    that order (separately rounded multiply and add), then the lanes are folded 16, 8, 4, 2, 1."""
+    T, H = x.shape
+    E = w.shape[0]
+    prod = (x.astype(np.float32)[:, None, :] * w.astype(np.float32)[None, :, :]).astype(np.float32)
+    prod = prod.reshape(T, E, H // 32, 32)
+    acc = np.zeros((T, E, 32), np.float32)
+    for i in range(H // 32):
+        acc = (acc + prod[:, :, i, :]).astype(np.float32)
+    for half in (16, 8, 4, 2, 1):
+        acc = (acc[:, :, :half] + acc[:, :, half:2 * half]).astype(np.float32)
+    return acc[:, :, 0]
 
 
 class Weights:
@@ -143,6 +170,15 @@ class Weights:
 
     def wdown(self, l):
         return self._mat(synth.layer_tid(l, synth.TID_WDOWN), self.cfg.hidden, self.cfg.ffn)
+
+    def router(self, l):
+        return self._mat(synth.layer_tid(l, synth.TID_ROUTER), self.cfg.experts, self.cfg.hidden)
+
+    def expert_gu(self, l, e):
+        return self._mat(synth.expert_tid(l, e, synth.TID_EXPERT_GU), 2 * self.cfg.ffn, self.cfg.hidden)
+
+    def expert_down(self, l, e):
+        return self._mat(synth.expert_tid(l, e, synth.TID_EXPERT_DOWN), self.cfg.hidden, self.cfg.ffn)
 
     def attn_norm(self, l):
         return self._gain(synth.layer_tid(l, synth.TID_ATTN_NORM), self.cfg.hidden)
@@ -225,15 +261,51 @@ class LlamaOracle:
             o = self._r(attn @ self.w.wo(l).T)
             x = self._r(x + o)
             xn2 = self._rmsnorm(x, self.w.ffn_norm(l))
-            gu = self._r(xn2 @ self.w.wgu(l).T)
-            g, u = gu[:, :c.ffn], gu[:, c.ffn:]
-            act = self._r(g / (np.float32(1.0) + np.exp(-g)))
-            h_ = self._r(act * u)
-            d = self._r(h_ @ self.w.wdown(l).T)
+            if c.experts:
+                d = self._moe(xn2, l)
+            else:
+                gu = self._r(xn2 @ self.w.wgu(l).T)
+                g, u = gu[:, :c.ffn], gu[:, c.ffn:]
+                act = self._r(g / (np.float32(1.0) + np.exp(-g)))
+                h_ = self._r(act * u)
+                d = self._r(h_ @ self.w.wdown(l).T)
             x = self._r(x + d)
         self.pos += T
         xf = self._rmsnorm(x if all_logits else x[-1:], self.w.final_norm())
         return (xf @ self.w.lm_head().T).astype(np.float32)
+
+    def _moe(self, xn2, l):
+        """Sparse MoE block of one layer (transformers MixtralSparseMoeBlock: softmax router, top-2,
+        renormalised weights, SwiGLU experts), with the engine's rounding points in bf16 mode:
+            r      = router_logits(xn2)   fp32, FIXED summation order (router_logits below) so that the
+                                          engine and the oracle select the same experts bit for bit
+            e0, e1 = the two largest logits (lowest index wins ties)
+            w0, w1 = 1/(1+exp(r1-r0)), exp(r1-r0)/(1+exp(r1-r0))     (= softmax renormalised over the top 2)
+            d_k    = bf16(h_k @ Wd_k^T),  h_k = bf16(bf16(silu(g)) * u),  [g|u] = bf16(xn2 @ Wgu_k^T)
+            out    = bf16(w0*d_0 + w1*d_1)     (two fp32 products, one fp32 add, one rounding)"""
+        c = self.cfg
+        T = xn2.shape[0]
+        r = router_logits(xn2, self.w.router(l))
+        e0 = np.argmax(r, axis=1)
+        r_masked = r.copy()
+        r_masked[np.arange(T), e0] = -np.inf
+        e1 = np.argmax(r_masked, axis=1)
+        ex = np.exp((r[np.arange(T), e1] - r[np.arange(T), e0]).astype(np.float32)).astype(np.float32)
+        w0 = (np.float32(1.0) / (np.float32(1.0) + ex)).astype(np.float32)
+        w1 = (ex / (np.float32(1.0) + ex)).astype(np.float32)
+        out0 = np.zeros((T, c.hidden), np.float32)
+        out1 = np.zeros((T, c.hidden), np.float32)
+        for e in range(c.experts):
+            for sel, dst in ((e0, out0), (e1, out1)):
+                rows = np.nonzero(sel == e)[0]
+                if rows.size == 0:
+                    continue
+                gu = self._r(xn2[rows] @ self.w.expert_gu(l, e).T)
+                g, u = gu[:, :c.ffn], gu[:, c.ffn:]
+                act = self._r(g / (np.float32(1.0) + np.exp(-g)))
+                dst[rows] = self._r(self._r(act * u) @ self.w.expert_down(l, e).T)
+        self.last_routing = (e0, e1, w0, w1)
+        return self._r((w0[:, None] * out0).astype(np.float32) + (w1[:, None] * out1).astype(np.float32))
 
     def greedy(self, prompt, max_new: int, eos=(), force=None):
         """Greedy decode; returns (token ids, per-step (top1-top2) logit margins).

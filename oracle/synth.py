@@ -24,11 +24,18 @@ IH_STD = 37837.22671196048  # sqrt(4 * (65536**2 - 1) / 12)
 # tensor ids (shared with csrc/model.h)
 TID_EMBED, TID_LM_HEAD, TID_FINAL_NORM = 1, 2, 3
 TID_LAYER_BASE, TID_LAYER_STRIDE = 16, 16
-TID_WQKV, TID_WO, TID_WGU, TID_WDOWN, TID_ATTN_NORM, TID_FFN_NORM = 0, 1, 2, 3, 4, 5
+TID_WQKV, TID_WO, TID_WGU, TID_WDOWN, TID_ATTN_NORM, TID_FFN_NORM, TID_ROUTER = 0, 1, 2, 3, 4, 5, 6
+# mixture-of-experts layers (Mixtral): expert e of layer l owns two tensors, [gate; up] and down
+TID_MOE_BASE, TID_MOE_LAYER_STRIDE = 1 << 20, 256
+TID_EXPERT_GU, TID_EXPERT_DOWN = 0, 1
 
 
 def layer_tid(layer: int, which: int) -> int:
     return TID_LAYER_BASE + layer * TID_LAYER_STRIDE + which
+
+
+def expert_tid(layer: int, expert: int, which: int) -> int:
+    return TID_MOE_BASE + layer * TID_MOE_LAYER_STRIDE + expert * 2 + which
 
 
 def _mix(z: np.ndarray) -> np.ndarray:

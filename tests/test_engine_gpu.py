@@ -49,7 +49,8 @@ def _prompt(rng, n):
 # heads on 1 KV head).  llama-3-8b-l2: the REAL Llama-3-8B width (hidden 4096, 32 q / 8 kv heads, ffn 14336,
 # vocab 128256) at 2 layers, where the numpy oracle still finishes in seconds; full depth is covered by
 # tests/test_fulldepth_gpu.py.
-@pytest.fixture(scope="module", params=["tiny", "tiny-g2", "tiny-g8", "llama-3-8b-l2"])
+# tiny-moe: the Mixtral architecture (8 experts, top-2 routing, grouped expert GEMMs; csrc/moe.cu).
+@pytest.fixture(scope="module", params=["tiny", "tiny-g2", "tiny-g8", "tiny-moe", "llama-3-8b-l2"])
 def eng(request):
     e = Engine({"model": request.param, "max_batch": 64, "kv_pages": 512, "max_tokens_per_step": 1024})
     e.model_name = request.param
