@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <set>
@@ -568,6 +569,10 @@ extern "C" int acp_host_checkpoint_tensor_bf16(const char* path, const char* nam
   return acp::st_to_bf16(*t, 0, *n_elems, out) ? ACP_OK : ACP_ERR_INVALID;
 }
 
+// completion the calling worker's next LLM step is forced to emit ("" = free-running); namespace scope: a
+// function-local thread_local is only initialised in threads that execute its declaration
+static thread_local std::string tl_script;
+
 extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char** result_json_out) {
   if (!config_json || !result_json_out) return ACP_ERR_INVALID;
   Json cfg;
@@ -586,6 +591,10 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
   const bool mixed = pt_min > 0 && pt_max >= pt_min;
   const int n_tools = (int)cfg.get("tools").as_int(0);
   const bool tool_loop = cfg.get("tool_loop").as_bool(false);
+  // BASELINE config 4: open-loop Poisson arrivals (Tasks/s, seeded exponential gaps; 0 = all at once) and
+  // sub-agent delegation chains of this depth (root -> sub-agent-1 -> ... ; executor.go:176-242)
+  const double arrival_rate = cfg.get("arrival_rate").as_double(0.0);
+  const int delegation_depth = std::max(0, std::min(4, (int)cfg.get("delegation_depth").as_int(0)));
   const uint64_t seed = (uint64_t)cfg.get("seed").as_int(1);
   const bool lease = cfg.find("emulate_lease") ? cfg.get("emulate_lease").as_bool(true) : true;
   if (provider == "local" && !engine) return ACP_ERR_INVALID;
@@ -675,8 +684,28 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
       aspec.set("mcpServers", servers);
     }
     astatus.set("ready", Json(true));
+    if (delegation_depth > 0) {
+      Json ref = Json::object(); ref.set("name", Json("sub-agent-1"));
+      Json subs = Json::array(); subs.push(ref);
+      aspec.set("subAgents", subs);
+    }
     agent.set("metadata", ameta); agent.set("spec", aspec); agent.set("status", astatus);
     store.Put("Agent", "test-agent", agent);
+    for (int d = 1; d <= delegation_depth; ++d) {   // sub-agent-d delegates to sub-agent-(d+1); the last one answers
+      Json sa = Json::object(), sm_ = Json::object(), ss = Json::object(), st = Json::object();
+      sm_.set("name", Json("sub-agent-" + std::to_string(d)));
+      ss.set("llmRef", llmref);
+      ss.set("system", Json("You are sub-agent " + std::to_string(d) + "."));
+      ss.set("description", Json("delegate level " + std::to_string(d)));
+      if (d < delegation_depth) {
+        Json ref = Json::object(); ref.set("name", Json("sub-agent-" + std::to_string(d + 1)));
+        Json subs = Json::array(); subs.push(ref);
+        ss.set("subAgents", subs);
+      }
+      st.set("ready", Json(true));
+      sa.set("metadata", sm_); sa.set("spec", ss); sa.set("status", st);
+      store.Put("Agent", "sub-agent-" + std::to_string(d), sa);
+    }
     Json llm = Json::object(), lmeta = Json::object(), lspec = Json::object(), params = Json::object();
     lmeta.set("name", Json("test-llm"));
     lspec.set("provider", Json(provider));
@@ -711,69 +740,127 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
   // ONE state machine shared by all reconcile workers, like the reference's TaskReconciler
   task::StateMachine sm(&store, &rec);
   sm.emulate_lease = lease;
-  static thread_local bool tl_scripted = false;   // this worker's next LLM step is the scripted tool call
   sm.client_hook = [&](llmclient::LLMClient* c) {
-    if (!tl_scripted) return;
-    // scripted step 1: force the model's output to be a tool call (BASELINE config 3).  The call must fit
-    // the completion budget or it is cut mid-JSON (one token per byte under the synthetic vocabulary):
+    if (tl_script.empty()) return;
+    // scripted step: force the model's output to be a tool call (BASELINE configs 3 and 4).  The call must
+    // fit the completion budget or it is cut mid-JSON (one token per byte under the synthetic vocabulary):
     // never fewer decode steps than configured.
     auto* lc = static_cast<llmclient::LocalClient*>(c);
-    if (bc.MaxTokens < (int)scripted_call.size() + 1) lc->set_max_tokens((int)scripted_call.size() + 1);
+    if (bc.MaxTokens < (int)tl_script.size() + 1) lc->set_max_tokens((int)tl_script.size() + 1);
     Json ext = Json::object();
     Json forced = Json::array();
-    for (unsigned char ch : scripted_call) forced.push(Json((int)ch));
+    for (unsigned char ch : tl_script) forced.push(Json((int)ch));
     forced.push(Json(TOK_EOT));
     ext.set("force_tokens", forced);
     lc->set_extension(ext);
   };
+  // arrival offsets of the root Tasks (seconds from the start of the run)
+  std::vector<double> arrival((size_t)std::max(0, n_tasks), 0.0);
+  if (arrival_rate > 0.0) {
+    double tcur = 0.0;
+    for (int i = 0; i < n_tasks; ++i) {
+      const double u = ((double)(mix64(seed * 0xA24BAED4963EE407ull + (uint64_t)i) >> 11) + 0.5) / 9007199254740992.0;
+      tcur += -std::log(u) / arrival_rate;
+      arrival[(size_t)i] = tcur;
+    }
+  }
+  std::vector<double> task_ms;   // arrival -> terminal phase of every ROOT Task
   const auto t0 = std::chrono::steady_clock::now();
+  // Runs one Task (root or delegated child) to a terminal phase on the calling worker: the Task controller's
+  // reconciles, with the (out of scope) ToolCall controller emulated in between — plain tools "execute" at once
+  // with a fixed result; a delegate_to_agent__X ToolCall creates the child Task like executeDelegateToAgent
+  // (toolcall/executor.go:176-242), the child runs to its end, and its Output becomes the ToolCall's Result
+  // (waitForSubAgent, toolcall/state_machine.go:218-267).
+  std::function<void(const std::string&, int, int)> run_task = [&](const std::string& name, int index, int level) {
+    int steps = 0;
+    for (int guard = 0; guard < 24; ++guard) {
+      Json tj;
+      if (!store.Get("Task", name, &tj)) return;  // r.getTask (task_controller.go:216)
+      task::Task t;
+      task::task_from_json(tj, &t);
+      const std::string& phase = t.Status.Phase;
+      llmclient::Context ctx;
+      std::string err;
+      if (phase.empty() || phase == "Initializing" || phase == "Pending") {
+        sm.Process(ctx, &t, mcp_by_server, engine, &err);   // initialize / validateAgent (delegated children start here)
+        if (!err.empty()) return;
+      } else if (phase == "ReadyForLLM") {
+        const auto s0 = std::chrono::steady_clock::now();
+        tl_script.clear();
+        if (provider == "local" && steps == 0) {
+          if (level < delegation_depth)
+            tl_script = "{\"name\": \"delegate_to_agent__sub-agent-" + std::to_string(level + 1) + "\", \"parameters\": {\"message\": \"" +
+                        synth_text(seed ^ 0xD1E6, index * 8 + level, 96) + "\"}}";
+          else if (tool_loop && !tools.empty() && level == 0)
+            tl_script = scripted_call;
+        }
+        sm.Process(ctx, &t, mcp_by_server, engine, &err);   // -> sendLLMRequest (a5, a6, CreateClient, a8, the LLM step)
+        tl_script.clear();
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count();
+        ++reconciles;
+        {
+          std::lock_guard<std::mutex> lk(lat_mu);
+          lat_ms.push_back(ms);
+        }
+        ++steps;
+        if (!err.empty()) return;  // would requeue after 5 s; out of the timed loop
+      } else if (phase == "ToolCallsPending") {
+        for (Json& tcj : store.ListToolCalls(name, t.Status.ToolCallRequestID)) {
+          task::ToolCall tc;
+          task::toolcall_from_json(tcj, &tc);
+          if (tc.ToolType == "DelegateToAgent") {
+            const std::string agentName = tc.ToolRef.substr(std::min(tc.ToolRef.size(), std::string("delegate_to_agent__").size()));
+            Json args;
+            std::string perr2;
+            if (!Json::parse(tc.Arguments, &args, &perr2) || !args.get("message").is_string()) {
+              tc.StatusStatus = "Error";
+              tc.StatusResult = "missing or invalid 'message' argument";
+            } else {
+              std::string child = "delegate-" + tc.Name + "-" + agentName;
+              if (child.size() > 63) child = child.substr(0, 55) + "-" + child.substr(child.size() - 7);
+              task::Task ct;
+              ct.Name = child;
+              ct.UID = "uid-" + child;
+              ct.AgentName = agentName;
+              ct.UserMessage = args.get("message").as_string();
+              ct.Labels["acp.humanlayer.dev/parent-toolcall"] = tc.Name;
+              store.Create("Task", child, task::task_to_json(ct));
+              run_task(child, index, level + 1);
+              Json cj;
+              task::Task done;
+              if (store.Get("Task", child, &cj)) task::task_from_json(cj, &done);
+              if (done.Status.Phase == "FinalAnswer") { tc.StatusStatus = "Succeeded"; tc.StatusResult = done.Status.Output; }
+              else { tc.StatusStatus = "Error"; tc.StatusResult = done.Status.Error.empty() ? "Sub-agent task failed" : done.Status.Error; }
+            }
+          } else {
+            tc.StatusStatus = "Succeeded";
+            tc.StatusResult = "{\"data\": \"" + synth_text(seed ^ 0x5151, index, 96) + "\"}";
+          }
+          store.Put("ToolCall", tc.Name, task::toolcall_to_json(tc));
+        }
+        sm.Process(ctx, &t, mcp_by_server, engine, &err);   // -> checkToolCalls
+      } else {
+        return;  // FinalAnswer / Failed
+      }
+    }
+  };
   auto worker = [&]() {
     while (true) {
       const int i = next.fetch_add(1);
       if (i >= n_tasks) break;
       const std::string name = "task-" + std::to_string(i);
-      int steps = 0;
-      while (steps < 8) {
-        Json tj;
-        if (!store.Get("Task", name, &tj)) break;  // r.getTask (task_controller.go:216)
-        task::Task t;
-        task::task_from_json(tj, &t);
-        if (t.Status.Phase == "ReadyForLLM") {
-          const auto s0 = std::chrono::steady_clock::now();
-          tl_scripted = provider == "local" && tool_loop && steps == 0 && !tools.empty();
-          llmclient::Context ctx;
-          std::string err;
-          sm.Process(ctx, &t, mcp_by_server, engine, &err);   // -> sendLLMRequest (a5, a6, CreateClient, a8, the LLM step)
-          tl_scripted = false;
-          const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count();
-          ++reconciles;
-          {
-            std::lock_guard<std::mutex> lk(lat_mu);
-            lat_ms.push_back(ms);
-          }
-          ++steps;
-          if (!err.empty()) break;  // would requeue after 5 s; out of the timed loop
-        } else if (t.Status.Phase == "ToolCallsPending") {
-          // the (out of scope) ToolCall controller "executes" instantly with a fixed result
-          for (Json& tcj : store.ListToolCalls(name, t.Status.ToolCallRequestID)) {
-            task::ToolCall tc;
-            task::toolcall_from_json(tcj, &tc);
-            tc.StatusStatus = "Succeeded";
-            tc.StatusResult = "{\"data\": \"" + synth_text(seed ^ 0x5151, i, 96) + "\"}";
-            store.Put("ToolCall", tc.Name, task::toolcall_to_json(tc));
-          }
-          llmclient::Context ctx;
-          std::string err;
-          sm.Process(ctx, &t, mcp_by_server, engine, &err);   // -> checkToolCalls
-        } else {
-          break;  // FinalAnswer / Failed
-        }
-      }
+      if (arrival_rate > 0.0)
+        std::this_thread::sleep_until(t0 + std::chrono::duration_cast<std::chrono::steady_clock::duration>(
+                                               std::chrono::duration<double>(arrival[(size_t)i])));
+      const auto a0 = std::chrono::steady_clock::now();
+      run_task(name, i, 0);
+      const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a0).count();
       Json tj;
       if (store.Get("Task", name, &tj)) {
         task::Task t;
         task::task_from_json(tj, &t);
         std::lock_guard<std::mutex> lk(lat_mu);
+        task_ms.push_back(total_ms);
         ++phases[t.Status.Phase];
         uint64_t h = 1469598103934665603ull;
         const std::string d = t.Status.Output + "|" + t.Status.Phase;
@@ -797,6 +884,11 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
   if (!lat_ms.empty()) {
     out.set("step_ms_p50", Json(lat_ms[lat_ms.size() / 2]));
     out.set("step_ms_p99", Json(lat_ms[std::min(lat_ms.size() - 1, (size_t)(lat_ms.size() * 0.99))]));
+  }
+  if (!task_ms.empty()) {
+    std::sort(task_ms.begin(), task_ms.end());
+    out.set("task_ms_p50", Json(task_ms[task_ms.size() / 2]));
+    out.set("task_ms_p99", Json(task_ms[std::min(task_ms.size() - 1, (size_t)(task_ms.size() * 0.99))]));
   }
   out.set("store_writes", Json(store.writes()));
   out.set("store_reads", Json(store.reads()));

@@ -59,6 +59,13 @@ WORKLOADS = {
     # (2 LLM steps per Task: scripted tool call -> ToolCall CR "executes" -> fold-back -> final answer)
     3: {"name": "llama-3-70b TP=8 provider:local, 256 concurrent Task CRs with tool-call loop, 512-token context, greedy, max_tokens 64",
         "model": "llama-3-70b", "tasks": 256, "prompt_tokens": 512, "max_tokens": 64, "tp": 8, "tools": 2, "tool_loop": True},
+    # BASELINE.json configs[4]: Mixtral-8x7B, experts spread over the 8 GPUs of ONE process (expert parallel on the
+    # tensor-parallel ranks), open-loop Poisson arrivals at 1024 Tasks/s, every root Task delegates down a depth-2
+    # sub-agent chain (5 LLM steps + 2 ToolCall CRs + 2 child Task CRs per root Task)
+    4: {"name": "mixtral-8x7b EP=8 provider:local, Poisson arrivals 1024 Tasks/s for 1 s (1024 root Tasks), depth-2 sub-agent "
+                "delegation chains, 512-token root windows, greedy, max_tokens 64",
+        "model": "mixtral-8x7b", "tasks": 1024, "prompt_tokens": 512, "max_tokens": 64, "tp": 8, "tools": 0, "tool_loop": False,
+        "arrival_rate": 1024.0, "delegation_depth": 2},
 }
 WORKLOAD = WORKLOADS[2]
 # DRAM bytes of ONE decode step from the committed `ncu --set full` captures (dram__bytes_read + write)
@@ -218,12 +225,12 @@ def main():
     ap.add_argument("--model", default=WORKLOAD["model"])
     ap.add_argument("--layers", type=int, default=0, help="dev only: truncate depth (result is then NOT a bench value)")
     ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS),
-                    help="BASELINE.json config index (2 = default; 1 = 64 x 512; 3 = 70B TP=8: run as ONE process on an 8-GPU box, --gpus 1)")
+                    help="BASELINE.json config index (2 = default; 1 = 64 x 512; 3 = 70B TP=8, 4 = Mixtral EP=8: ONE process on an 8-GPU box, --gpus 1)")
     ap.add_argument("--max-tokens-per-step", type=int, default=4096, help="engine knob: token rows per prefill step (4096 measured 1.3 %% faster than 8192)")
     ap.add_argument("--tp", type=int, default=0, help="dev only: override the tensor-parallel degree of --config 3")
     args = ap.parse_args()
     WORKLOAD = dict(WORKLOADS[args.config])
-    if args.config == 3:
+    if args.config in (3, 4):
         if args.model == WORKLOADS[1]["model"]:
             args.model = WORKLOAD["model"]
         else:
@@ -268,7 +275,7 @@ def main():
             WORKLOAD["name"] += f" [windows are {probe} tokens: tool schemas under the byte-level synthetic tokenizer]"
             plen = probe
     pages_per_seq = (plen + max_new) // 32 + 2
-    if WORKLOAD["tool_loop"]:
+    if WORKLOAD["tool_loop"] or WORKLOAD.get("delegation_depth"):
         pages_per_seq += 12   # second LLM step: window + tool call + tool result
     kv_pages = n_tasks * pages_per_seq * 2 + 8
     if dry is not None:   # mixed windows: size the KV pool from the dry run
@@ -278,13 +285,16 @@ def main():
             "kv_pages": kv_pages, "max_pages_per_seq": max(32, pages_per_seq), "tp": WORKLOAD["tp"],
             # config 1 measures cold Task steps: KV retention stays off so that no prefill work is skipped;
             # the tool loop of config 3 is exactly the case retention exists for (second turn of a Task)
-            "prefix_cache": bool(WORKLOAD["tool_loop"])}
+            "prefix_cache": bool(WORKLOAD["tool_loop"] or WORKLOAD.get("delegation_depth"))}
     if args.layers:
         ecfg["layers"] = args.layers
     eng = Engine(ecfg)
     sim = {"tasks": n_tasks, "workers": n_tasks, "provider": "local", "model": args.model, "max_tokens": max_new,
            "tools": WORKLOAD["tools"], "tool_loop": WORKLOAD["tool_loop"],
            **(window_cfg(WORKLOAD) if WORKLOAD.get("prompt_min") else {"prompt_tokens": plen})}
+    for key in ("arrival_rate", "delegation_depth"):
+        if WORKLOAD.get(key):
+            sim[key] = WORKLOAD[key]
 
     def barrier():
         torch.cuda.synchronize(local_rank)
@@ -299,11 +309,13 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     t0 = time.perf_counter()
-    reconciles, p50s, phases = 0, [], {}
+    reconciles, p50s, phases, task_p50, task_p99 = 0, [], {}, [], []
     for i in range(args.steps):
         r = host.hostsim_run(dict(sim, seed=i + 1), eng)
         reconciles += r["reconciles"]
         p50s.append(r["step_ms_p50"])
+        task_p50.append(r.get("task_ms_p50"))
+        task_p99.append(r.get("task_ms_p99"))
         for k, v in r["final_phases"].items():
             phases[k] = phases.get(k, 0) + v
     barrier()
@@ -401,6 +413,8 @@ def main():
             "p50_decode_step_ms": s1.get("decode_step_ms_p50"),
             "p99_decode_step_ms": s1.get("decode_step_ms_p99"),
             "p50_reconcile_ms": sorted(p50s)[len(p50s) // 2],
+            "task_ms_p50": sorted(task_p50)[len(task_p50) // 2] if task_p50 and task_p50[0] is not None else None,
+            "task_ms_p99": max(task_p99) if task_p99 and task_p99[0] is not None else None,
             "e2e": {"value": total_reconciles / wall_max, "unit": "reconciles/s",
                     "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) / args.steps,
                     "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) / args.steps,
@@ -429,7 +443,7 @@ def main():
             line["config1"] = config1
         if tp8 is not None:
             line["tp8_70b"] = tp8
-        if world == 1 and args.config != 3:
+        if world == 1 and args.config not in (3, 4):
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
     if eng is not None:

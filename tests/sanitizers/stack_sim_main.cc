@@ -61,6 +61,28 @@ int main() {
     if (s.get("kv_pages_free").as_int() + s.get("prefix_cache_pages").as_int() != s.get("kv_pages_total").as_int()) { fprintf(stderr, "page leak\n"); ++bad; }
     hits_before = hits;
   }
+  // BASELINE config 4's shape: open-loop Poisson arrivals and sub-agent delegation chains of depth 2 —
+  // root Task: delegate tool call -> child Task (sub-agent-1): delegate -> grandchild (sub-agent-2): answer ->
+  // results fold back up: 5 LLM steps and 2 ToolCall CRs per root Task, every child created like
+  // executeDelegateToAgent does (toolcall/executor.go:176-242)
+  {
+    const std::string cfg = "{\"tasks\": 40, \"workers\": 40, \"provider\": \"local\", \"model\": \"sim\", \"max_tokens\": 24, "
+                            "\"prompt_tokens\": 256, \"seed\": 9, \"arrival_rate\": 400.0, \"delegation_depth\": 2}";
+    char* out = nullptr;
+    if (acp_hostsim_run(e, cfg.c_str(), &out) != 0 || !out) { fprintf(stderr, "hostsim (delegation) failed\n"); return 1; }
+    Json r;
+    std::string err;
+    Json::parse(std::string(out), &r, &err);
+    acp_infer_free(out);
+    const long long fa = r.get("final_phases").get("FinalAnswer").as_int(0), failed = r.get("final_phases").get("Failed").as_int(0);
+    printf("delegation: reconciles=%lld FinalAnswer=%lld Failed=%lld task_ms_p50=%.2f wall=%.3f\n", (long long)r.get("reconciles").as_int(), fa, failed,
+           r.get("task_ms_p50").as_double(), r.get("wall_s").as_double());
+    if (fa + failed != 40) { fprintf(stderr, "root tasks lost\n"); ++bad; }
+    // a chain that completes takes 5 LLM steps; an empty completion (1 in 23 per step) ends its Task as Failed earlier
+    if (r.get("reconciles").as_int() < 3 * fa || r.get("reconciles").as_int() > 5 * 40) { fprintf(stderr, "unexpected LLM step count\n"); ++bad; }
+    if (fa < 20) { fprintf(stderr, "too few delegation chains completed\n"); ++bad; }
+    if (r.get("wall_s").as_double() < 40 / 400.0 * 0.5) { fprintf(stderr, "arrivals were not spread out\n"); ++bad; }
+  }
   acp_infer_shutdown(e);
   return bad ? 1 : 0;
 }
