@@ -398,10 +398,7 @@ int Model::build_rope_tables() {
 // placed by gather_weight_kernel through the SAME SynthMap the synthetic generator uses.
 int Model::load_weights(const Checkpoint& ck) {
   const ModelConfig& c = cfg_;
-  if (c.experts > 0) {
-    fprintf(stderr, "[acp_infer] mixture-of-experts checkpoints are not loadable yet (synthetic weights only)\n");
-    return -1;
-  }
+
   const size_t H = c.hidden;
   const int r = tp_rank_;
   size_t stage_elems = (size_t)c.qkv_dim() * H;
@@ -474,6 +471,29 @@ int Model::load_weights(const Checkpoint& ck) {
       if ((rc = upload(whole(pre + "self_attn.o_proj.weight", H, c.q_dim()), stage)) != 0) break;
       if ((rc = launch_gather_weight(L.wo, H * qdim_l_, stage, 0, stream_, tiled(qdim_l_, c.q_dim(), r * qdim_l_))) != 0) break;
       ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      if (c.experts > 0) {
+        // Mixtral (hub layout): block_sparse_moe.gate.weight [E][H]; experts.<e>.w1 = gate, w3 = up ([ffn][H]), w2 = down ([H][ffn])
+        const std::string moe = pre + "block_sparse_moe.";
+        if ((rc = upload(whole(moe + "gate.weight", c.experts, H), L.router)) != 0) break;
+        for (int j = 0; j < experts_l_ && rc == 0; ++j) {
+          const std::string ex = moe + "experts." + std::to_string(expert0_ + j) + ".";
+          if ((rc = upload(whole(ex + "w1.weight", c.ffn, H), stage)) != 0) break;
+          if ((rc = upload(whole(ex + "w3.weight", c.ffn, H), stage + (size_t)c.ffn * H)) != 0) break;
+          SynthMap m = tiled((int)H, (int)H, 0);
+          m.interleave_half = c.ffn;
+          m.seg_global[0] = 0;
+          m.seg_global[1] = c.ffn;
+          if ((rc = launch_gather_weight(L.wgu_e + (size_t)j * 2 * c.ffn * H, (size_t)2 * c.ffn * H, stage, 0, stream_, m)) != 0) break;
+          ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+          if ((rc = upload(whole(ex + "w2.weight", H, c.ffn), stage)) != 0) break;
+          if ((rc = launch_gather_weight(L.wdown_e + (size_t)j * H * c.ffn, H * c.ffn, stage, 0, stream_, tiled(c.ffn, c.ffn, 0))) != 0) break;
+          ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        }
+        if (rc != 0) break;
+        if ((rc = upload(whole(pre + "input_layernorm.weight", H, 1), L.attn_norm)) != 0) break;
+        if ((rc = upload(whole(pre + "post_attention_layernorm.weight", H, 1), L.ffn_norm)) != 0) break;
+        continue;
+      }
       {  // logical [gate; up], stored interleaved (2j = gate_j, 2j+1 = up_j)
         if ((rc = upload(whole(pre + "mlp.gate_proj.weight", c.ffn, H), stage)) != 0) break;
         if ((rc = upload(whole(pre + "mlp.up_proj.weight", c.ffn, H), stage + (size_t)c.ffn * H)) != 0) break;

@@ -22,6 +22,9 @@ def hf_config(cfg: LlamaConfig, **extra) -> dict:
          "intermediate_size": cfg.ffn, "vocab_size": cfg.vocab, "rope_theta": cfg.rope_theta,
          "rms_norm_eps": cfg.eps, "max_position_embeddings": 8192, "hidden_act": "silu",
          "tie_word_embeddings": False, "torch_dtype": "bfloat16", "attention_bias": False, "mlp_bias": False}
+    if cfg.experts:
+        c.update({"architectures": ["MixtralForCausalLM"], "model_type": "mixtral", "num_local_experts": cfg.experts,
+                  "num_experts_per_tok": 2, "sliding_window": None})
     c.update(extra)
     return c
 
@@ -33,14 +36,23 @@ def tensors_from_oracle(cfg: LlamaConfig, seed: int, dtype=torch.bfloat16) -> di
     q, kv = cfg.q_dim, cfg.kv_dim
     for l in range(cfg.layers):
         p = f"model.layers.{l}."
-        qkv, gu = w.wqkv(l), w.wgu(l)
+        qkv = w.wqkv(l)
+        gu = None if cfg.experts else w.wgu(l)
         t[p + "self_attn.q_proj.weight"] = _bf16(qkv[:q])
         t[p + "self_attn.k_proj.weight"] = _bf16(qkv[q:q + kv])
         t[p + "self_attn.v_proj.weight"] = _bf16(qkv[q + kv:])
         t[p + "self_attn.o_proj.weight"] = _bf16(w.wo(l))
-        t[p + "mlp.gate_proj.weight"] = _bf16(gu[:cfg.ffn])
-        t[p + "mlp.up_proj.weight"] = _bf16(gu[cfg.ffn:])
-        t[p + "mlp.down_proj.weight"] = _bf16(w.wdown(l))
+        if cfg.experts:   # hub layout of Mixtral-8x7B: block_sparse_moe.gate + experts.<e>.{w1 = gate, w3 = up, w2 = down}
+            t[p + "block_sparse_moe.gate.weight"] = _bf16(w.router(l))
+            for e in range(cfg.experts):
+                egu = w.expert_gu(l, e)
+                t[p + f"block_sparse_moe.experts.{e}.w1.weight"] = _bf16(egu[:cfg.ffn])
+                t[p + f"block_sparse_moe.experts.{e}.w3.weight"] = _bf16(egu[cfg.ffn:])
+                t[p + f"block_sparse_moe.experts.{e}.w2.weight"] = _bf16(w.expert_down(l, e))
+        else:
+            t[p + "mlp.gate_proj.weight"] = _bf16(gu[:cfg.ffn])
+            t[p + "mlp.up_proj.weight"] = _bf16(gu[cfg.ffn:])
+            t[p + "mlp.down_proj.weight"] = _bf16(w.wdown(l))
         t[p + "input_layernorm.weight"] = _bf16(w.attn_norm(l))
         t[p + "post_attention_layernorm.weight"] = _bf16(w.ffn_norm(l))
     if dtype != torch.bfloat16:

@@ -146,3 +146,19 @@ def test_llama31_rope_scaling_checkpoint_matches_oracle(tmp_path):
         if g != w:
             assert margins[i] < 0.06, (got, want, margins)
             break
+
+
+def test_mixtral_checkpoint_equals_synthetic_weights(tmp_path, prompts):
+    """A Mixtral-format checkpoint (model_type mixtral; block_sparse_moe.gate + experts.<e>.{w1, w3, w2}, the hub
+    layout of Mixtral-8x7B) loads into the router / grouped expert tensors and gives exactly the synthetic path's
+    tokens and logits."""
+    with Engine(dict(BASE, model="tiny-moe")) as e:
+        want = _gen(e, "tiny-moe", prompts, 6)
+    d = str(tmp_path / "tiny-moe-ckpt")
+    write_checkpoint(d, PRESETS["tiny-moe"], SEED, shards=2)
+    idx = __import__("agentcontrolplane_b200.host", fromlist=["host"]).checkpoint_index(d)
+    assert idx["config"]["model_type"] == "mixtral" and idx["model"]["layers"] == 2
+    with Engine(dict(BASE, weights=d)) as e:
+        got = _gen(e, "tiny-moe-ckpt", prompts, 6)
+    for (a, la), (b, lb) in zip(got, want):
+        assert a == b and np.array_equal(la, lb)
