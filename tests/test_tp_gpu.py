@@ -68,3 +68,29 @@ def test_tp_matches_tp1_and_oracle(tp, comm):
             if x != w or y != w:
                 assert margins[i] < 0.06, (tp, len(p), a, b, want, margins)   # near-tie policy
                 break
+
+
+@pytest.mark.parametrize("tp,comm", [(2, "p2p"), (2, "nccl"), (4, "p2p"), (8, "p2p")])
+def test_expert_parallel_matches_single_gpu_and_oracle(tp, comm):
+    """Mixtral-style MoE with the experts spread over the tensor-parallel ranks (tp = 2: four experts per GPU;
+    tp = 8: one expert per GPU, BASELINE config 4's layout): the weighted combine runs as the row-parallel
+    exchange, one rounding after it, so tokens equal the single-GPU engine's and the oracle's."""
+    if _ngpu() < tp:
+        pytest.skip(f"needs {tp} GPUs")
+    model = "tiny-moe"
+    cfg = PRESETS[model]
+    rng = np.random.default_rng(100 + tp)
+    prompts = [[128000] + [int(t) for t in rng.integers(0, 256, size=n - 1)] for n in (4, 33, 120, 290)]
+    n_new = 5
+    base = {"model": model, "max_batch": 16, "kv_pages": 256, "max_tokens_per_step": 1024}
+    with Engine(dict(base, tp=tp, tp_comm=comm)) as e:
+        got_tp = _gen(e, model, prompts, n_new)
+        assert e.stats()["tp"] == tp
+    with Engine(base) as e:
+        got_1 = _gen(e, model, prompts, n_new)
+    for p, a, b in zip(prompts, got_tp, got_1):
+        want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(p, n_new, eos=(128001, 128008, 128009))
+        for i, (x, y, w) in enumerate(zip(a, b, want)):
+            if x != w or y != w:
+                assert margins[i] < 0.06, (tp, len(p), a, b, want, margins)
+                break
