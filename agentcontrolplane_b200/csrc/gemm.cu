@@ -114,7 +114,8 @@ static int launch_one(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t s
   a.M = g.M; a.N = g.N; a.K = g.K; a.splits = g.splits; a.ld = g.ld; a.n_cap = g.n_cap;
   a.out = g.out; a.amax_val = g.amax_val; a.amax_idx = g.amax_idx; a.n_dev = g.n_dev;
   a.group_ranges = g.groups > 0 ? g.group_ranges : nullptr;
-  dim3 grid((g.N + BN - 1) / BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.groups > 0 ? g.groups : g.splits);
+  // grouped: g.N = the tile-list capacity in ROWS (moe_tile_cap * BN), grid.x walks the flat tile list
+  dim3 grid((g.N + BN - 1) / BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.groups > 0 ? 1 : g.splits);
   cudaError_t e;
   constexpr int kShallow = GemmCfg<BN>::kShallowStages;
   if (kShallow != GemmCfg<BN>::kStages && shallow_enabled())

@@ -37,8 +37,9 @@ struct GemmLaunch {
   const int* n_dev = nullptr;
   int bn_override = 0;  // 0 = pick from N
   // grouped mode (mixture of experts): `groups` weight tensors of M rows each, concatenated in `w`;
-  // group g works on rows [ranges[2g], ranges[2g] + ranges[2g+1]) of x / out (device array).  N = the
-  // largest row count any group can have (grid sizing; CTAs past a group's rows exit at once).
+  // group g works on rows [ranges[2g], ranges[2g] + ranges[2g+1]) of x / out (device array, layout of
+  // moe_dispatch_kernel incl. its flat tile list).  bn_override = the tile height the list was built for,
+  // N = tile capacity * bn_override (grid.x = capacity).
   int groups = 0;
   const int* group_ranges = nullptr;
 };

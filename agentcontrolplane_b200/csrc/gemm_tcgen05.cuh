@@ -51,9 +51,11 @@ struct GemmArgs {
   float* amax_val;   // EPI_ARGMAX: [N][m_tiles]
   int* amax_idx;     // EPI_ARGMAX: [N][m_tiles]
   const int* n_dev;  // optional device scalar overriding N (CUDA-graph replay with varying batch)
-  // GROUPED mode (mixture of experts): blockIdx.z = group g, its weights are m-tiles [g*gridDim.y, (g+1)*gridDim.y)
-  // of the (concatenated) weight tensor, its activation / output rows are [ranges[2g], ranges[2g] + ranges[2g+1])
-  // — written on the device by the dispatch kernel, so the row counts never visit the host.  splits must be 1.
+  // GROUPED mode (mixture of experts): group g's weights are m-tiles [g*gridDim.y, (g+1)*gridDim.y) of the
+  // (concatenated) weight tensor, its activation / output rows are [ranges[2g], ranges[2g] + ranges[2g+1]).
+  // blockIdx.x indexes a flat tile list {group, first row inside the group} at ranges[32 + 2 ...] (count at
+  // ranges[32]) — all written on the device by moe_dispatch_kernel, so row counts never visit the host and
+  // no CTA is launched for rows that do not exist (beyond the <= E slack of the grid bound).  splits must be 1.
   const int* group_ranges;
 };
 
@@ -112,7 +114,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   const int lane = threadIdx.x & 31;
   // blockIdx.x = n-tile (fastest): the CTAs that run together share ONE weight tile and sweep the
   // activation rows, so W streams from HBM once and X (<= 67 MB at 8192 x 4096) is served by L2.
-  const int n0 = blockIdx.x * BN;
+  int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * GEMM_BM;
   const int m_tiles = gridDim.y;
   const bool grouped = args.group_ranges != nullptr;
@@ -122,10 +124,12 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   pdl_launch_dependents();
   if (grouped) {
     pdl_wait();                        // the ranges come from the previous kernel (moe_dispatch)
-    row_off = args.group_ranges[2 * blockIdx.z];
-    group_rows = args.group_ranges[2 * blockIdx.z + 1];
-    if (n0 >= group_rows) return;      // whole CTA, before any barrier / TMEM allocation
-    m_tile = (int)blockIdx.z * m_tiles + (int)blockIdx.y;
+    if ((int)blockIdx.x >= args.group_ranges[32]) return;   // whole CTA, before any barrier / TMEM allocation
+    const int group = args.group_ranges[34 + 2 * blockIdx.x];
+    n0 = args.group_ranges[34 + 2 * blockIdx.x + 1];
+    row_off = args.group_ranges[2 * group];
+    group_rows = args.group_ranges[2 * group + 1];
+    m_tile = group * m_tiles + (int)blockIdx.y;
     split = 0;
   }
   const int nkb_total = (args.K + GEMM_BK - 1) / GEMM_BK;

@@ -264,7 +264,7 @@ int Model::alloc_all() {
     ACP_TRY(dmalloc_t(allocs_, &moe_topk_idx_, (size_t)2 * T));
     ACP_TRY(dmalloc_t(allocs_, &moe_topk_w_, (size_t)2 * T));
     ACP_TRY(dmalloc_t(allocs_, &moe_row_of_, (size_t)2 * T));
-    ACP_TRY(dmalloc_t(allocs_, &moe_ranges_, (size_t)2 * 16));
+    ACP_TRY(dmalloc_t(allocs_, &moe_ranges_, (size_t)moe_ranges_ints(T), true));
   }
   ACP_TRY(dmalloc_t(allocs_, &xs_, (size_t)Bp * H, true));
   int max_m = qkv_l_;
@@ -813,11 +813,14 @@ int Model::forward(const StepInput& in) {
 int Model::moe_mlp(Layer& L, int T, const __nv_bfloat16* gain, bool last_layer) {
   const ModelConfig& c = cfg_;
   PROF("moe_router", launch_moe_router(xn_, L.router, c.hidden, c.experts, T, moe_topk_idx_, moe_topk_w_, stream_));
-  PROF("moe_dispatch", launch_moe_dispatch(moe_topk_idx_, T, expert0_, experts_l_, moe_ranges_, moe_row_of_, stream_));
+  // N tile of the expert GEMMs: an expert sees about 2T / E rows (a token picks an expert at most once)
+  const int bn = gemm_pick_bn((2 * T + c.experts - 1) / c.experts);
+  PROF("moe_dispatch", launch_moe_dispatch(moe_topk_idx_, T, expert0_, experts_l_, bn, moe_ranges_, moe_row_of_, stream_));
   PROF("moe_gather", launch_moe_gather(xn_, moe_row_of_, c.hidden, T, xe_, stream_));
   GemmLaunch g;
   g.groups = experts_l_; g.group_ranges = moe_ranges_; g.splits = 1;
-  g.N = T;   // a token picks an expert at most once: no group has more than T rows
+  g.bn_override = bn;
+  g.N = moe_tile_cap(T, bn, experts_l_) * bn;   // grid.x = capacity of the device-side tile list
   g.w = &L.m_gu_e.w; g.x = &m_xe_; g.M = 2 * c.ffn; g.K = c.hidden; g.epi = EPI_SWIGLU; g.out = he_; g.ld = c.ffn; g.n_cap = T;
   PROF("gemm_experts_gateup_swiglu", gemm_launch(g, stream_));
   g.w = &L.m_down_e.w; g.x = &m_he_; g.M = c.hidden; g.K = c.ffn; g.epi = EPI_BF16; g.out = ye_; g.ld = c.hidden;

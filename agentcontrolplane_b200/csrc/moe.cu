@@ -66,7 +66,7 @@ moe_router_kernel(const __nv_bfloat16* __restrict__ xn, const __nv_bfloat16* __r
 // One CTA of 1024 threads; thread i owns tokens [i*per, (i+1)*per).  Experts e_first .. e_first+e_local-1
 // live on this rank (expert parallel); assignments to other experts get row -1.
 __global__ void __launch_bounds__(1024)
-moe_dispatch_kernel(const int* __restrict__ topk_idx, int T, int e_first, int e_local, int* __restrict__ ranges,
+moe_dispatch_kernel(const int* __restrict__ topk_idx, int T, int e_first, int e_local, int bn, int* __restrict__ ranges,
                     int* __restrict__ row_of) {
   pdl_launch_dependents();
   pdl_wait();
@@ -116,6 +116,13 @@ moe_dispatch_kernel(const int* __restrict__ topk_idx, int T, int e_first, int e_
       off += s_cnt[e][1024];
     }
     s_off[e_local] = off;
+    // flat work list of the grouped GEMMs: one entry {expert, first row inside the expert} per BN-row tile,
+    // ranges[2*MOE_MAX_E] = number of entries, entries from ranges[2*MOE_MAX_E + 2] on
+    int n = 0;
+    int* tiles = ranges + 2 * MOE_MAX_E + 2;
+    for (int e = 0; e < e_local; ++e)
+      for (int n0 = 0; n0 < (int)s_cnt[e][1024]; n0 += bn) { tiles[2 * n] = e; tiles[2 * n + 1] = n0; ++n; }
+    ranges[2 * MOE_MAX_E] = n;
   }
   __syncthreads();
   int pos[MOE_MAX_E];
@@ -199,12 +206,14 @@ int launch_moe_router(const __nv_bfloat16* xn, const __nv_bfloat16* wr, int hidd
   MOE_LAUNCH("moe_router", acp_launch(moe_router_kernel, dim3((T + 3) / 4), dim3(128), 0, s, xn, wr, hidden, E, T, topk_idx, topk_w));
   return 0;
 }
-int launch_moe_dispatch(const int* topk_idx, int T, int e_first, int e_local, int* ranges, int* row_of, cudaStream_t s) {
+int launch_moe_dispatch(const int* topk_idx, int T, int e_first, int e_local, int bn, int* ranges, int* row_of, cudaStream_t s) {
   if (T <= 0) return 0;
-  if (e_local < 1 || e_local > MOE_MAX_E || 2 * T > 65535) return -1;
-  MOE_LAUNCH("moe_dispatch", acp_launch(moe_dispatch_kernel, dim3(1), dim3(1024), 0, s, topk_idx, T, e_first, e_local, ranges, row_of));
+  if (e_local < 1 || e_local > MOE_MAX_E || 2 * T > 65535 || bn < 16) return -1;
+  MOE_LAUNCH("moe_dispatch", acp_launch(moe_dispatch_kernel, dim3(1), dim3(1024), 0, s, topk_idx, T, e_first, e_local, bn, ranges, row_of));
   return 0;
 }
+int moe_ranges_ints(int T) { return 2 * MOE_MAX_E + 2 + 2 * (2 * T / 16 + MOE_MAX_E + 1); }
+int moe_tile_cap(int T, int bn, int e_local) { return (2 * T + bn - 1) / bn + e_local; }
 int launch_moe_gather(const __nv_bfloat16* xn, const int* row_of, int hidden, int T, __nv_bfloat16* xe, cudaStream_t s) {
   if (T <= 0) return 0;
   MOE_LAUNCH("moe_gather", acp_launch(moe_gather_kernel, dim3(T), dim3(128), 0, s, xn, row_of, hidden, xe));
