@@ -382,17 +382,16 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     fence_mbar_init();
   }
   __syncthreads();
+  // (Starting the K/V stream BEFORE the grid-dependency wait — legal, the cached keys predate the step — was
+  // measured in round 2 and lost: 4.157 vs 4.128 ms per config-1 decode step, 9.44 vs 9.21 ms at B = 256; the
+  // early loads compete with the QKV GEMM's weight stream instead of hiding under its tail.)
+  pdl_wait();  // the QKV planes of the new token come from the previous kernel
   if (warp == CONSUMER_WARPS) {
-    // The cached keys 0..ctx-2 were written by EARLIER steps (the new token's K/V never leaves shared
-    // memory here) and the step descriptors by the memcpy that opens the step, so the producer does
-    // not wait for the previous kernel (the QKV GEMM): the K/V stream ramps up under that kernel's
-    // tail, like the GEMM's weight prefetch.
     if (lane == 0)
       produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
                     a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, tile_begin, tile_end, tok_end);
     return;
   }
-  pdl_wait();  // the QKV planes of the new token come from the previous kernel
   const float sl2e = a.scale * 1.4426950408889634f;
   const int r_lo = lane >> 2;
   const int tok_off = warp * 16;
@@ -496,13 +495,13 @@ attn_decode_item_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
   if (warp == CONSUMER_WARPS) {
-    if (lane == 0)   // no grid-dependency wait: cached K/V and descriptors predate this step's kernels (see attn_decode_kernel)
+    if (lane == 0)
       produce_tiles(&tm_k, &tm_v, L.stages, L.full_bar, L.empty_bar,
                     a.page_table + (size_t)b * a.max_pages, kh, a.kv_heads, 0, n_tiles, cached);
     return;
   }
-  pdl_wait();
   const int r_lo = lane >> 2;
   new_token_prologue(a, L, b, kh, ctx, true);
   uint32_t qf[8][4];

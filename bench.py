@@ -277,6 +277,8 @@ def main():
     pages_per_seq = (plen + max_new) // 32 + 2
     if WORKLOAD["tool_loop"] or WORKLOAD.get("delegation_depth"):
         pages_per_seq += 12   # second LLM step: window + tool call + tool result
+    if WORKLOAD.get("delegation_depth"):
+        pages_per_seq += 16   # the delegate tool's schema in the window + the scripted delegate call (byte-level tokenizer)
     kv_pages = n_tasks * pages_per_seq * 2 + 8
     if dry is not None:   # mixed windows: size the KV pool from the dry run
         pages_per_seq = (dry["prompt_tokens_max"] + max_new) // 32 + 2

@@ -305,6 +305,11 @@ class LlamaOracle:
                 act = self._r(g / (np.float32(1.0) + np.exp(-g)))
                 dst[rows] = self._r(self._r(act * u) @ self.w.expert_down(l, e).T)
         self.last_routing = (e0, e1, w0, w1)
+        # closest call of the discrete routing so far: gap between the 2nd and 3rd largest router logit.  bf16
+        # rounding noise UPSTREAM of the router (the engine and the oracle agree on the router arithmetic bit for
+        # bit, not on every bit of its input) can flip the second expert when this gap is inside that noise.
+        r3 = np.partition(r, -3, axis=1)
+        self.min_router_gap = min(getattr(self, "min_router_gap", np.inf), float(np.min(r3[:, -2] - r3[:, -3])))
         return self._r((w0[:, None] * out0).astype(np.float32) + (w1[:, None] * out1).astype(np.float32))
 
     def greedy(self, prompt, max_new: int, eos=(), force=None):

@@ -134,7 +134,7 @@ def test_many_concurrent_reconciles_form_one_batch(eng):
     assert s["decode_steps"] < 64 * 7                      # batched: far fewer steps than serial
     ser = host.hostsim_run(dict(cfg, workers=1), eng)
     assert ser["digest"] == par["digest"]
-    assert par["store_writes"] == 64 * 4 + 64                # 4 writes per step + initial create
+    assert par["store_writes"] == 64 * 4 + 64 + 2            # 4 writes per step + initial create + the Agent and LLM objects
 
 
 def test_tool_loop_two_llm_steps(eng):

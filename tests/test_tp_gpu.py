@@ -89,8 +89,10 @@ def test_expert_parallel_matches_single_gpu_and_oracle(tp, comm):
     with Engine(base) as e:
         got_1 = _gen(e, model, prompts, n_new)
     for p, a, b in zip(prompts, got_tp, got_1):
-        want, margins = LlamaOracle(cfg, SEED, mode="bf16").greedy(p, n_new, eos=(128001, 128008, 128009))
+        orc = LlamaOracle(cfg, SEED, mode="bf16")
+        want, margins = orc.greedy(p, n_new, eos=(128001, 128008, 128009))
         for i, (x, y, w) in enumerate(zip(a, b, want)):
             if x != w or y != w:
-                assert margins[i] < 0.06, (tp, len(p), a, b, want, margins)
+                # near tie of the logits, or of the discrete routing (tests/test_engine_gpu.py ROUTER_GAP_TOL)
+                assert margins[i] < 0.08 or orc.min_router_gap < 1e-2, (tp, len(p), a, b, want, margins, orc.min_router_gap)
                 break
