@@ -126,7 +126,7 @@ static int dmalloc_t(std::vector<void*>& allocs, T** p, size_t count, bool zero 
 //   see gemm()) — the batch-invariance the tests check.
 //   N > 256 rows (BASELINE config 2, B = 512): the GEMMs are tensor-bound and 5-7 fp32 planes of
 //   512 rows cost more than the MMAs (r1: QKV 0.5, O 0.4 PFLOP/s); there the split only has to give
-//   every SM a tile: the smallest S with m_tiles * n_tiles * S >= 148.  Still a fixed function of
+//   every SM the same share: S minimises ceil(tiles * S / 148) / S.  Still a fixed function of
 //   (M, K, number of N tiles) — deterministic run to run — but a sequence decoded inside a batch of
 //   more than 256 sums its K range in different pieces than inside a smaller batch
 //   ("strict_batch_invariance": true keeps the one-tile splits everywhere).
@@ -136,8 +136,15 @@ int Model::choose_splits(int M, int K, int N) const {
   const int max_s = nkb / 4 > 0 ? nkb / 4 : 1;  // at least 4 k-blocks per split
   int s;
   if (N > 256 && !lim_.strict_batch_invariance) {
+    // co-resident CTAs share an SM's tensor pipe, so the GEMM's time follows the busiest SM: minimise
+    // ceil(tiles * S / 148) / S (waves of one CTA per SM, each doing 1/S of K); ties -> fewer planes
     const int tiles = m_tiles * ((N + 255) / 256);
-    s = (148 + tiles - 1) / tiles;
+    s = 1;
+    double best = 1e30;
+    for (int cand = 1; cand <= (max_s < 8 ? max_s : 8); ++cand) {
+      const double cost = (double)((tiles * cand + 147) / 148) / cand;
+      if (cost < best - 1e-9) { best = cost; s = cand; }
+    }
   } else {
     s = (lim_.splitk_target_ctas + m_tiles / 2) / m_tiles;
   }

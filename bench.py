@@ -69,9 +69,11 @@ WORKLOADS = {
 }
 WORKLOAD = WORKLOADS[2]
 # DRAM bytes of ONE decode step from the committed `ncu --set full` captures (dram__bytes_read + write)
-NCU_TRAFFIC = {1: 20.00e9}
+NCU_TRAFFIC = {1: 20.00e9, 2: 107.4e9}
 NCU_TRAFFIC_SOURCE = {1: "profiles/r1_v3_ncu_full_decode_kernels.md: 32 x (QKV 51.2 + attention 146.0 + O 34.1 "
-                         "+ gate/up 238.4 + down 122.3 MB) + LM head 1054.4 MB, ctx 515"}
+                         "+ gate/up 238.4 + down 122.3 MB) + LM head 1054.4 MB, ctx 515",
+                      2: "profiles/r2_config2_decode_ncu.md: 32 x 3321.8 MB (attention 2668.3 + merge 59.9 + gate/up 256.0 + O/down 193.2 "
+                         "+ QKV 56.2 + add_rmsnorm 58.8 + swiglu 29.4) + LM head 1.06 GB, B = 512"}
 
 
 def measured_peaks():
