@@ -141,7 +141,8 @@ int Model::choose_splits(int M, int K, int N) const {
     const int tiles = m_tiles * ((N + 255) / 256);
     s = 1;
     double best = 1e30;
-    for (int cand = 1; cand <= (max_s < 8 ? max_s : 8); ++cand) {
+    // (>= one tile per SM already: no split — the persistent kernel balances those itself, bf16 epilogue)
+    for (int cand = 1; tiles < 148 && cand <= (max_s < 8 ? max_s : 8); ++cand) {
       const double cost = (double)((tiles * cand + 147) / 148) / cand;
       if (cost < best - 1e-9) { best = cost; s = cand; }
     }
