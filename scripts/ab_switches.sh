@@ -1,7 +1,6 @@
 #!/usr/bin/env bash
-# Round 2, first GPU call: (1) the new parity tests at BASELINE shapes on the default kernels,
-# (2) validate-or-delete A/B of the four experimental switches left by round 1 (parity first, then
-# timing, all on ONE box so the numbers share a chip).  Output: gpurun_out/ab_switches.log
+# Round 2, GPU call 1 (HISTORICAL: the four switches it A/B-ed were measured with it and then REMOVED from the
+# tree — profiles/r2_ab_switches.md; the env vars below are no-ops now).  Kept as the provenance of those numbers.
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
