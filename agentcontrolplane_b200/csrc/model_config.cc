@@ -16,7 +16,7 @@ bool model_preset(const std::string& name, ModelConfig* c) {
   else if (name == "llama-3-8b") { m.hidden = 4096; m.layers = 32; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; }
   // Mixtral-8x7B architecture (BASELINE config 4).  Synthetic presets keep the 128256-entry vocabulary of
   // the synthetic tokenizer; a real checkpoint brings its own 32000 entries + tokenizer.json.
-  else if (name == "tiny-moe") { m.hidden = 512; m.layers = 2; m.heads = 4; m.kv_heads = 1; m.ffn = 768; m.experts = 8; m.rope_theta = 1000000.0; }
+  else if (name == "tiny-moe") { m.hidden = 512; m.layers = 2; m.heads = 4; m.kv_heads = 2; m.ffn = 768; m.experts = 8; m.rope_theta = 1000000.0; }
   else if (name == "mixtral-8x7b-l2") { m.hidden = 4096; m.layers = 2; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; m.experts = 8; m.rope_theta = 1000000.0; }
   else if (name == "mixtral-8x7b") { m.hidden = 4096; m.layers = 32; m.heads = 32; m.kv_heads = 8; m.ffn = 14336; m.experts = 8; m.rope_theta = 1000000.0; }
   else if (name == "llama-3-70b") { m.hidden = 8192; m.layers = 80; m.heads = 64; m.kv_heads = 8; m.ffn = 28672; }

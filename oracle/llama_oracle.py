@@ -76,7 +76,7 @@ PRESETS = {
                                ffn=28672),
     # Mixtral-8x7B architecture (BASELINE config 4): 8 experts, top-2, rope theta 1e6.  The synthetic
     # presets keep the 128256-entry vocabulary of the synthetic tokenizer (a real checkpoint has 32000).
-    "tiny-moe": LlamaConfig("tiny-moe", hidden=512, layers=2, heads=4, kv_heads=1, ffn=768, experts=8,
+    "tiny-moe": LlamaConfig("tiny-moe", hidden=512, layers=2, heads=4, kv_heads=2, ffn=768, experts=8,
                             rope_theta=1000000.0),
     "mixtral-8x7b-l2": LlamaConfig("mixtral-8x7b-l2", hidden=4096, layers=2, heads=32, kv_heads=8, ffn=14336,
                                    experts=8, rope_theta=1000000.0),
