@@ -32,6 +32,12 @@ namespace acp {
 constexpr int GEMM_BM = 128;  // UMMA M (weight rows per tile)
 constexpr int GEMM_BK = 64;   // bf16 elements per k-block (= one 128-byte swizzle row)
 constexpr int GEMM_THREADS = 192;
+// grouped mode: layout of the device-side `group_ranges` array (written by moe_dispatch_kernel):
+//   [2g], [2g+1]                    first row and row count of group g            (g < GEMM_GROUP_MAX)
+//   [GEMM_GROUP_TILES]              number of entries of the flat tile list
+//   [GEMM_GROUP_TILES + 2 + 2i ..]  tile i = {group, first row inside the group}
+constexpr int GEMM_GROUP_MAX = 16;
+constexpr int GEMM_GROUP_TILES = 2 * GEMM_GROUP_MAX;
 
 enum GemmEpi : int {
   EPI_BF16 = 0,     // out_bf16[n*ld + m]
@@ -53,8 +59,8 @@ struct GemmArgs {
   const int* n_dev;  // optional device scalar overriding N (CUDA-graph replay with varying batch)
   // GROUPED mode (mixture of experts): group g's weights are m-tiles [g*gridDim.y, (g+1)*gridDim.y) of the
   // (concatenated) weight tensor, its activation / output rows are [ranges[2g], ranges[2g] + ranges[2g+1]).
-  // blockIdx.x indexes a flat tile list {group, first row inside the group} at ranges[32 + 2 ...] (count at
-  // ranges[32]) — all written on the device by moe_dispatch_kernel, so row counts never visit the host and
+  // blockIdx.x indexes a flat tile list {group, first row inside the group} (layout: GEMM_GROUP_TILES above)
+  // — all written on the device by moe_dispatch_kernel, so row counts never visit the host and
   // no CTA is launched for rows that do not exist (beyond the <= E slack of the grid bound).  splits must be 1.
   const int* group_ranges;
 };
@@ -124,9 +130,9 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   pdl_launch_dependents();
   if (grouped) {
     pdl_wait();                        // the ranges come from the previous kernel (moe_dispatch)
-    if ((int)blockIdx.x >= args.group_ranges[32]) return;   // whole CTA, before any barrier / TMEM allocation
-    const int group = args.group_ranges[34 + 2 * blockIdx.x];
-    n0 = args.group_ranges[34 + 2 * blockIdx.x + 1];
+    if ((int)blockIdx.x >= args.group_ranges[GEMM_GROUP_TILES]) return;   // whole CTA, before any barrier / TMEM allocation
+    const int group = args.group_ranges[GEMM_GROUP_TILES + 2 + 2 * blockIdx.x];
+    n0 = args.group_ranges[GEMM_GROUP_TILES + 2 + 2 * blockIdx.x + 1];
     row_off = args.group_ranges[2 * group];
     group_rows = args.group_ranges[2 * group + 1];
     m_tile = group * m_tiles + (int)blockIdx.y;

@@ -178,6 +178,10 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int 
     // attention stays head-parallel.  Tokens are replicated across the ranks (every rank holds xn after the
     // fused exchange), so "dispatch" is a local gather and "combine" is the row-parallel all-reduce.
     if (cfg.experts % tp_size) { fprintf(stderr, "[acp_infer] tp=%d does not divide experts=%d\n", tp_size, cfg.experts); return -1; }
+    if (cfg.experts > 16 || lim.max_tokens > 32767) {
+      fprintf(stderr, "[acp_infer] mixture of experts: at most 16 experts and max_tokens_per_step <= 32767 (got %d, %d)\n", cfg.experts, lim.max_tokens);
+      return -1;
+    }
     experts_l_ = cfg.experts / tp_size;
     expert0_ = tp_rank * experts_l_;
     ffn_l_ = cfg.ffn;

@@ -17,12 +17,13 @@
 // (Mixtral-8x7B); architecture = transformers MixtralSparseMoeBlock (oracle/llama_oracle.py _moe).
 #include "moe.h"
 #include "common.cuh"
+#include "gemm_tcgen05.cuh"
 
 namespace acp {
 
 namespace {
 
-constexpr int MOE_MAX_E = 16;
+constexpr int MOE_MAX_E = GEMM_GROUP_MAX;   // experts per rank
 
 __global__ void __launch_bounds__(128)
 moe_router_kernel(const __nv_bfloat16* __restrict__ xn, const __nv_bfloat16* __restrict__ wr, int hidden, int E, int T,
@@ -116,13 +117,13 @@ moe_dispatch_kernel(const int* __restrict__ topk_idx, int T, int e_first, int e_
       off += s_cnt[e][1024];
     }
     s_off[e_local] = off;
-    // flat work list of the grouped GEMMs: one entry {expert, first row inside the expert} per BN-row tile,
-    // ranges[2*MOE_MAX_E] = number of entries, entries from ranges[2*MOE_MAX_E + 2] on
+    // flat work list of the grouped GEMMs (layout: GEMM_GROUP_TILES in gemm_tcgen05.cuh): one entry
+    // {expert, first row inside the expert} per BN-row tile
     int n = 0;
-    int* tiles = ranges + 2 * MOE_MAX_E + 2;
+    int* tiles = ranges + GEMM_GROUP_TILES + 2;
     for (int e = 0; e < e_local; ++e)
       for (int n0 = 0; n0 < (int)s_cnt[e][1024]; n0 += bn) { tiles[2 * n] = e; tiles[2 * n + 1] = n0; ++n; }
-    ranges[2 * MOE_MAX_E] = n;
+    ranges[GEMM_GROUP_TILES] = n;
   }
   __syncthreads();
   int pos[MOE_MAX_E];
@@ -212,7 +213,7 @@ int launch_moe_dispatch(const int* topk_idx, int T, int e_first, int e_local, in
   MOE_LAUNCH("moe_dispatch", acp_launch(moe_dispatch_kernel, dim3(1), dim3(1024), 0, s, topk_idx, T, e_first, e_local, bn, ranges, row_of));
   return 0;
 }
-int moe_ranges_ints(int T) { return 2 * MOE_MAX_E + 2 + 2 * (2 * T / 16 + MOE_MAX_E + 1); }
+int moe_ranges_ints(int T) { return GEMM_GROUP_TILES + 2 + 2 * (2 * T / 16 + MOE_MAX_E + 1); }
 int moe_tile_cap(int T, int bn, int e_local) { return (2 * T + bn - 1) / bn + e_local; }
 int launch_moe_gather(const __nv_bfloat16* xn, const int* row_of, int hidden, int T, __nv_bfloat16* xe, cudaStream_t s) {
   if (T <= 0) return 0;
