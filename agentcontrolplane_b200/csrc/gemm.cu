@@ -104,7 +104,7 @@ int gemm_pick_bn(int N) {
 // ACP_GEMM_SHALLOW=0: wide tiles keep the deep ring / one CTA per SM (A/B switch)
 static bool shallow_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("ACP_GEMM_SHALLOW"); v = (e && *e == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("ACP_GEMM_SHALLOW"); v = (e && *e == '1') ? 1 : 0; }
   return v == 1;
 }
 
@@ -145,12 +145,57 @@ static int launch_bn(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t st
 
 static bool persistent_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("ACP_GEMM_PERSISTENT"); v = (e && *e == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("ACP_GEMM_PERSISTENT"); v = (e && *e == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// ACP_GEMM_2CTA=0: prefill GEMMs stay on the 1-CTA persistent kernel (A/B switch of the cta_group::2 kernel)
+static bool two_cta_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACP_GEMM_2CTA"); v = (e && *e == '1') ? 1 : 0; }
   return v == 1;
 }
 
 template <int EPI>
+static int launch_persistent2(const GemmLaunch& g, cudaStream_t stream) {
+  GemmArgs a;
+  a.M = g.M; a.N = g.N; a.K = g.K; a.splits = 1; a.ld = g.ld; a.n_cap = g.n_cap;
+  a.out = g.out; a.amax_val = nullptr; a.amax_idx = nullptr; a.n_dev = g.n_dev;
+  a.group_ranges = nullptr;
+  const int m_pairs = (g.M + GEMM_BM - 1) / GEMM_BM / 2, n_tiles = (g.N + PGEMM_BN - 1) / PGEMM_BN;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = P2_SMEM;
+  cfg.stream = stream;
+  // co-resident CTA pairs (74 = one per TPC on a full B200); asked once per instantiation
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_wx_persistent2_kernel<EPI>, &cfg) != cudaSuccess || n <= 0) n = 74;
+    max_clusters = n;
+  }
+  int clusters = m_pairs * n_tiles;
+  if (clusters > max_clusters) clusters = max_clusters;
+  cfg.gridDim = dim3(2 * clusters);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = acp_pdl_enabled() ? 1 : 0;   // the cluster shape is compiled in (__cluster_dims__)
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wx_persistent2_kernel<EPI>, *g.w, g.x->x[3], a, m_pairs, n_tiles);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[acp_infer] 2-CTA persistent gemm launch failed EPI=%d: %s\n", EPI, cudaGetErrorString(e));
+    return -5;
+  }
+  return 0;
+}
+
+template <int EPI>
 static int launch_persistent(const GemmLaunch& g, cudaStream_t stream) {
+  // cta_group::2 kernel when the weight rows pair up (every shape of the served models does)
+  const bool want2 = g.two_cta < 0 ? two_cta_enabled() : g.two_cta == 1;
+  if (want2 && ((g.M + GEMM_BM - 1) / GEMM_BM) % 2 == 0 && g.M % GEMM_BM == 0) return launch_persistent2<EPI>(g, stream);
   GemmArgs a;
   a.M = g.M; a.N = g.N; a.K = g.K; a.splits = 1; a.ld = g.ld; a.n_cap = g.n_cap;
   a.out = g.out; a.amax_val = nullptr; a.amax_idx = nullptr; a.n_dev = g.n_dev;
@@ -206,7 +251,9 @@ static int set_attr_bn() {
 int gemm_setup_attributes() {
   int rc = set_attr_bn<16>() | set_attr_bn<32>() | set_attr_bn<64>() | set_attr_bn<128>() |
            set_attr_bn<256>();
-  if (cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess ||
+  if (cudaFuncSetAttribute(gemm_wx_persistent2_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_wx_persistent2_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess)
     rc = -5;
   if (rc != 0) fprintf(stderr, "[acp_infer] cudaFuncSetAttribute(max dyn smem) failed\n");

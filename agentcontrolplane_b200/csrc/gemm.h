@@ -36,6 +36,7 @@ struct GemmLaunch {
   int* amax_idx = nullptr;
   const int* n_dev = nullptr;
   int bn_override = 0;  // 0 = pick from N
+  int two_cta = -1;     // prefill (N > 256) GEMMs: -1 = policy (gemm.cu two_cta_enabled), 0 = 1-CTA persistent kernel, 1 = cta_group::2 kernel
   // grouped mode (mixture of experts): `groups` weight tensors of M rows each, concatenated in `w`;
   // group g works on rows [ranges[2g], ranges[2g] + ranges[2g+1]) of x / out (device array, layout of
   // moe_dispatch_kernel incl. its flat tile list).  bn_override = the tile height the list was built for,

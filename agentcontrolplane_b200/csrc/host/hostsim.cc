@@ -736,6 +736,7 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
   std::mutex lat_mu;
   std::vector<double> lat_ms;
   std::map<std::string, int> phases;
+  std::string first_error;
   uint64_t digest = 0;
   // ONE state machine shared by all reconcile workers, like the reference's TaskReconciler
   task::StateMachine sm(&store, &rec);
@@ -862,6 +863,8 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
         std::lock_guard<std::mutex> lk(lat_mu);
         task_ms.push_back(total_ms);
         ++phases[t.Status.Phase];
+        if (t.Status.Phase == "Failed" && first_error.empty())
+          first_error = name + ": " + (t.Status.Error.empty() ? t.Status.StatusDetail : t.Status.Error);
         uint64_t h = 1469598103934665603ull;
         const std::string d = t.Status.Output + "|" + t.Status.Phase;
         for (unsigned char ch : d) { h ^= ch; h *= 1099511628211ull; }
@@ -898,6 +901,7 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
   Json ph = Json::object();
   for (auto& kv : phases) ph.set(kv.first, Json(kv.second));
   out.set("final_phases", ph);
+  if (!first_error.empty()) out.set("first_error", Json(first_error));   // why the first Failed Task failed
   char dbuf[32];
   snprintf(dbuf, sizeof dbuf, "%016llx", (unsigned long long)digest);
   out.set("digest", Json(std::string(dbuf)));

@@ -71,7 +71,8 @@ extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int 
   g.w = &mw.w; g.x = &mx; g.M = M; g.N = N; g.K = Kp; g.splits = splits; g.epi = epi;
   g.ld = (epi == EPI_SWIGLU) ? M / 2 : M; g.n_cap = N;
   g.out = (epi == EPI_ARGMAX && out == nullptr) ? nullptr : dout.p;
-  g.amax_val = (float*)dval.p; g.amax_idx = (int*)didx.p; g.bn_override = bn;
+  g.amax_val = (float*)dval.p; g.amax_idx = (int*)didx.p; g.bn_override = bn > 0 ? bn : 0;
+  g.two_cta = bn == -2 ? 1 : (bn == -1 ? 0 : -1);   // hook-only: bn -2 / -1 force the 2-CTA / 1-CTA prefill kernel
   int rc = gemm_launch(g, 0);
   if (rc != 0) return rc;
   ACP_CUDA_CHECK(cudaDeviceSynchronize());

@@ -281,6 +281,9 @@ def main():
         pages_per_seq += 12   # second LLM step: window + tool call + tool result
     if WORKLOAD.get("delegation_depth"):
         pages_per_seq += 16   # the delegate tool's schema in the window + the scripted delegate call (byte-level tokenizer)
+        # the child's Output comes back as the ToolCall result: a generated token re-encodes to up to 5 byte tokens
+        # under the synthetic vocabulary (" " + base-26 letters), so the fold-back adds up to 5 x max_tokens rows
+        pages_per_seq += (5 * max_new) // 32 + 2
     kv_pages = n_tasks * pages_per_seq * 2 + 8
     if dry is not None:   # mixed windows: size the KV pool from the dry run
         pages_per_seq = (dry["prompt_tokens_max"] + max_new) // 32 + 2
@@ -322,6 +325,9 @@ def main():
         task_p99.append(r.get("task_ms_p99"))
         for k, v in r["final_phases"].items():
             phases[k] = phases.get(k, 0) + v
+        if r["final_phases"].get("Failed"):
+            # a Failed Task is work that was NOT done (its remaining LLM steps never ran): the number would be invalid
+            raise SystemExit(f"bench: {r['final_phases']['Failed']} Tasks ended Failed — {r.get('first_error')}")
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None

@@ -19,7 +19,8 @@ extern "C" {
  * epi 0: out = bf16 [N][M]; epi 1: out = fp32 [splits][N][M] (split-K partial planes);
  * epi 2: amax_val/amax_idx = per-row arg-max over M (lowest index wins ties), out = optional
  * fp32 logits [N][M] (may be NULL); epi 3: rows of w interleaved (gate_j, up_j), out = bf16
- * [N][M/2] = bf16(bf16(silu(g)) * u).  bn = 0 picks the N tile from N; otherwise 16..256.
+ * [N][M/2] = bf16(bf16(silu(g)) * u).  bn = 0 picks the N tile from N; otherwise 16..256;
+ * bn = -1 / -2 (N > 256, epi 0 or 3) force the 1-CTA / the cta_group::2 persistent prefill kernel.
  * iters > 0 additionally times `iters` launches with CUDA events (L2 flushed between
  * launches) and stores the mean milliseconds in *elapsed_ms. */
 int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int N, int K, int splits,

@@ -130,3 +130,37 @@ def test_gemm_fused_swiglu_epilogue(M, N, K):
     assert np.all(err <= tol), float(np.max(err / np.maximum(np.abs(ref), 1e-3)))
     # ... but almost every element must agree to one ulp
     assert np.mean(err <= np.maximum(np.abs(ref) * 2.0 ** -7, 1e-3)) > 0.995
+
+
+# ---- cta_group::2 persistent prefill kernel (gemm_persistent.cuh gemm_wx_persistent2_kernel) ----------------
+# Same fp32 accumulation order as the 1-CTA kernel (K in order, one accumulator per output element), so the two
+# must agree BIT FOR BIT; the 1-CTA kernel is the one test_gemm_bf16_out pins against numpy.
+@pytest.mark.parametrize("M,N,K,epi", [
+    (256, 300, 128, 0),       # one CTA pair, two N tiles (ragged: the second has 44 valid rows)
+    (256, 1000, 4096, 0),     # long K: the 6-stage ring wraps 10 times per tile
+    (2560, 2600, 192, 0),     # 10 pairs x 11 N tiles = 110 tiles > 74 clusters: both TMEM buffers, tile loop
+    (4096, 8192, 4096, 0),    # Llama-3-8B wo at an 8192-token chunk
+    (2048, 3000, 320, 3),     # fused SwiGLU epilogue
+    (3584, 4096, 512, 3),
+])
+def test_gemm_two_cta_matches_one_cta(M, N, K, epi):
+    rng = np.random.default_rng(M + 3 * N + K + epi)
+    w = _rand_bits(rng, (M, K), 0.05)
+    x = _rand_bits(rng, (N, K), 1.0)
+    one, _, _, _ = _gemm(w, x, epi=epi, bn=-1)
+    two, _, _, _ = _gemm(w, x, epi=epi, bn=-2)
+    assert np.array_equal(one, two), int(np.count_nonzero(one != two))
+    if epi == 0 and M * N <= 2560 * 2600:
+        ref = bits_to_f32(x) @ bits_to_f32(w).T
+        got = bits_to_f32(two)
+        assert np.all(np.abs(got - ref) <= np.maximum(np.abs(ref) * 2.0 ** -7, 1e-3))
+
+
+def test_gemm_two_cta_repeatable():
+    rng = np.random.default_rng(11)
+    w = _rand_bits(rng, (1024, 1024), 0.05)
+    x = _rand_bits(rng, (5000, 1024), 1.0)
+    a, _, _, _ = _gemm(w, x, epi=0, bn=-2)
+    for _ in range(3):
+        b, _, _, _ = _gemm(w, x, epi=0, bn=-2)
+        assert np.array_equal(a, b)
