@@ -804,7 +804,11 @@ extern "C" int acp_hostsim_run(acp_engine* engine, const char* config_json, char
           lat_ms.push_back(ms);
         }
         ++steps;
-        if (!err.empty()) return;  // would requeue after 5 s; out of the timed loop
+        if (!err.empty()) {        // would requeue after 5 s; out of the timed loop
+          std::lock_guard<std::mutex> lk(lat_mu);
+          if (first_error.empty()) first_error = name + " (phase " + t.Status.Phase + "): " + err;
+          return;
+        }
       } else if (phase == "ToolCallsPending") {
         for (Json& tcj : store.ListToolCalls(name, t.Status.ToolCallRequestID)) {
           task::ToolCall tc;

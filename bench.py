@@ -328,6 +328,8 @@ def main():
         if r["final_phases"].get("Failed"):
             # a Failed Task is work that was NOT done (its remaining LLM steps never ran): the number would be invalid
             raise SystemExit(f"bench: {r['final_phases']['Failed']} Tasks ended Failed — {r.get('first_error')}")
+    if reconciles == 0 or not phases.get("FinalAnswer"):
+        raise SystemExit(f"bench: no Task reached FinalAnswer (phases {phases}) — {r.get('first_error')}")
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None

@@ -18,6 +18,8 @@ def main():
     rng = np.random.default_rng(0)
     shapes = [("qkv", 6144, 4096, 0), ("o", 4096, 4096, 0), ("gate_up", 28672, 4096, 3), ("down", 4096, 14336, 0)]
     Ns = [int(a) for a in sys.argv[1:]] or [8192]
+    only, iters = os.environ.get("ONLY"), int(os.environ.get("ITERS", "10"))   # ONLY=gate_up ITERS=0: one launch each (ncu)
+    shapes = [s for s in shapes if not only or s[0] == only]
     res = []
     for name, M, K, epi in shapes:
         w = rng.integers(0x3000, 0x3C00, size=(M, K), dtype=np.uint16)
@@ -29,7 +31,7 @@ def main():
                 out = np.zeros((N, M // 2 if epi == 3 else M), np.uint16)
                 ms = ctypes.c_float(0)
                 rc = lib.acp_kernel_gemm(w.ctypes.data_as(u16p), x.ctypes.data_as(u16p), M, N, K, 1, epi, mode,
-                                         out.ctypes.data_as(ctypes.c_void_p), None, None, 10, ctypes.byref(ms))
+                                         out.ctypes.data_as(ctypes.c_void_p), None, None, iters, ctypes.byref(ms))
                 outs[mode] = out
                 tf = 2.0 * M * N * K / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0
                 r = dict(gemm=name, M=M, K=K, N=N, kernel="1cta" if mode == -1 else "2cta", rc=rc, ms=ms.value, tflops=tf)

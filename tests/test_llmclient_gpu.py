@@ -158,6 +158,32 @@ def test_tool_loop_two_llm_steps(eng):
     assert s1["prefix_tokens_reused"] - s0["prefix_tokens_reused"] >= 8 * (640 + (window // 32) * 32)
 
 
+@pytest.mark.parametrize("model", ["tiny", "tiny-moe"])
+def test_delegation_chain_five_llm_steps(model):
+    """BASELINE config 4's Task shape (toolcall/executor.go:176-242, toolcall/state_machine.go:218-267): every root
+    Task delegates down a depth-2 sub-agent chain — 5 LLM steps, 2 ToolCall CRs and 2 child Task CRs per root —
+    under open-loop Poisson arrivals.  Every Task must end in FinalAnswer (a Failed Task is skipped work: this is
+    the check bench.py --config 4 relies on), and the KV sizing rule of bench.py must hold the fold-back of the
+    child's Output (a generated token re-encodes to up to 5 byte tokens under the synthetic vocabulary)."""
+    n, max_new, plen = 24, 64, 512
+    pages_per_seq = (plen + max_new) // 32 + 2 + 12 + 16 + (5 * max_new) // 32 + 2      # bench.py main()
+    e = Engine({"model": model, "max_batch": 64, "kv_pages": n * pages_per_seq * 2 + 8, "max_tokens_per_step": 4096,
+                "max_pages_per_seq": pages_per_seq, "prefix_cache": True})
+    try:
+        cfg = {"tasks": n, "workers": n, "provider": "local", "model": model, "max_tokens": max_new, "prompt_tokens": plen,
+               "tools": 0, "tool_loop": False, "arrival_rate": 200.0, "delegation_depth": 2, "seed": 9}
+        r = host.hostsim_run(cfg, e)
+        assert r["final_phases"] == {"FinalAnswer": n}, (r["final_phases"], r.get("first_error"))
+        assert r["reconciles"] == 5 * n
+        s = e.stats()
+        assert s["requests_failed"] == 0
+        assert s["prefix_hits"] >= 2 * n          # the second turn of the root and of the first child re-use their windows
+        again = host.hostsim_run(cfg, e)
+        assert again["digest"] == r["digest"]     # outputs do not depend on arrival interleaving or on cache state
+    finally:
+        e.close()
+
+
 def test_cancel_and_sampling(eng):
     t = eng.submit({"model": "tiny", "max_tokens": 400, "acp": {"prompt_token_ids": [128000, 65, 66]}})
     eng.cancel(t)
