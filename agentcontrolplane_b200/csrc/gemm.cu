@@ -145,11 +145,11 @@ static int launch_bn(const GemmLaunch& g, const CUtensorMap& tx, cudaStream_t st
 
 static bool persistent_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("ACP_GEMM_PERSISTENT"); v = (e && *e == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("ACP_GEMM_PERSISTENT"); v = (e && *e == '0') ? 0 : 1; }
   return v == 1;
 }
 
-// ACP_GEMM_2CTA=0: prefill GEMMs stay on the 1-CTA persistent kernel (A/B switch of the cta_group::2 kernel)
+// ACP_GEMM_2CTA=1: prefill GEMMs use the cta_group::2 kernel (default: the 1-CTA persistent kernel)
 static bool two_cta_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("ACP_GEMM_2CTA"); v = (e && *e == '1') ? 1 : 0; }

@@ -26,7 +26,10 @@ static bool debug_sync_enabled() {
 #define ACP_TRY(expr)                                                                      \
   do {                                                                                     \
     int _rc = (expr);                                                                      \
-    if (_rc != 0) return _rc;                                                              \
+    if (_rc != 0) {   /* never fail silently: name the call (one line per frame up the stack) */ \
+      fprintf(stderr, "[acp_infer] `%s` failed with %d (%s:%d)\n", #expr, _rc, __FILE__, __LINE__); \
+      return _rc;                                                                          \
+    }                                                                                      \
     if (debug_sync_enabled() && stream_) {                                                 \
       cudaError_t _e = cudaStreamSynchronize(stream_);                                     \
       if (_e != cudaSuccess) {                                                             \
@@ -641,8 +644,11 @@ int Model::bench_exchange(int T, int iters, float* avg_us, int diag) {
 
 int Model::forward(const StepInput& in) {
   const ModelConfig& c = cfg_;
-  if (in.T <= 0 || in.T > lim_.max_tokens || in.B > lim_.max_batch || in.n_sample > lim_.max_batch)
+  if (in.T <= 0 || in.T > lim_.max_tokens || in.B > lim_.max_batch || in.n_sample > lim_.max_batch) {
+    fprintf(stderr, "[acp_infer] step outside the model limits: T=%d (max %d) B=%d n_sample=%d (max_batch %d)\n", in.T, lim_.max_tokens, in.B,
+            in.n_sample, lim_.max_batch);
     return -1;
+  }
   ACP_CUDA_CHECK(cudaSetDevice(device_));
   // every tensor-parallel shard uploads the SAME pinned step descriptor (the lead shard's staging)
   const int* src_ints = lead_ ? lead_->h_ints_ : h_ints_;
