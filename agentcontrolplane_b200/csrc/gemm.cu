@@ -191,11 +191,20 @@ static int launch_persistent2(const GemmLaunch& g, cudaStream_t stream) {
   return 0;
 }
 
+// Which kernel gemm_launch picks (pure host logic: tests/test_abi_cpu.py pins the defaults without a GPU):
+// prefill-sized problems (N > 256, bf16 or fused-SwiGLU output, not grouped) run the persistent kernel with
+// double-buffered TMEM accumulators — its cta_group::2 flavour only on request and when the weight rows pair up.
+int gemm_path(const GemmLaunch& g) {
+  if (g.N > 256 && g.bn_override == 0 && g.groups == 0 && persistent_enabled() && (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU)) {
+    const bool want2 = g.two_cta < 0 ? two_cta_enabled() : g.two_cta == 1;
+    if (want2 && g.M % (2 * GEMM_BM) == 0) return GEMM_PATH_PERSISTENT_2CTA;
+    return GEMM_PATH_PERSISTENT;
+  }
+  return GEMM_PATH_TILED;
+}
+
 template <int EPI>
 static int launch_persistent(const GemmLaunch& g, cudaStream_t stream) {
-  // cta_group::2 kernel when the weight rows pair up (every shape of the served models does)
-  const bool want2 = g.two_cta < 0 ? two_cta_enabled() : g.two_cta == 1;
-  if (want2 && ((g.M + GEMM_BM - 1) / GEMM_BM) % 2 == 0 && g.M % GEMM_BM == 0) return launch_persistent2<EPI>(g, stream);
   GemmArgs a;
   a.M = g.M; a.N = g.N; a.K = g.K; a.splits = 1; a.ld = g.ld; a.n_cap = g.n_cap;
   a.out = g.out; a.amax_val = nullptr; a.amax_idx = nullptr; a.n_dev = g.n_dev;
@@ -216,10 +225,10 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   if (g.N <= 0 || g.M <= 0) return 0;
   if (g.epi != EPI_F32 && g.splits != 1) return -1;
   if (g.groups > 0 && (g.splits != 1 || g.group_ranges == nullptr || (g.epi != EPI_BF16 && g.epi != EPI_SWIGLU))) return -1;
-  // prefill-sized problems: persistent kernel with double-buffered TMEM accumulators
-  if (g.N > 256 && g.bn_override == 0 && g.groups == 0 && persistent_enabled()) {
-    if (g.epi == EPI_BF16) return launch_persistent<EPI_BF16>(g, stream);
-    if (g.epi == EPI_SWIGLU) return launch_persistent<EPI_SWIGLU>(g, stream);
+  switch (gemm_path(g)) {
+    case GEMM_PATH_PERSISTENT: return g.epi == EPI_BF16 ? launch_persistent<EPI_BF16>(g, stream) : launch_persistent<EPI_SWIGLU>(g, stream);
+    case GEMM_PATH_PERSISTENT_2CTA: return g.epi == EPI_BF16 ? launch_persistent2<EPI_BF16>(g, stream) : launch_persistent2<EPI_SWIGLU>(g, stream);
+    default: break;
   }
   const int bn = g.bn_override ? g.bn_override : gemm_pick_bn(g.N);
   switch (bn) {

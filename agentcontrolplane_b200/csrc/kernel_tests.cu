@@ -29,6 +29,14 @@ extern "C" int acp_kernel_device_count(void) {
   return n;
 }
 
+extern "C" int acp_kernel_gemm_path(int M, int N, int K, int epi, int bn) {
+  GemmLaunch g;
+  g.M = M; g.N = N; g.K = K; g.epi = epi; g.splits = 1;
+  g.bn_override = bn > 0 ? bn : 0;
+  g.two_cta = bn == -2 ? 1 : (bn == -1 ? 0 : -1);
+  return gemm_path(g);
+}
+
 extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int N, int K,
                                int splits, int epi, int bn, void* out, float* amax_val,
                                int* amax_idx, int iters, float* elapsed_ms) {

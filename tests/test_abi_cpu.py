@@ -43,6 +43,24 @@ def test_version_and_no_device_behaviour():
         assert ei.value.code == -5          # ACP_ERR_CUDA: loud failure, never a CPU path
 
 
+def test_default_kernel_dispatch():
+    """The kernel the GEMM dispatcher picks by default, with no environment switch set (host logic, no GPU):
+    prefill-sized problems must run the persistent kernel — an inverted default here silently costs ~13 % of the
+    bench (it happened once) — and the cta_group::2 flavour only on request."""
+    import subprocess, sys
+    code = (
+        "import os\n"
+        "for k in ('ACP_GEMM_PERSISTENT', 'ACP_GEMM_2CTA'): os.environ.pop(k, None)\n"
+        "from agentcontrolplane_b200 import _lib\n"
+        "p = _lib.load().acp_kernel_gemm_path\n"
+        "print(p(28672, 4096, 4096, 3, 0), p(4096, 8192, 14336, 0, 0), p(4096, 64, 4096, 0, 0), p(4096, 256, 4096, 0, 0),\n"
+        "      p(4096, 512, 4096, 1, 0), p(4096, 4096, 4096, 0, -2), p(4224, 4096, 4096, 0, -2), p(4096, 4096, 4096, 0, -1), p(4096, 4096, 4096, 0, 256))\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    #          gate/up  down  decode  N=256  fp32 planes  2-CTA  odd m-tiles  1-CTA  forced tile
+    assert out.stdout.split() == ["1", "1", "0", "0", "0", "2", "1", "1", "0"], out.stdout
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "agentcontrolplane_b200")
     for dirpath, _, files in os.walk(pkg):
