@@ -149,10 +149,11 @@ static bool persistent_enabled() {
   return v == 1;
 }
 
-// ACP_GEMM_2CTA=1: prefill GEMMs use the cta_group::2 kernel (default: the 1-CTA persistent kernel)
+// ACP_GEMM_2CTA=0: prefill GEMMs stay on the 1-CTA persistent kernel (A/B switch; the cta_group::2 kernel is the
+// default since it measured +10..15 % at 8192 rows and +7 % on the bench line, profiles/r2_gemm_2cta.md)
 static bool two_cta_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("ACP_GEMM_2CTA"); v = (e && *e == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("ACP_GEMM_2CTA"); v = (e && *e == '0') ? 0 : 1; }
   return v == 1;
 }
 
@@ -193,7 +194,8 @@ static int launch_persistent2(const GemmLaunch& g, cudaStream_t stream) {
 
 // Which kernel gemm_launch picks (pure host logic: tests/test_abi_cpu.py pins the defaults without a GPU):
 // prefill-sized problems (N > 256, bf16 or fused-SwiGLU output, not grouped) run the persistent kernel with
-// double-buffered TMEM accumulators — its cta_group::2 flavour only on request and when the weight rows pair up.
+// double-buffered TMEM accumulators — the cta_group::2 flavour whenever the weight rows pair up (M % 256 == 0:
+// every matrix of the served models), the 1-CTA flavour otherwise.
 int gemm_path(const GemmLaunch& g) {
   if (g.N > 256 && g.bn_override == 0 && g.groups == 0 && persistent_enabled() && (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU)) {
     const bool want2 = g.two_cta < 0 ? two_cta_enabled() : g.two_cta == 1;

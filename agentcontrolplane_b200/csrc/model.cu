@@ -143,11 +143,20 @@ int Model::choose_splits(int M, int K, int N) const {
     // ceil(tiles * S / 148) / S (waves of one CTA per SM, each doing 1/S of K); ties -> fewer planes
     const int tiles = m_tiles * ((N + 255) / 256);
     s = 1;
-    double best = 1e30;
     // (>= one tile per SM already: no split — the persistent kernel balances those itself, bf16 epilogue)
-    for (int cand = 1; tiles < 148 && cand <= (max_s < 8 ? max_s : 8); ++cand) {
-      const double cost = (double)((tiles * cand + 147) / 148) / cand;
-      if (cost < best - 1e-9) { best = cost; s = cand; }
+    if (tiles < 148) {
+      const int cap = max_s < 8 ? max_s : 8;
+      double best = 1e30;
+      for (int cand = 1; cand <= cap; ++cand) {
+        const double cost = (double)((tiles * cand + 147) / 148) / cand;
+        if (cost < best) best = cost;
+      }
+      // every extra plane is N x M fp32 written and re-read: take the FEWEST planes within 15 % of the best
+      // wave count (128 tiles: 1 plane at cost 1.0, not 8 planes at 0.875; 64 tiles: 2; 96 tiles: 3)
+      for (int cand = 1; cand <= cap; ++cand) {
+        const double cost = (double)((tiles * cand + 147) / 148) / cand;
+        if (cost <= best * 1.15 + 1e-9) { s = cand; break; }
+      }
     }
   } else {
     s = (lim_.splitk_target_ctas + m_tiles / 2) / m_tiles;
@@ -296,8 +305,12 @@ int Model::alloc_all() {
   const int shapes[4][2] = {{qkv_l_, c.hidden}, {c.hidden, qdim_l_}, {2 * ffn_l_, c.hidden}, {c.hidden, ffn_l_}};
   for (auto& s : shapes) {
     if (c.experts > 0 && (&s - shapes) >= 2) continue;   // the expert GEMMs are grouped, never split-K
-    size_t b = (size_t)choose_splits(s[0], s[1], 0) * lim_.max_batch * s[0] * sizeof(float);
-    if (b > ws) ws = b;
+    // the split factor depends on the row count beyond 256 rows (choose_splits): size for every step height
+    for (int n = 256; n < lim_.max_batch + 256; n += 256) {
+      const int rows = n < lim_.max_batch ? n : lim_.max_batch;
+      const size_t b = (size_t)choose_splits(s[0], s[1], rows) * rows * s[0] * sizeof(float);
+      if (b > ws) ws = b;
+    }
   }
   if (tp_size_ > 1) {  // row-parallel GEMMs write fp32 (one rounding after the all-reduce), prefill too
     const size_t b = (size_t)T * H * sizeof(float);
@@ -554,7 +567,7 @@ int Model::gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool de
   const int splits = choose_splits(M, K, N);
   if (decode && splits > 1) {  // a single split writes bf16 directly (same rounding, half the bytes)
     g.epi = EPI_F32; g.splits = splits; g.out = ws_; g.ld = M; g.n_cap = N;
-    if ((size_t)splits * N * M * sizeof(float) > ws_bytes_) return -4;
+    if ((size_t)splits * N * M * sizeof(float) > ws_bytes_) { fprintf(stderr, "[acp_infer] split-K workspace too small: %d planes x %d x %d\n", splits, N, M); return -4; }
     out->ptr = ws_; out->splits = splits; out->n_cap = N; out->ld = M;
   } else {
     g.epi = EPI_BF16; g.splits = 1; g.out = gemm_bf16_; g.ld = M; g.n_cap = N;
@@ -571,7 +584,7 @@ int Model::gemm_rowpar(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, 
   g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
   const int splits = decode ? choose_splits(M, K, N) : 1;
   g.epi = EPI_F32; g.splits = splits; g.out = ws_; g.ld = M; g.n_cap = N;
-  if ((size_t)splits * N * M * sizeof(float) > ws_bytes_) return -4;
+  if ((size_t)splits * N * M * sizeof(float) > ws_bytes_) { fprintf(stderr, "[acp_infer] split-K workspace too small: %d planes x %d x %d\n", splits, N, M); return -4; }
   ++launches_;
   int rc = gemm_launch(g, stream_);
   if (rc != 0) return rc;
@@ -601,7 +614,7 @@ int Model::rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool d
   const int splits = decode ? choose_splits(M, K, N) : 1;
   g.epi = EPI_F32; g.splits = splits; g.ld = M; g.n_cap = N;
   g.out = splits > 1 ? ws_ : ar_buf_;
-  if (splits > 1 && (size_t)splits * N * M * sizeof(float) > ws_bytes_) return -4;
+  if (splits > 1 && (size_t)splits * N * M * sizeof(float) > ws_bytes_) { fprintf(stderr, "[acp_infer] split-K workspace too small: %d planes x %d x %d\n", splits, N, M); return -4; }
   int rc = gemm_launch(g, stream_);
   if (rc != 0) return rc;
   ++launches_;

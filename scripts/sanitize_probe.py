@@ -14,7 +14,7 @@ from agentcontrolplane_b200 import _lib  # noqa: E402
 from agentcontrolplane_b200.engine import Engine  # noqa: E402
 
 rng = np.random.default_rng(7)
-for model, mode in (("tiny", "item"), ("tiny-g8", "chunked")):
+for model, mode in (("tiny", "item"), ("tiny-g8", "chunked"), ("tiny-moe", "chunked")):   # tiny-moe: router / dispatch / gather / grouped GEMMs / combine
     with Engine({"model": model, "max_batch": 8, "kv_pages": 96, "max_tokens_per_step": 128, "attn_decode_mode": mode}) as eng:
         prompts = [[128000] + [int(t) for t in rng.integers(0, 256, size=n)] for n in (5, 40, 150, 150, 300)]
         prompts[3] = prompts[2][:130] + prompts[3][130:]          # shares four prefix pages with prompt 2
@@ -39,4 +39,16 @@ for heads, kvh, q_len, ctx in ((4, 1, 70, 200), (8, 1, 33, 33)):
         rc = lib.acp_kernel_attn_prefill(q.ctypes.data_as(u16p), k.ctypes.data_as(u16p), v.ctypes.data_as(u16p), heads, kvh, q_len, ctx,
                                          impl, out.ctypes.data_as(u16p), 0, ctypes.byref(ms))
         assert rc == 0, rc
+# persistent prefill GEMM, 1-CTA and cta_group::2 (two N tiles, ragged), both epilogues
+f32p, i32p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
+for epi in (0, 3):
+    w, x = bits((256, 128)), bits((300, 128))
+    outs = []
+    for mode in (-1, -2):
+        out = np.zeros((300, 128 if epi == 3 else 256), np.uint16)
+        rc = lib.acp_kernel_gemm(w.ctypes.data_as(u16p), x.ctypes.data_as(u16p), 256, 300, 128, 1, epi, mode,
+                                 out.ctypes.data_as(ctypes.c_void_p), None, None, 0, ctypes.byref(ms))
+        assert rc == 0, rc
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
 print("hooks ok", flush=True)

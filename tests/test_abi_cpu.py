@@ -45,8 +45,8 @@ def test_version_and_no_device_behaviour():
 
 def test_default_kernel_dispatch():
     """The kernel the GEMM dispatcher picks by default, with no environment switch set (host logic, no GPU):
-    prefill-sized problems must run the persistent kernel — an inverted default here silently costs ~13 % of the
-    bench (it happened once) — and the cta_group::2 flavour only on request."""
+    prefill-sized problems must run the persistent kernel, in its cta_group::2 flavour when the weight rows pair
+    up — an inverted default here silently costs 7-13 % of the bench (it happened once)."""
     import subprocess, sys
     code = (
         "import os\n"
@@ -58,7 +58,7 @@ def test_default_kernel_dispatch():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0, out.stderr
     #          gate/up  down  decode  N=256  fp32 planes  2-CTA  odd m-tiles  1-CTA  forced tile
-    assert out.stdout.split() == ["1", "1", "0", "0", "0", "2", "1", "1", "0"], out.stdout
+    assert out.stdout.split() == ["2", "2", "0", "0", "0", "2", "1", "1", "0"], out.stdout
 
 
 def test_product_never_imports_the_oracle():
