@@ -193,11 +193,12 @@ static int launch_persistent2(const GemmLaunch& g, cudaStream_t stream) {
 }
 
 // Which kernel gemm_launch picks (pure host logic: tests/test_abi_cpu.py pins the defaults without a GPU):
-// prefill-sized problems (N > 256, bf16 or fused-SwiGLU output, not grouped) run the persistent kernel with
+// prefill-sized problems (N > 256; bf16, fused-SwiGLU or ONE fp32 plane out; not grouped) run the persistent kernel with
 // double-buffered TMEM accumulators — the cta_group::2 flavour whenever the weight rows pair up (M % 256 == 0:
 // every matrix of the served models), the 1-CTA flavour otherwise.
 int gemm_path(const GemmLaunch& g) {
-  if (g.N > 256 && g.bn_override == 0 && g.groups == 0 && persistent_enabled() && (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU)) {
+  if (g.N > 256 && g.bn_override == 0 && g.groups == 0 && persistent_enabled() &&
+      (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU || (g.epi == EPI_F32 && g.splits == 1))) {
     const bool want2 = g.two_cta < 0 ? two_cta_enabled() : g.two_cta == 1;
     if (want2 && g.M % (2 * GEMM_BM) == 0) return GEMM_PATH_PERSISTENT_2CTA;
     return GEMM_PATH_PERSISTENT;
@@ -228,8 +229,12 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   if (g.epi != EPI_F32 && g.splits != 1) return -1;
   if (g.groups > 0 && (g.splits != 1 || g.group_ranges == nullptr || (g.epi != EPI_BF16 && g.epi != EPI_SWIGLU))) return -1;
   switch (gemm_path(g)) {
-    case GEMM_PATH_PERSISTENT: return g.epi == EPI_BF16 ? launch_persistent<EPI_BF16>(g, stream) : launch_persistent<EPI_SWIGLU>(g, stream);
-    case GEMM_PATH_PERSISTENT_2CTA: return g.epi == EPI_BF16 ? launch_persistent2<EPI_BF16>(g, stream) : launch_persistent2<EPI_SWIGLU>(g, stream);
+    case GEMM_PATH_PERSISTENT:
+      return g.epi == EPI_BF16 ? launch_persistent<EPI_BF16>(g, stream)
+             : g.epi == EPI_F32 ? launch_persistent<EPI_F32>(g, stream) : launch_persistent<EPI_SWIGLU>(g, stream);
+    case GEMM_PATH_PERSISTENT_2CTA:
+      return g.epi == EPI_BF16 ? launch_persistent2<EPI_BF16>(g, stream)
+             : g.epi == EPI_F32 ? launch_persistent2<EPI_F32>(g, stream) : launch_persistent2<EPI_SWIGLU>(g, stream);
     default: break;
   }
   const int bn = g.bn_override ? g.bn_override : gemm_pick_bn(g.N);
@@ -262,7 +267,9 @@ static int set_attr_bn() {
 int gemm_setup_attributes() {
   int rc = set_attr_bn<16>() | set_attr_bn<32>() | set_attr_bn<64>() | set_attr_bn<128>() |
            set_attr_bn<256>();
-  if (cudaFuncSetAttribute(gemm_wx_persistent2_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM) != cudaSuccess ||
+  if (cudaFuncSetAttribute(gemm_wx_persistent2_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_wx_persistent2_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(gemm_wx_persistent2_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(gemm_wx_persistent_kernel<EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGEMM_SMEM) != cudaSuccess)

@@ -133,6 +133,13 @@ gemm_wx_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w, const __gr
             if (n < n_valid && m < args.M)
               out[(size_t)n * args.ld + m] = __float2bfloat16_rn(__uint_as_float(r[j]));
           }
+        } else if constexpr (EPI == EPI_F32) {   // one fp32 plane (row-parallel shards: rounded once AFTER the exchange)
+          float* outf = (float*)args.out;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c + j;
+            if (n < n_valid && m < args.M) outf[(size_t)n * args.ld + m] = __uint_as_float(r[j]);
+          }
         } else {  // EPI_SWIGLU
           swiglu_store16(out, r, n0 + c, n_valid, m, args.M, args.ld, lane);
         }
@@ -320,6 +327,13 @@ gemm_wx_persistent2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
             const int n = n0 + c + j;
             if (n < n_valid && m < args.M)
               out[(size_t)n * args.ld + m] = __float2bfloat16_rn(__uint_as_float(r[j]));
+          }
+        } else if constexpr (EPI == EPI_F32) {   // one fp32 plane (row-parallel shards: rounded once AFTER the exchange)
+          float* outf = (float*)args.out;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c + j;
+            if (n < n_valid && m < args.M) outf[(size_t)n * args.ld + m] = __uint_as_float(r[j]);
           }
         } else {  // EPI_SWIGLU
           swiglu_store16(out, r, n0 + c, n_valid, m, args.M, args.ld, lane);

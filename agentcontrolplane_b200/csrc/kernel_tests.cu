@@ -29,9 +29,9 @@ extern "C" int acp_kernel_device_count(void) {
   return n;
 }
 
-extern "C" int acp_kernel_gemm_path(int M, int N, int K, int epi, int bn) {
+extern "C" int acp_kernel_gemm_path(int M, int N, int K, int splits, int epi, int bn) {
   GemmLaunch g;
-  g.M = M; g.N = N; g.K = K; g.epi = epi; g.splits = 1;
+  g.M = M; g.N = N; g.K = K; g.epi = epi; g.splits = splits;
   g.bn_override = bn > 0 ? bn : 0;
   g.two_cta = bn == -2 ? 1 : (bn == -1 ? 0 : -1);
   return gemm_path(g);

@@ -53,12 +53,13 @@ def test_default_kernel_dispatch():
         "for k in ('ACP_GEMM_PERSISTENT', 'ACP_GEMM_2CTA'): os.environ.pop(k, None)\n"
         "from agentcontrolplane_b200 import _lib\n"
         "p = _lib.load().acp_kernel_gemm_path\n"
-        "print(p(28672, 4096, 4096, 3, 0), p(4096, 8192, 14336, 0, 0), p(4096, 64, 4096, 0, 0), p(4096, 256, 4096, 0, 0),\n"
-        "      p(4096, 512, 4096, 1, 0), p(4096, 4096, 4096, 0, -2), p(4224, 4096, 4096, 0, -2), p(4096, 4096, 4096, 0, -1), p(4096, 4096, 4096, 0, 256))\n")
+        "print(p(28672, 4096, 4096, 1, 3, 0), p(4096, 8192, 14336, 1, 0, 0), p(4096, 64, 4096, 1, 0, 0), p(4096, 256, 4096, 1, 0, 0),\n"
+        "      p(4096, 512, 4096, 2, 1, 0), p(8192, 4096, 1024, 1, 1, 0), p(4096, 4096, 4096, 1, 0, -2), p(4224, 4096, 4096, 1, 0, -2),\n"
+        "      p(4096, 4096, 4096, 1, 0, -1), p(4096, 4096, 4096, 1, 0, 256))\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0, out.stderr
-    #          gate/up  down  decode  N=256  fp32 planes  2-CTA  odd m-tiles  1-CTA  forced tile
-    assert out.stdout.split() == ["2", "2", "0", "0", "0", "2", "1", "1", "0"], out.stdout
+    #          gate/up  down  decode  N=256  2 fp32 planes  1 fp32 plane (TP prefill)  2-CTA  odd m-tiles  1-CTA  forced tile
+    assert out.stdout.split() == ["2", "2", "0", "0", "0", "2", "2", "1", "1", "0"], out.stdout
 
 
 def test_product_never_imports_the_oracle():

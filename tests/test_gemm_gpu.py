@@ -164,3 +164,18 @@ def test_gemm_two_cta_repeatable():
     for _ in range(3):
         b, _, _, _ = _gemm(w, x, epi=0, bn=-2)
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(8192, 4096, 1024, 0), (8192, 4096, 1024, -1), (1024, 700, 3584, 0), (384, 1000, 256, 0)])
+def test_gemm_persistent_fp32_plane_matches_tiled_kernel(M, N, K, mode):
+    """epi 1 with ONE plane and more than 256 rows (the row-parallel O / down projections of a tensor-parallel
+    prefill step) runs on the persistent kernels; the tiled kernel (bn = 256 forces it) is the reference: same
+    accumulation order, so the fp32 planes must be bit-identical."""
+    rng = np.random.default_rng(M + N + K)
+    w = _rand_bits(rng, (M, K), 0.05)
+    x = _rand_bits(rng, (N, K), 1.0)
+    tiled, _, _, _ = _gemm(w, x, splits=1, epi=1, bn=256)
+    pers, _, _, _ = _gemm(w, x, splits=1, epi=1, bn=mode)
+    assert np.array_equal(tiled, pers), int(np.count_nonzero(tiled != pers))
+    ref = bits_to_f32(x) @ bits_to_f32(w).T
+    assert np.allclose(pers[0], ref, rtol=2e-4, atol=2e-4)
