@@ -104,7 +104,7 @@ int gemm_pick_bn(int N) {
 // ACP_GEMM_SHALLOW=0: wide tiles keep the deep ring / one CTA per SM (A/B switch)
 static bool shallow_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("ACP_GEMM_SHALLOW"); v = (e && *e == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("ACP_GEMM_SHALLOW"); v = (e && *e == '0') ? 0 : 1; }
   return v == 1;
 }
 
@@ -203,7 +203,8 @@ int gemm_path(const GemmLaunch& g) {
     if (want2 && g.M % (2 * GEMM_BM) == 0) return GEMM_PATH_PERSISTENT_2CTA;
     return GEMM_PATH_PERSISTENT;
   }
-  return GEMM_PATH_TILED;
+  const int bn = g.bn_override ? g.bn_override : gemm_pick_bn(g.N);
+  return (bn >= 128 && shallow_enabled()) ? GEMM_PATH_TILED_SHALLOW : GEMM_PATH_TILED;
 }
 
 template <int EPI>

@@ -46,7 +46,7 @@ struct GemmLaunch {
 };
 int gemm_pick_bn(int N);
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
-enum { GEMM_PATH_TILED = 0, GEMM_PATH_PERSISTENT = 1, GEMM_PATH_PERSISTENT_2CTA = 2 };
+enum { GEMM_PATH_TILED = 0, GEMM_PATH_PERSISTENT = 1, GEMM_PATH_PERSISTENT_2CTA = 2, GEMM_PATH_TILED_SHALLOW = 3 };
 int gemm_path(const GemmLaunch& g);   // the kernel gemm_launch would pick for this problem
 int gemm_setup_attributes();  // cudaFuncSetAttribute for every instantiation (once per device)
 

@@ -24,7 +24,8 @@ extern "C" {
  * iters > 0 additionally times `iters` launches with CUDA events (L2 flushed between
  * launches) and stores the mean milliseconds in *elapsed_ms. */
 /* Which kernel the dispatcher picks for this problem (host logic only, no GPU needed): 0 = tiled
- * gemm_wx_kernel, 1 = persistent kernel (TMEM double-buffered), 2 = its cta_group::2 flavour.  `splits`, `epi`
+ * gemm_wx_kernel (3 = its shallow-ring flavour, two CTAs per SM, for 128 / 256-row tiles), 1 = persistent kernel
+ * (TMEM double-buffered), 2 = its cta_group::2 flavour.  `splits`, `epi`
  * and `bn` as below. */
 int acp_kernel_gemm_path(int M, int N, int K, int splits, int epi, int bn);
 

@@ -50,7 +50,7 @@ def test_default_kernel_dispatch():
     import subprocess, sys
     code = (
         "import os\n"
-        "for k in ('ACP_GEMM_PERSISTENT', 'ACP_GEMM_2CTA'): os.environ.pop(k, None)\n"
+        "for k in ('ACP_GEMM_PERSISTENT', 'ACP_GEMM_2CTA', 'ACP_GEMM_SHALLOW'): os.environ.pop(k, None)\n"
         "from agentcontrolplane_b200 import _lib\n"
         "p = _lib.load().acp_kernel_gemm_path\n"
         "print(p(28672, 4096, 4096, 1, 3, 0), p(4096, 8192, 14336, 1, 0, 0), p(4096, 64, 4096, 1, 0, 0), p(4096, 256, 4096, 1, 0, 0),\n"
@@ -59,7 +59,7 @@ def test_default_kernel_dispatch():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0, out.stderr
     #          gate/up  down  decode  N=256  2 fp32 planes  1 fp32 plane (TP prefill)  2-CTA  odd m-tiles  1-CTA  forced tile
-    assert out.stdout.split() == ["2", "2", "0", "0", "0", "2", "2", "1", "1", "0"], out.stdout
+    assert out.stdout.split() == ["2", "2", "0", "3", "3", "2", "2", "1", "1", "3"], out.stdout
 
 
 def test_product_never_imports_the_oracle():
