@@ -77,7 +77,7 @@ def test_unusable_checkpoints_are_rejected_with_a_reason(tmp_path, breakage, nee
         with pytest.raises(ValueError, match=needle):
             host.checkpoint_index(d)
         return
-    extra = {"head_dim": {"head_dim": 64}, "vocab": {"vocab_size": 1000}, "model_type": {"model_type": "mixtral"}}.get(breakage, {})
+    extra = {"head_dim": {"head_dim": 64}, "vocab": {"vocab_size": 1000}, "model_type": {"model_type": "gpt_neox"}}.get(breakage, {})
     write_checkpoint(d, CFG, SEED, **extra)
     if breakage == "no_config":
         os.remove(os.path.join(d, "config.json"))
