@@ -135,15 +135,26 @@ ACP_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure),
-// never as a hung GPU.  ~2^28 polls of a HW-sleeping try_wait is many seconds.
+ACP_DEVINL uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a
+// hung GPU.  The bound is wall time (8 s; the cross-GPU waits of tp_comm.cu allow 40 s, so a kernel stuck on
+// ONE GPU names itself here before its peers give up on it): block, thread (= role) and barrier are printed.
 ACP_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) {
-      printf("[acp_infer] mbarrier wait timeout block=(%d,%d,%d) thread=%d\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
+    if ((++spins & 0xFFFu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ull) {
+        printf("[acp_infer] mbarrier wait timeout block=(%d,%d,%d) thread=%d bar=0x%x parity=%u\n", blockIdx.x,
+               blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }

@@ -104,6 +104,25 @@ extern "C" int acp_kernel_gemm(const uint16_t* w, const uint16_t* x, int M, int 
       amax_idx[n] = bi;
     }
   }
+  if (iters < 0 && elapsed_ms != nullptr) {
+    // STRESS mode: -iters back-to-back launches (programmatic dependent launch on, no L2 flush, one sync at the
+    // end) — what a rare pipeline deadlock needs to show up; a hang ends in the kernels' own bounded waits
+    cudaEvent_t e0, e1;
+    ACP_CUDA_CHECK(cudaEventCreate(&e0));
+    ACP_CUDA_CHECK(cudaEventCreate(&e1));
+    ACP_CUDA_CHECK(cudaEventRecord(e0, 0));
+    for (int it = 0; it < -iters; ++it) {
+      rc = gemm_launch(g, 0);
+      if (rc != 0) return rc;
+    }
+    ACP_CUDA_CHECK(cudaEventRecord(e1, 0));
+    ACP_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    ACP_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *elapsed_ms = ms / (float)(-iters);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   if (iters > 0 && elapsed_ms != nullptr) {
     const size_t flush_n = (size_t)64 << 20;  // 256 MiB of fp32 > 126 MB L2
     if (dflush.alloc(flush_n * 4)) return -5;

@@ -22,10 +22,15 @@ ACP_DEVINL void tp_signal(const TpPeers& P, int lane, int epoch) {  // lanes 0..
 ACP_DEVINL void tp_wait_all(const TpPeers& P, int lane, int epoch) {  // lanes 0..size-1 of one warp
   if (lane < P.size) {
     unsigned spins = 0;
+    uint64_t t0 = 0;
     while (ld_acquire_sys(P.flags[P.rank] + lane) < epoch) {
-      if (++spins > (1u << 27)) {
-        printf("[acp_infer] tp wait timeout rank=%d waiting for %d epoch=%d\n", P.rank, lane, epoch);
-        __trap();
+      if ((++spins & 0x3FFu) == 0) {   // wall-time bound (40 s): a stuck peer traps its own kernel first (8 s, common.cuh)
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 40000000000ull) {
+          printf("[acp_infer] tp wait timeout rank=%d waiting for %d epoch=%d\n", P.rank, lane, epoch);
+          __trap();
+        }
       }
     }
   }

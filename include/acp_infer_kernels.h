@@ -22,7 +22,8 @@ extern "C" {
  * [N][M/2] = bf16(bf16(silu(g)) * u).  bn = 0 picks the N tile from N; otherwise 16..256;
  * bn = -1 / -2 (N > 256, epi 0 or 3) force the 1-CTA / the cta_group::2 persistent prefill kernel.
  * iters > 0 additionally times `iters` launches with CUDA events (L2 flushed between
- * launches) and stores the mean milliseconds in *elapsed_ms. */
+ * launches) and stores the mean milliseconds in *elapsed_ms; iters < 0 is a stress mode: -iters launches back
+ * to back (no flush, one synchronize at the end), mean milliseconds in *elapsed_ms. */
 /* Which kernel the dispatcher picks for this problem (host logic only, no GPU needed): 0 = tiled
  * gemm_wx_kernel (3 = its shallow-ring flavour, two CTAs per SM, for 128 / 256-row tiles), 1 = persistent kernel
  * (TMEM double-buffered), 2 = its cta_group::2 flavour.  `splits`, `epi`
