@@ -196,10 +196,19 @@ static int launch_persistent2(const GemmLaunch& g, cudaStream_t stream) {
 // prefill-sized problems (N > 256; bf16, fused-SwiGLU or ONE fp32 plane out; not grouped) run the persistent kernel with
 // double-buffered TMEM accumulators — the cta_group::2 flavour whenever the weight rows pair up (M % 256 == 0:
 // every matrix of the served models), the 1-CTA flavour otherwise.
+// Tensor-parallel shards: the 70B TP=8 and Mixtral EP=8 runs with the cta_group::2 kernel + the persistent fp32-plane
+// epilogue ended in a stuck rank after ~2e4 exchanges (profiles/r2_call13_8gpu.md) while 1e6 single-GPU launches
+// and the TP=4/8 tests are clean; until that is understood a shard keeps the kernels of the validated 8-GPU runs.
+static bool tp_env(const char* name) {
+  const char* e = getenv(name);
+  return e && *e == '1';
+}
 int gemm_path(const GemmLaunch& g) {
+  static const bool tp_2cta = tp_env("ACP_TP_GEMM_2CTA"), tp_f32 = tp_env("ACP_TP_GEMM_PERSISTENT_F32");
+  const bool f32_ok = g.epi == EPI_F32 && g.splits == 1 && (!g.tp_shard || tp_f32);
   if (g.N > 256 && g.bn_override == 0 && g.groups == 0 && persistent_enabled() &&
-      (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU || (g.epi == EPI_F32 && g.splits == 1))) {
-    const bool want2 = g.two_cta < 0 ? two_cta_enabled() : g.two_cta == 1;
+      (g.epi == EPI_BF16 || g.epi == EPI_SWIGLU || f32_ok)) {
+    const bool want2 = g.two_cta >= 0 ? g.two_cta == 1 : (two_cta_enabled() && (!g.tp_shard || tp_2cta));
     if (want2 && g.M % (2 * GEMM_BM) == 0) return GEMM_PATH_PERSISTENT_2CTA;
     return GEMM_PATH_PERSISTENT;
   }

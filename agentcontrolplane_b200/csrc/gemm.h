@@ -36,6 +36,10 @@ struct GemmLaunch {
   int* amax_idx = nullptr;
   const int* n_dev = nullptr;
   int bn_override = 0;  // 0 = pick from N
+  // a tensor-parallel shard's GEMM: keeps the kernels the 8-GPU runs were validated with (1-CTA persistent kernel,
+  // tiled kernel for the fp32 plane of the row-parallel projections) unless ACP_TP_GEMM_2CTA=1 /
+  // ACP_TP_GEMM_PERSISTENT_F32=1 — see gemm.cu gemm_path
+  bool tp_shard = false;
   int two_cta = -1;     // prefill (N > 256) GEMMs: -1 = policy (gemm.cu two_cta_enabled), 0 = 1-CTA persistent kernel, 1 = cta_group::2 kernel
   // grouped mode (mixture of experts): `groups` weight tensors of M rows each, concatenated in `w`;
   // group g works on rows [ranges[2g], ranges[2g] + ranges[2g+1]) of x / out (device array, layout of

@@ -563,6 +563,7 @@ StepInput& Model::stage_begin(int T, int B, int n_blocks) {
 
 int Model::gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool decode, GemmOut* out) {
   GemmLaunch g;
+  g.tp_shard = tp_size_ > 1;
   g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
   const int splits = choose_splits(M, K, N);
   if (decode && splits > 1) {  // a single split writes bf16 directly (same rounding, half the bytes)
@@ -581,6 +582,7 @@ int Model::gemm(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool de
 // split-K reduce, NCCL all-reduce (sum) across the group over NVLink, consumer rounds to bf16 ONCE.
 int Model::gemm_rowpar(const TmaMaps& w, const TmaMaps& x, int M, int K, int N, bool decode, GemmOut* out) {
   GemmLaunch g;
+  g.tp_shard = tp_size_ > 1;
   g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
   const int splits = decode ? choose_splits(M, K, N) : 1;
   g.epi = EPI_F32; g.splits = splits; g.out = ws_; g.ld = M; g.n_cap = N;
@@ -610,6 +612,7 @@ int Model::rowpar_fused(const TmaMaps& w, const TmaMaps& x, int K, int N, bool d
                         bool push_x) {
   const int M = cfg_.hidden;
   GemmLaunch g;
+  g.tp_shard = tp_size_ > 1;
   g.w = &w.w; g.x = &x; g.M = M; g.N = N; g.K = K;
   const int splits = decode ? choose_splits(M, K, N) : 1;
   g.epi = EPI_F32; g.splits = splits; g.ld = M; g.n_cap = N;
@@ -749,6 +752,7 @@ int Model::forward(const StepInput& in) {
       // SwiGLU in the GEMM epilogue.  Decode (non-persistent kernel, epilogue exposed at the end of
       // every CTA) measured no gain, so it stays a separate kernel there unless ACP_FUSE_SWIGLU=1.
       GemmLaunch g;
+      g.tp_shard = tp_size_ > 1;
       g.w = &L.m_gu.w; g.x = &m_xn_; g.M = 2 * ffn_l_; g.N = T; g.K = c.hidden; g.splits = 1;
       g.epi = EPI_SWIGLU; g.out = h_; g.ld = ffn_l_; g.n_cap = T;
       PROF("gemm_gateup_swiglu", gemm_launch(g, stream_));
@@ -783,6 +787,7 @@ int Model::forward(const StepInput& in) {
   if (in.n_sample > 0) {
     const int m_tiles = (lm_rows_l_ + GEMM_BM - 1) / GEMM_BM;
     GemmLaunch g;
+    g.tp_shard = tp_size_ > 1;
     g.w = &m_lm_.w; g.x = &m_xs_; g.M = lm_rows_l_; g.N = in.n_sample; g.K = c.hidden; g.splits = 1;
     g.epi = EPI_ARGMAX; g.ld = lm_rows_per_rank_; g.n_cap = in.n_sample;   // == lm_rows_l_ when tp == 1
     const bool logits = in.want_logits || !in.all_greedy;
@@ -849,6 +854,7 @@ int Model::moe_mlp(Layer& L, int T, const __nv_bfloat16* gain, bool last_layer) 
   PROF("moe_dispatch", launch_moe_dispatch(moe_topk_idx_, T, expert0_, experts_l_, bn, moe_ranges_, moe_row_of_, stream_));
   PROF("moe_gather", launch_moe_gather(xn_, moe_row_of_, c.hidden, T, xe_, stream_));
   GemmLaunch g;
+  g.tp_shard = tp_size_ > 1;
   g.groups = experts_l_; g.group_ranges = moe_ranges_; g.splits = 1;
   g.bn_override = bn;
   g.N = moe_tile_cap(T, bn, experts_l_) * bn;   // grid.x = capacity of the device-side tile list

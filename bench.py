@@ -390,7 +390,12 @@ def main():
                        "roofline_prefill_frac_per_gpu": j["roofline_prefill"]["frac"], "gpu_launches": j["gpu_launches"],
                        "llm_steps_per_task": j["config"]["llm_steps_per_task"], "prefix_tokens_reused": j["config"]["prefix_tokens_reused"]}
             except Exception as e:  # noqa: BLE001
-                tp8 = {"unavailable": f"{type(e).__name__}: {e}"[:400]}
+                tail = ""
+                try:   # what the subprocess said last (device-side printf of a bounded wait lands on stdout)
+                    tail = " | stdout: " + " / ".join(out.stdout.strip().splitlines()[-2:])[-300:] + " | stderr: " + " / ".join(out.stderr.strip().splitlines()[-3:])[-400:]
+                except Exception:  # noqa: BLE001
+                    pass
+                tp8 = {"unavailable": (f"{type(e).__name__}: {e}"[:200] + tail)[:1000]}
             store.set("acp_bench_tp8_done", "1")
         else:
             import datetime
