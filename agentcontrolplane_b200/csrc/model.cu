@@ -214,6 +214,8 @@ int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int 
   // Prefill: SwiGLU runs in the persistent gate/up GEMM's epilogue (paired-lane exchange, hidden
   // behind the next tile's mainloop by the double-buffered TMEM accumulator): A/B on one box
   // 471 -> 450 ms per 32768 prompt tokens.  ACP_FUSE_SWIGLU_PREFILL=0 restores the separate kernel.
+  env = getenv("ACP_TP_SYNC_EVERY");
+  tp_sync_every_ = (env && tp_size > 1) ? atoi(env) : 0;
   env = getenv("ACP_FUSE_SWIGLU_PREFILL");
   fuse_swiglu_prefill_ = !(env && *env == '0');
   ACP_CUDA_CHECK(cudaSetDevice(device));
@@ -693,6 +695,8 @@ int Model::forward(const StepInput& in) {
   for (int l = 0; l < c.layers; ++l) {
     Layer& L = layers_[l];
     GemmOut qkv, o, dn;
+    // investigation knob (profiles/r2_call13_8gpu.md, hypothesis 1): bound this shard's launch queue
+    if (tp_sync_every_ > 0 && l > 0 && l % tp_sync_every_ == 0) ACP_CUDA_CHECK(cudaStreamSynchronize(stream_));
     PROF("gemm_qkv", gemm(L.m_qkv, m_xn_, qkv_l_, c.hidden, T, in.decode, &qkv));
     if (!in.decode) {
       RopeKvArgs ra;

@@ -103,6 +103,7 @@ class Model {
   cudaStream_t stream_ = nullptr;
   long long launches_ = 0, h2d_bytes_ = 0, d2h_bytes_ = 0;
   bool fuse_swiglu_ = false, fuse_swiglu_prefill_ = false;
+  int tp_sync_every_ = 0;   // ACP_TP_SYNC_EVERY=n (tensor-parallel engines only): stream synchronize every n layers
   // tensor parallel
   int tp_rank_ = 0, tp_size_ = 1;
   NcclComm comm_ = nullptr;
