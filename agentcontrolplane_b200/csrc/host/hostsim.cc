@@ -524,6 +524,13 @@ static std::string synth_text(uint64_t seed, int task, int n) {
   return s;
 }
 
+extern "C" int acp_host_splitk_factor(int M, int K, int N, int target_ctas, int strict) {
+  return acp::splitk_factor(M, K, N, target_ctas, strict != 0);
+}
+extern "C" size_t acp_host_splitk_workspace_bytes(int M, int K, int max_batch, int target_ctas, int strict) {
+  return acp::splitk_workspace_bytes(M, K, max_batch, target_ctas, strict != 0);
+}
+
 extern "C" int acp_host_checkpoint_index(const char* path, char** out_json) {
   if (!path || !out_json) return ACP_ERR_INVALID;
   acp::Checkpoint ck;

@@ -134,37 +134,7 @@ static int dmalloc_t(std::vector<void*>& allocs, T** p, size_t count, bool zero 
 //   more than 256 sums its K range in different pieces than inside a smaller batch
 //   ("strict_batch_invariance": true keeps the one-tile splits everywhere).
 int Model::choose_splits(int M, int K, int N) const {
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  const int nkb = (K + GEMM_BK - 1) / GEMM_BK;
-  const int max_s = nkb / 4 > 0 ? nkb / 4 : 1;  // at least 4 k-blocks per split
-  int s;
-  if (N > 256 && !lim_.strict_batch_invariance) {
-    // co-resident CTAs share an SM's tensor pipe, so the GEMM's time follows the busiest SM: minimise
-    // ceil(tiles * S / 148) / S (waves of one CTA per SM, each doing 1/S of K); ties -> fewer planes
-    const int tiles = m_tiles * ((N + 255) / 256);
-    s = 1;
-    // (>= one tile per SM already: no split — the persistent kernel balances those itself, bf16 epilogue)
-    if (tiles < 148) {
-      const int cap = max_s < 8 ? max_s : 8;
-      double best = 1e30;
-      for (int cand = 1; cand <= cap; ++cand) {
-        const double cost = (double)((tiles * cand + 147) / 148) / cand;
-        if (cost < best) best = cost;
-      }
-      // every extra plane is N x M fp32 written and re-read: take the FEWEST planes within 15 % of the best
-      // wave count (128 tiles: 1 plane at cost 1.0, not 8 planes at 0.875; 64 tiles: 2; 96 tiles: 3)
-      for (int cand = 1; cand <= cap; ++cand) {
-        const double cost = (double)((tiles * cand + 147) / 148) / cand;
-        if (cost <= best * 1.15 + 1e-9) { s = cand; break; }
-      }
-    }
-  } else {
-    s = (lim_.splitk_target_ctas + m_tiles / 2) / m_tiles;
-  }
-  if (s < 1) s = 1;
-  if (s > max_s) s = max_s;
-  if (s > 16) s = 16;
-  return s;
+  return splitk_factor(M, K, N, lim_.splitk_target_ctas, lim_.strict_batch_invariance);   // model_config.cc
 }
 
 int Model::init(const ModelConfig& cfg, const ModelLimits& lim, int device, int tp_rank, int tp_size,
@@ -307,12 +277,9 @@ int Model::alloc_all() {
   const int shapes[4][2] = {{qkv_l_, c.hidden}, {c.hidden, qdim_l_}, {2 * ffn_l_, c.hidden}, {c.hidden, ffn_l_}};
   for (auto& s : shapes) {
     if (c.experts > 0 && (&s - shapes) >= 2) continue;   // the expert GEMMs are grouped, never split-K
-    // the split factor depends on the row count beyond 256 rows (choose_splits): size for every step height
-    for (int n = 256; n < lim_.max_batch + 256; n += 256) {
-      const int rows = n < lim_.max_batch ? n : lim_.max_batch;
-      const size_t b = (size_t)choose_splits(s[0], s[1], rows) * rows * s[0] * sizeof(float);
-      if (b > ws) ws = b;
-    }
+    // the split factor depends on the row count beyond 256 rows: sized over every step height (model_config.cc)
+    const size_t b = splitk_workspace_bytes(s[0], s[1], lim_.max_batch, lim_.splitk_target_ctas, lim_.strict_batch_invariance);
+    if (b > ws) ws = b;
   }
   if (tp_size_ > 1) {  // row-parallel GEMMs write fp32 (one rounding after the all-reduce), prefill too
     const size_t b = (size_t)T * H * sizeof(float);

@@ -97,4 +97,50 @@ bool model_config_from_hf(const Json& hf, ModelConfig* out, std::string* err) {
   return true;
 }
 
+int splitk_factor(int M, int K, int N, int target_ctas, bool strict) {
+  const int m_tiles = (M + 127) / 128;
+  const int nkb = (K + 63) / 64;
+  const int max_s = nkb / 4 > 0 ? nkb / 4 : 1;  // at least 4 k-blocks per split
+  int s;
+  if (N > 256 && !strict) {
+    // co-resident CTAs share an SM's tensor pipe, so the GEMM's time follows the busiest SM: minimise
+    // ceil(tiles * S / 148) / S (waves of one CTA per SM, each doing 1/S of K); ties -> fewer planes
+    const int tiles = m_tiles * ((N + 255) / 256);
+    s = 1;
+    // (>= one tile per SM already: no split — the persistent kernel balances those itself, bf16 epilogue)
+    if (tiles < 148) {
+      const int cap = max_s < 8 ? max_s : 8;
+      double best = 1e30;
+      for (int cand = 1; cand <= cap; ++cand) {
+        const double cost = (double)((tiles * cand + 147) / 148) / cand;
+        if (cost < best) best = cost;
+      }
+      // every extra plane is N x M fp32 written and re-read: take the FEWEST planes within 15 % of the best
+      // wave count (128 tiles: 1 plane at cost 1.0, not 8 planes at 0.875; 64 tiles: 2; 96 tiles: 3)
+      for (int cand = 1; cand <= cap; ++cand) {
+        const double cost = (double)((tiles * cand + 147) / 148) / cand;
+        if (cost <= best * 1.15 + 1e-9) { s = cand; break; }
+      }
+    }
+  } else {
+    s = (target_ctas + m_tiles / 2) / m_tiles;
+  }
+  if (s < 1) s = 1;
+  if (s > max_s) s = max_s;
+  if (s > 16) s = 16;
+  return s;
+}
+
+size_t splitk_workspace_bytes(int M, int K, int max_batch, int target_ctas, bool strict) {
+  // the factor depends on the row count beyond 256 rows, and only through ceil(rows / 256): the largest plane set
+  // of every 256-row band is at its top
+  size_t ws = 0;
+  for (int n = 256; n < max_batch + 256; n += 256) {
+    const int rows = n < max_batch ? n : max_batch;
+    const size_t b = (size_t)splitk_factor(M, K, rows, target_ctas, strict) * rows * M * sizeof(float);
+    if (b > ws) ws = b;
+  }
+  return ws;
+}
+
 }  // namespace acp

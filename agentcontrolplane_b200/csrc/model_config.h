@@ -55,4 +55,10 @@ bool model_config_from_hf(const Json& hf, ModelConfig* out, std::string* err);
 // inverse RoPE frequencies [64] as the engine and oracle/llama_oracle.py rope_tables() build them
 void rope_inv_freq(const ModelConfig& c, float* inv64);
 
+// Split-K factor of a decode GEMM out[N][M] = X[N][K] W[M][K]^T (pure host logic; the rule and its reasons are
+// written out at Model::choose_splits in model.cu).  target_ctas = ModelLimits::splitk_target_ctas.
+int splitk_factor(int M, int K, int N, int target_ctas, bool strict_batch_invariance);
+// fp32 split-K workspace that holds the planes of ANY decode step of up to max_batch rows of a [M][K] GEMM
+size_t splitk_workspace_bytes(int M, int K, int max_batch, int target_ctas, bool strict_batch_invariance);
+
 }  // namespace acp

@@ -94,6 +94,11 @@ int acp_host_render_prompt_with(const char* tokenizer_path, const char* chat_req
  *             "eps":…, "tied_embeddings":…, "rope_inv_freq":[64 floats]}}
  * or {"error": "..."} with return code ACP_ERR_INVALID. */
 int acp_host_checkpoint_index(const char* path, char** out_json);
+
+/* The engine's split-K rule for decode GEMMs (csrc/model_config.cc, pure host logic): the number of fp32 planes of
+ * out[N][M] = X[N][K] W[M][K]^T, and the workspace bytes that hold the planes of ANY step of up to max_batch rows. */
+int acp_host_splitk_factor(int M, int K, int N, int target_ctas, int strict_batch_invariance);
+size_t acp_host_splitk_workspace_bytes(int M, int K, int max_batch, int target_ctas, int strict_batch_invariance);
 /* One tensor of the checkpoint as the bf16 bits the loader uploads (BF16 verbatim; F16 / F32 rounded
  * to nearest even).  out == NULL: only *n_elems is set.  ACP_ERR_NOT_FOUND: no such tensor. */
 int acp_host_checkpoint_tensor_bf16(const char* path, const char* name, uint16_t* out, size_t max_elems,

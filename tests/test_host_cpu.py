@@ -475,3 +475,39 @@ def test_task_lease_follows_the_reference_rules():
     out = host.task_step({"op": "process", "task": _task(), "emulate_lease": False, "now": 1000.0, "podName": "pod-a",
                           "objects": cluster + _objs(("Lease", lease("pod-b", 999.0)))})
     assert "unsupported provider: cohere" in out["task"]["status"]["error"]
+
+
+def test_splitk_rule_and_workspace():
+    """The engine's split-K rule (csrc/model_config.cc, pure host logic).  (1) Steps of <= 256 rows: the factor is a
+    function of (M, K) only — batch invariance.  (2) Steps of more than 256 rows: the fewest fp32 planes whose wave
+    count is within 15 % of the best (64 tiles -> 2, 96 -> 3, 128 -> 1), none once every SM has a tile.  (3) The
+    workspace holds the planes of EVERY step height up to max_batch — a B = 1024 Mixtral step (O-proj: 128 tiles,
+    formerly 8 planes against a workspace sized for 7 x 1024 rows) once overflowed it and stopped the engine."""
+    import ctypes
+    from agentcontrolplane_b200 import _lib
+    lib = _lib.load_host()
+    f = lib.acp_host_splitk_factor
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int] * 5
+    w = lib.acp_host_splitk_workspace_bytes
+    w.restype = ctypes.c_size_t
+    w.argtypes = [ctypes.c_int] * 5
+    shapes = {"qkv": (6144, 4096), "o": (4096, 4096), "gate_up": (28672, 4096), "down": (4096, 14336),
+              "70b_o_shard": (8192, 1024), "mixtral_qkv_shard": (768, 4096), "mixtral_o_shard": (4096, 512)}
+    for name, (M, K) in shapes.items():
+        small = {f(M, K, n, 222, 0) for n in (1, 7, 64, 200, 256)}
+        assert len(small) == 1, (name, small)                      # (1)
+        assert {f(M, K, n, 222, 1) for n in (300, 512, 1024)} == small, name   # strict mode keeps them everywhere
+    assert (f(6144, 4096, 64, 222, 0), f(4096, 4096, 64, 222, 0), f(28672, 4096, 64, 222, 0), f(4096, 14336, 64, 222, 0)) == (5, 7, 1, 7)
+    # (2) B = 512 at Llama-3-8B (config 2): 96 / 64 / 448 / 64 tiles
+    assert (f(6144, 4096, 512, 222, 0), f(4096, 4096, 512, 222, 0), f(28672, 4096, 512, 222, 0), f(4096, 14336, 512, 222, 0)) == (3, 2, 1, 2)
+    assert f(4096, 4096, 1024, 222, 0) == 1                        # 128 tiles: one plane, not eight
+    assert f(4096, 4096, 2048, 222, 0) == 1                        # >= 148 tiles: never split
+    # (3) every step height fits the workspace, for every shape and both modes
+    for name, (M, K) in shapes.items():
+        for strict in (0, 1):
+            for max_batch in (64, 256, 512, 1000, 1024, 2048):
+                ws = w(M, K, max_batch, 222, strict)
+                for n in range(1, max_batch + 1, 7):
+                    assert f(M, K, n, 222, strict) * n * M * 4 <= ws, (name, strict, max_batch, n)
+                assert f(M, K, max_batch, 222, strict) * max_batch * M * 4 <= ws
