@@ -141,8 +141,10 @@ ACP_DEVINL uint64_t global_timer_ns() {
   return t;
 }
 // Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a
-// hung GPU.  The bound is wall time (8 s; the cross-GPU waits of tp_comm.cu allow 40 s, so a kernel stuck on
-// ONE GPU names itself here before its peers give up on it): block, thread (= role) and barrier are printed.
+// hung GPU.  The bound is wall time: 20 s — far above any legitimate wait (a GEMM's MMA thread sits here while its
+// producer waits for the previous kernel, which on a tensor-parallel shard can be an exchange waiting for a peer
+// that is still loading its kernels on the first step) and below the 40 s of the cross-GPU waits in tp_comm.cu,
+// so a kernel stuck on ONE GPU names itself before its peers give up on it: block, thread (= role), barrier.
 ACP_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
@@ -150,7 +152,7 @@ ACP_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 0xFFFu) == 0) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 8000000000ull) {
+      else if (now - t0 > 20000000000ull) {
         printf("[acp_infer] mbarrier wait timeout block=(%d,%d,%d) thread=%d bar=0x%x parity=%u\n", blockIdx.x,
                blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
         __trap();

@@ -24,7 +24,7 @@ ACP_DEVINL void tp_wait_all(const TpPeers& P, int lane, int epoch) {  // lanes 0
     unsigned spins = 0;
     uint64_t t0 = 0;
     while (ld_acquire_sys(P.flags[P.rank] + lane) < epoch) {
-      if ((++spins & 0x3FFu) == 0) {   // wall-time bound (40 s): a stuck peer traps its own kernel first (8 s, common.cuh)
+      if ((++spins & 0x3FFu) == 0) {   // wall-time bound (40 s): a stuck peer traps its own kernel first (20 s, common.cuh)
         const uint64_t now = global_timer_ns();
         if (t0 == 0) t0 = now;
         else if (now - t0 > 40000000000ull) {
